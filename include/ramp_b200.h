@@ -1,0 +1,214 @@
+/*
+ * ramp_b200 -- C ABI of the B200-native RAMP cluster simulator hot path.
+ *
+ * The reference (cwfparsonson/ddls @ 9e0b5ba) is pure Python and has no FFI; the interface this
+ * library sits behind is the Python class surface of
+ *   ddls/environments/ramp_cluster/ramp_cluster_environment.py  ("RCE")
+ *     RampClusterEnvironment.__init__  RCE:75-83    -> ramp_engine_create
+ *     RampClusterEnvironment.reset     RCE:202-295  -> ramp_reset
+ *     RampClusterEnvironment.step      RCE:894-1179 -> ramp_step_host / ramp_step_device
+ *       _place_ops/_schedule_ops/_place_deps/_schedule_deps RCE:1305-1415 -> ramp_register_template (+ per-step mount rows)
+ *       _perform_lookahead_job_completion_time + memo dicts RCE:469-518, RCE:269-275 -> memo hash table inside the step
+ *       _run_lookahead                  RCE:379-467  -> ramp_lookahead_kernel (also callable alone: ramp_run_lookaheads)
+ *       _register_completed_lookahead   RCE:793-888  -> ramp_register_kernel
+ *       outer event loop + stats        RCE:942-1167 -> ramp_advance_kernel
+ *     RampClusterEnvironment.is_done   RCE:1542-1557 -> stats[RAMP_SS_DONE]
+ * batched over `n_episodes` independent cluster instances (one per RL rollout) that advance in lock step.
+ * ddls_b200/engine.py is the ctypes binding; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns RAMP_OK (0) or a negative error code; ramp_last_error() returns a
+ * message for the calling thread (the Python wrapper re-raises it as `Exception`, the type the reference
+ * raises, e.g. RCE:462, RCE:1328).  All pointers are plain host or device pointers as documented; the
+ * library owns only what ramp_engine_create / ramp_register_template allocate.  One host thread per engine.
+ */
+#ifndef RAMP_B200_H
+#define RAMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAMP_OK 0
+#define RAMP_ERR_CUDA (-1)
+#define RAMP_ERR_BAD_ARG (-2)
+#define RAMP_ERR_CAPACITY (-3)       /* a table / pool configured at create time is full             */
+#define RAMP_ERR_SIM (-4)            /* the simulation itself raised (see per-episode status codes)   */
+
+#define RAMP_NO_CHANNEL 0xFFFFu
+
+/* per-lookahead / per-episode status codes written by the kernels */
+#define RAMP_ST_OK 0
+#define RAMP_ST_INFINITE_TICK 1      /* RCE:462 "Last tick was infinite" (deadlocked job graph)       */
+#define RAMP_ST_TRACE_OVERFLOW 2     /* more ticks than ramp_config_t.trace_cap                       */
+#define RAMP_ST_TABLE_FULL 3         /* running-job table full (ramp_config_t.max_running)            */
+#define RAMP_ST_NO_QUEUED_JOB 4      /* an action was given for an episode with an empty job queue    */
+#define RAMP_ST_JOBS_EXHAUSTED 5     /* more arrivals than ramp_config_t.max_jobs                     */
+
+/* memo modes (RCE:269-277, RCE:488-506) */
+#define RAMP_MEMO_REFERENCE 0        /* key = (episode, model, max partition degree): first seen wins, per episode */
+#define RAMP_MEMO_EXACT 1            /* key = 64-bit fingerprint of the lowered job: shared across episodes        */
+#define RAMP_MEMO_OFF 2              /* every mount runs its lookahead                                              */
+
+typedef struct ramp_engine ramp_engine_t;
+
+typedef struct {
+    int32_t device;              /* CUDA device ordinal                                                   */
+    int32_t n_episodes;          /* B: independent cluster instances                                      */
+    int32_t n_cluster_workers;   /* topology.graph.graph['num_workers'] RCE:991                           */
+    int32_t max_jobs;            /* arrivals per episode the arrival stream can hold                      */
+    int32_t max_running;         /* rows of the per-episode running-job table (<= n_cluster_workers suffices) */
+    int32_t max_templates;       /* lowered jobs that can be registered                                    */
+    int32_t memo_mode;           /* RAMP_MEMO_*                                                            */
+    int32_t memo_capacity_log2;  /* hash table slots = 1 << this (0 -> sized from n_episodes)              */
+    int32_t trace_cap;           /* max ticks recorded per lookahead (0 -> 16384)                          */
+    int32_t job_queue_capacity;  /* RCE:205 (default 10; the queue never holds more than one job)          */
+    double  machine_epsilon;     /* RCE:83 (1e-7)                                                          */
+    double  max_simulation_run_time; /* RCE:204                                                            */
+} ramp_config_t;
+
+/* One lowered (partitioned + placed + scheduled) job == the complete input of _run_lookahead.
+ * Op index = rank of the op id in sorted() order; dep index = rank of (u, v, k) in sorted() order
+ * (== CSR-by-source position).  HOST pointers; copied to the device by ramp_register_template. */
+typedef struct {
+    int32_t n_ops, n_deps, n_workers, n_channels;
+    int32_t num_training_steps;   /* JOB:82, RCE:450-452                                   */
+    int32_t model_id;             /* dense id of job.details['model'] RCE:489              */
+    int32_t degree;               /* max partition degree RCE:488                          */
+    int32_t _pad;
+    const double*   op_cost;      /* [N] compute_cost[device_type] RCE:1334                */
+    const int64_t*  op_prio;      /* [N] worker.mounted_job_op_to_priority RCE:1397        */
+    const uint16_t* op_worker;    /* [N] job-local worker id RCE:1336                      */
+    const uint16_t* op_n_parents; /* [N] predecessors that are not also successors JOB:508-523 */
+    const int32_t*  row_ptr;      /* [N+1] CSR out-edges                                   */
+    const int32_t*  dep_dst;      /* [E]                                                   */
+    const double*   dep_run_time; /* [E] init_run_time after RCE:542-560                   */
+    const int64_t*  dep_prio;     /* [E] channel.mounted_job_dep_to_priority RCE:1412      */
+    const uint16_t* dep_channel;  /* [E] job-local channel id or RAMP_NO_CHANNEL           */
+    const uint8_t*  dep_is_flow;  /* [E] RCE:531-536                                       */
+} ramp_lowered_job_t;
+
+/* Result of one lookahead (RCE:467). */
+typedef struct {
+    double  jct, comm, comp;      /* x num_training_steps RCE:450-452 */
+    int32_t n_ticks;
+    int32_t status;               /* RAMP_ST_*                        */
+} ramp_lookahead_result_t;
+
+/* Per-arrival job description (JobsGenerator stays host-side Python; RCE:351-377 reads only these). */
+typedef struct {
+    double interarrival;          /* gap added to time_next_job_to_arrive when THIS job arrives RCE:363 (inf after the last) */
+    double orig_op_mem;           /* original_job.details['job_total_op_memory_cost'] RCE:364, RCE:971 */
+    double orig_dep_size;         /* original_job.details['job_total_dep_size']                        */
+} ramp_arrival_t;
+
+/* Per-episode, per-step action row.  template_id < 0 is Action() (RJPE:395): no job handled, a queued
+ * job is blocked (RCE:914-919). */
+typedef struct {
+    double  max_acceptable_jct;   /* details['max_acceptable_job_completion_time'][device] RCE:815 */
+    double  part_op_mem;          /* partitioned job details['job_total_op_memory_cost'] RCE:966    */
+    double  part_dep_size;        /* partitioned job details['job_total_dep_size'] RCE:967          */
+    double  flow_size;            /* details['job_total_flow_size'] RCE:882-888                     */
+    int32_t n_mounted_workers;    /* len(details['mounted_workers'])  RCE:832                       */
+    int32_t n_mounted_channels;   /* len(details['mounted_channels']) RCE:979                       */
+    int32_t template_id;          /* from ramp_register_template, or -1                             */
+    int32_t flags;                /* RAMP_ACT_*                                                     */
+} ramp_action_t;
+
+#define RAMP_ACT_SKIP 1           /* leave this episode untouched this call (e.g. it is done)          */
+
+/* step statistics: double[RAMP_STEP_STATS_LEN] per episode; same names as step_stats RCE:306-338, 1046-1084 */
+enum {
+    RAMP_SS_STEP_COUNTER = 0, RAMP_SS_STEP_START_TIME, RAMP_SS_STEP_END_TIME, RAMP_SS_STEP_TIME,
+    RAMP_SS_NUM_JOBS_COMPLETED, RAMP_SS_NUM_JOBS_ARRIVED, RAMP_SS_NUM_JOBS_BLOCKED, RAMP_SS_JOB_QUEUE_LENGTH,
+    RAMP_SS_MEAN_NUM_JOBS_RUNNING, RAMP_SS_MEAN_NUM_MOUNTED_WORKERS, RAMP_SS_MEAN_NUM_MOUNTED_CHANNELS,
+    RAMP_SS_MEAN_COMPUTE_OVERHEAD_FRAC, RAMP_SS_MEAN_COMMUNICATION_OVERHEAD_FRAC,
+    RAMP_SS_COMPUTE_INFO_PROCESSED, RAMP_SS_DEP_INFO_PROCESSED, RAMP_SS_FLOW_INFO_PROCESSED,
+    RAMP_SS_CLUSTER_INFO_PROCESSED, RAMP_SS_DEMAND_COMPUTE_INFO_PROCESSED, RAMP_SS_DEMAND_DEP_INFO_PROCESSED,
+    RAMP_SS_DEMAND_TOTAL_INFO_PROCESSED,
+    RAMP_SS_MEAN_COMPUTE_THROUGHPUT, RAMP_SS_MEAN_DEP_THROUGHPUT, RAMP_SS_MEAN_FLOW_THROUGHPUT,
+    RAMP_SS_MEAN_CLUSTER_THROUGHPUT, RAMP_SS_MEAN_DEMAND_COMPUTE_THROUGHPUT, RAMP_SS_MEAN_DEMAND_DEP_THROUGHPUT,
+    RAMP_SS_MEAN_DEMAND_TOTAL_THROUGHPUT,
+    RAMP_SS_UTIL_MOUNTED_SUM,     /* sum of the step's 'mean_mounted_worker_utilisation_frac' list RCE:990 */
+    RAMP_SS_UTIL_CLUSTER_SUM,     /* sum of the step's 'mean_cluster_worker_utilisation_frac' list RCE:991 */
+    RAMP_SS_NUM_TICKS,            /* outer-loop iterations (= length of the two lists above)               */
+    RAMP_SS_DONE,                 /* is_done() after the step RCE:1176                                     */
+    RAMP_SS_LOOKAHEAD_RAN,        /* 1 if this step executed _run_lookahead (memo miss)                    */
+    RAMP_STEP_STATS_LEN
+};
+
+/* job record table: one row per (episode, job idx) */
+enum { RAMP_JS_NOT_ARRIVED = 0, RAMP_JS_QUEUED = 1, RAMP_JS_RUNNING = 2, RAMP_JS_COMPLETED = 3, RAMP_JS_BLOCKED = 4 };
+typedef struct {
+    int32_t status;               /* RAMP_JS_*                                        */
+    int32_t event_seq;            /* order of the completion / blocking event          */
+    double  time_arrived, time_started, time_completed;
+    double  jct, comm, comp, util; /* lookahead results + mean_mounted_worker_utilisation_frac RCE:830-832 */
+} ramp_job_record_t;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+const char* ramp_last_error(void);
+int ramp_engine_create(const ramp_config_t* cfg, ramp_engine_t** out);
+int ramp_engine_destroy(ramp_engine_t* eng);
+/* the CUDA stream all engine work is issued on (cudaStream_t as void*) */
+void* ramp_engine_stream(ramp_engine_t* eng);
+
+/* Copies a lowered job to HBM, derives the priority-rank keys and the initial ready set, and returns its id. */
+int ramp_register_template(ramp_engine_t* eng, const ramp_lowered_job_t* job, int32_t* template_id_out);
+int ramp_template_count(ramp_engine_t* eng);
+
+/* ---- batched RampClusterEnvironment.reset / step ------------------------------------------------ */
+/* RCE:202-295 for every episode.  arrivals: HOST [n_episodes][n_jobs]; clears the memo (RCE:269-275). */
+int ramp_reset(ramp_engine_t* eng, const ramp_arrival_t* arrivals, int32_t n_jobs);
+
+/* One RampClusterEnvironment.step for every episode.  HOST buffers; the host<->device copies are issued
+ * on the engine stream inside the call:  actions [n_episodes] in,  stats [n_episodes][RAMP_STEP_STATS_LEN]
+ * out (may be NULL).  fuse_empty_steps != 0 additionally runs, per episode, the RJPE:394-395 loop
+ * `while len(job_queue) == 0 and not done: step(Action())` on the device; stats then describe the action
+ * step, n_cluster_steps_out[b] (may be NULL) how many cluster steps episode b took in total. */
+int ramp_step_host(ramp_engine_t* eng, const ramp_action_t* actions, int32_t fuse_empty_steps,
+                   double* stats_out, int32_t* n_cluster_steps_out);
+/* Same with DEVICE pointers (inputs already resident in HBM, outputs left there); asynchronous on the
+ * engine stream -- call ramp_sync() before reading. */
+int ramp_step_device(ramp_engine_t* eng, const ramp_action_t* d_actions, int32_t fuse_empty_steps,
+                     double* d_stats_out, int32_t* d_n_cluster_steps_out);
+int ramp_sync(ramp_engine_t* eng);
+/* Raises (returns RAMP_ERR_SIM) if any episode recorded a RAMP_ST_* error since the last check. */
+int ramp_check_status(ramp_engine_t* eng, int32_t* first_bad_episode_out, int32_t* status_out);
+
+/* ---- state read-back (HOST destinations) -------------------------------------------------------- */
+int ramp_get_job_records(ramp_engine_t* eng, ramp_job_record_t* out /* [n_episodes][max_jobs] */);
+/* per-episode scalars: double[n_episodes][RAMP_EP_LEN] */
+enum { RAMP_EP_TIME = 0, RAMP_EP_NEXT_ARRIVAL, RAMP_EP_NUM_ARRIVED, RAMP_EP_NUM_COMPLETED, RAMP_EP_NUM_BLOCKED,
+       RAMP_EP_QUEUED_JOB, RAMP_EP_NUM_RUNNING, RAMP_EP_STEP_COUNTER, RAMP_EP_LOAD_RATE_SUM, RAMP_EP_LOAD_RATE_N,
+       RAMP_EP_DONE, RAMP_EP_STATUS, RAMP_EP_LEN };
+int ramp_get_episode_state(ramp_engine_t* eng, double* out);
+/* device pointer of the same table (for NCCL all-gather of episode metrics without a host bounce) */
+int ramp_episode_state_device(ramp_engine_t* eng, double** d_out);
+/* memo statistics since the last reset: lookups, hits, lookaheads executed */
+int ramp_get_memo_stats(ramp_engine_t* eng, int64_t* lookups, int64_t* hits, int64_t* lookaheads);
+/* the lookahead (memoised or fresh) used by episode `episode`'s most recent mount: result + trace
+ * (tick_counter_to_active_workers_tick_size RCE:467); trace buffers are HOST, capacity trace_cap. */
+int ramp_get_last_lookahead(ramp_engine_t* eng, int32_t episode, ramp_lookahead_result_t* res,
+                            int32_t* trace_n_active, double* trace_tick, int32_t trace_cap);
+
+/* ---- the lookahead kernel on its own ------------------------------------------------------------ */
+/* Runs _run_lookahead (RCE:379-467) for n work items; item k uses template template_ids[k] (HOST array).
+ * results: HOST [n].  trace_n_active / trace_tick: HOST [n][trace_cap] or NULL.  kernel_ms_out (may be
+ * NULL) receives the CUDA-event duration of the kernel alone. */
+int ramp_run_lookaheads(ramp_engine_t* eng, const int32_t* template_ids, int32_t n,
+                        ramp_lookahead_result_t* results, int32_t* trace_n_active, double* trace_tick,
+                        int32_t trace_cap, float* kernel_ms_out);
+
+/* kernel launch counter (gpu_launches in bench.py) and device time spent in the lookahead kernel inside
+ * ramp_step_* since the last call (CUDA events on the engine stream) */
+int64_t ramp_launch_count(ramp_engine_t* eng);
+int ramp_get_lookahead_kernel_time(ramp_engine_t* eng, double* total_ms, int64_t* launches, int64_t* work_items,
+                                   int64_t* algorithmic_bytes, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
