@@ -1,0 +1,642 @@
+// ramp_engine.cu -- host side of the C ABI declared in include/ramp_b200.h.
+//
+// Owns the HBM-resident state (templates, memo table, result slots, trace pool, per-episode tables,
+// per-CTA scratch slabs) and launches the three kernels of a batched RampClusterEnvironment.step:
+//   plan (memo) -> lookahead (persistent CTAs, one lookahead per CTA at a time) -> step (one thread per episode).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "ramp_kernels.cuh"
+
+using namespace ramp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return set_error(RAMP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int MAX_EVENT_PAIRS = 64;
+
+// The lookahead kernel is instantiated for several CTA sizes; small CTAs (1-2 warps) keep more lookaheads
+// resident per SM and waste fewer lanes on the small per-tick frontiers, large CTAs finish one lookahead sooner.
+using LookaheadKernel = void (*)(const LookaheadArgs);
+LookaheadKernel lookahead_kernel_for(int nt) {
+    switch (nt) {
+        case 32: return ramp_lookahead_kernel<32>;
+        case 64: return ramp_lookahead_kernel<64>;
+        case 128: return ramp_lookahead_kernel<128>;
+        case 256: return ramp_lookahead_kernel<256>;
+        default: return nullptr;
+    }
+}
+
+struct HostTemplate {
+    TemplateDev dev;             // copy of what sits in the device array
+    void* blob = nullptr;        // single device allocation holding all arrays
+    std::vector<unsigned char> bytes;  // canonical host bytes for exact-duplicate detection
+    uint64_t hash = 0;
+};
+
+}  // namespace
+
+struct ramp_engine {
+    ramp_config_t cfg{};
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    // templates
+    std::vector<HostTemplate> templates;
+    TemplateDev* d_templates = nullptr;
+    uint64_t max_scratch = 0;
+    int32_t max_w = 1, max_c = 1;
+    // memo + results
+    uint32_t memo_cap = 0;
+    unsigned long long* d_memo_keys = nullptr;
+    ResultSlots res{};
+    int32_t n_slots = 0;
+    TracePool pool{};
+    // per-step
+    WorkItem* d_items = nullptr;
+    Counters* d_counters = nullptr;
+    MemoStats* d_stats = nullptr;
+    ramp_action_t* d_actions = nullptr;
+    double* d_step_stats = nullptr;
+    int32_t* d_n_cluster_steps = nullptr;
+    double* d_ep_export = nullptr;
+    // episode state
+    EpisodeState ep{};
+    ramp_arrival_t* d_arrivals = nullptr;
+    // lookahead scratch
+    unsigned char* d_scratch = nullptr;
+    uint64_t scratch_stride = 0;
+    int scratch_grid = 0;
+    int grid = 0;
+    int nt = 64;                 // threads per lookahead CTA (RAMP_LOOKAHEAD_THREADS overrides)
+    int max_ctas_per_sm = 0;     // optional cap (RAMP_LOOKAHEAD_CTAS_PER_SM)
+    size_t smem_bytes = 0;
+    // standalone lookahead buffers
+    ResultSlots sa_res{};
+    int32_t sa_cap = 0;
+    WorkItem* sa_items = nullptr;
+    Counters* sa_counters = nullptr;
+    // instrumentation
+    int64_t launches = 0;
+    cudaEvent_t ev_a[MAX_EVENT_PAIRS]{}, ev_b[MAX_EVENT_PAIRS]{};
+    int ev_pending = 0;
+    double la_ms_total = 0.0;
+    int64_t la_launches = 0;
+    unsigned long long la_items_base = 0, la_bytes_base = 0;
+};
+
+namespace {
+
+int alloc_result_slots(ResultSlots& r, int32_t n) {
+    CUDA_TRY(cudaMalloc(&r.jct, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc(&r.comm, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc(&r.comp, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc(&r.n_ticks, sizeof(int32_t) * n));
+    CUDA_TRY(cudaMalloc(&r.status, sizeof(int32_t) * n));
+    CUDA_TRY(cudaMalloc(&r.trace_off, sizeof(int64_t) * n));
+    return RAMP_OK;
+}
+
+void free_result_slots(ResultSlots& r) {
+    cudaFree(r.jct); cudaFree(r.comm); cudaFree(r.comp); cudaFree(r.n_ticks); cudaFree(r.status); cudaFree(r.trace_off);
+    r = ResultSlots{};
+}
+
+int resolve_events(ramp_engine* e) {
+    for (int k = 0; k < e->ev_pending; ++k) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e->ev_a[k], e->ev_b[k]));
+        e->la_ms_total += ms;
+        e->la_launches++;
+    }
+    e->ev_pending = 0;
+    return RAMP_OK;
+}
+
+// (re)allocates the per-CTA scratch slabs for the largest registered template and picks the grid
+int ensure_scratch(ramp_engine* e) {
+    const uint64_t trace_bytes = align_up((uint64_t)e->cfg.trace_cap * 12, 16);
+    const uint64_t stride = align_up(std::max<uint64_t>(e->max_scratch, 16), 256) + align_up(trace_bytes, 256);
+    const size_t smem = sizeof(uint32_t) * ((size_t)e->max_w * 2 + (size_t)e->max_c);
+    if (smem > 200 * 1024)
+        return set_error(RAMP_ERR_CAPACITY, "a template needs %zu B of shared memory for its worker/channel key arrays (max 200 KiB)", smem);
+    if (smem != e->smem_bytes || e->grid == 0) {
+        LookaheadKernel kern = lookahead_kernel_for(e->nt);
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, e->nt, smem));
+        if (occ < 1) occ = 1;
+        if (e->max_ctas_per_sm > 0 && occ > e->max_ctas_per_sm) occ = e->max_ctas_per_sm;
+        e->grid = e->sm_count * occ;     // persistent CTAs: a whole number of waves (148 SMs x resident CTAs per SM)
+        e->smem_bytes = smem;
+    }
+    if (stride != e->scratch_stride || e->grid != e->scratch_grid || e->d_scratch == nullptr) {
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        if (e->d_scratch) cudaFree(e->d_scratch);
+        e->d_scratch = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_scratch, stride * (uint64_t)e->grid));
+        e->scratch_stride = stride;
+        e->scratch_grid = e->grid;
+    }
+    return RAMP_OK;
+}
+
+LookaheadArgs make_lookahead_args(ramp_engine* e, const WorkItem* items, Counters* counters, const ResultSlots& res,
+                                  bool use_pool, MemoStats* stats) {
+    LookaheadArgs a{};
+    a.templates = e->d_templates;
+    a.items = items;
+    a.n_work = &counters->n_work;
+    a.cursor = &counters->work_cursor;
+    a.scratch = e->d_scratch;
+    a.scratch_stride = e->scratch_stride;
+    a.res = res;
+    a.pool = e->pool;
+    if (!use_pool) a.pool.top = nullptr;
+    a.trace_cap = e->cfg.trace_cap;
+    a.w_cap = e->max_w;
+    a.c_cap = e->max_c;
+    a.stats = stats;
+    return a;
+}
+
+uint64_t fnv1a(const unsigned char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// rank keys: larger key wins.  Sorting by (priority desc, index asc) and numbering from the top reproduces
+// "iterate in sorted() order, replace only on strictly greater priority" (RCE:56-66, RCE:672-685).
+void make_rank_keys(const int64_t* prio, int32_t n, std::vector<uint32_t>& key) {
+    std::vector<int32_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return prio[a] > prio[b]; });
+    key.resize(n);
+    for (int32_t r = 0; r < n; ++r) key[order[r]] = (uint32_t)(n - r);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ramp_last_error(void) { return g_last_error.c_str(); }
+
+int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
+    if (!cfg_in || !out) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    ramp_config_t cfg = *cfg_in;
+    if (cfg.n_episodes < 1 || cfg.max_jobs < 1 || cfg.n_cluster_workers < 1)
+        return set_error(RAMP_ERR_BAD_ARG, "n_episodes, max_jobs and n_cluster_workers must be >= 1");
+    if (cfg.max_running < 1) cfg.max_running = cfg.n_cluster_workers;
+    if (cfg.max_templates < 1) cfg.max_templates = 1024;
+    if (cfg.trace_cap < 1) cfg.trace_cap = 16384;
+    if (cfg.job_queue_capacity < 0) cfg.job_queue_capacity = 10;
+    if (cfg.machine_epsilon == 0.0) cfg.machine_epsilon = 1e-7;
+    if (cfg.memo_capacity_log2 <= 0) {
+        int lg = 10;
+        while ((1ll << lg) < (long long)cfg.n_episodes * 16 && lg < 26) ++lg;
+        cfg.memo_capacity_log2 = lg;
+    }
+    CUDA_TRY(cudaSetDevice(cfg.device));
+    ramp_engine* e = new ramp_engine();
+    e->cfg = cfg;
+    if (const char* v = getenv("RAMP_LOOKAHEAD_THREADS")) {
+        const int nt = atoi(v);
+        if (lookahead_kernel_for(nt) == nullptr) { delete e; return set_error(RAMP_ERR_BAD_ARG, "RAMP_LOOKAHEAD_THREADS must be 32, 64, 128 or 256"); }
+        e->nt = nt;
+    }
+    if (const char* v = getenv("RAMP_LOOKAHEAD_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg.device));
+    e->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const int B = cfg.n_episodes;
+
+    CUDA_TRY(cudaMalloc(&e->d_templates, sizeof(TemplateDev) * cfg.max_templates));
+    e->memo_cap = 1u << cfg.memo_capacity_log2;
+    CUDA_TRY(cudaMalloc(&e->d_memo_keys, sizeof(unsigned long long) * e->memo_cap));
+    CUDA_TRY(cudaMemset(e->d_memo_keys, 0, sizeof(unsigned long long) * e->memo_cap));
+    e->n_slots = (int32_t)e->memo_cap + B;
+    if (alloc_result_slots(e->res, e->n_slots) != RAMP_OK) return RAMP_ERR_CUDA;
+    CUDA_TRY(cudaMemset(e->res.status, 0, sizeof(int32_t) * e->n_slots));
+
+    // trace pool: exact-size allocations, default budget 48 Mi entries (576 MiB) or enough for B x 4 x 2048 ticks
+    e->pool.len = std::max<uint64_t>(48ull << 20, (uint64_t)B * 4ull * 2048ull);
+    CUDA_TRY(cudaMalloc(&e->pool.n_active, sizeof(int32_t) * e->pool.len));
+    CUDA_TRY(cudaMalloc(&e->pool.tick, sizeof(double) * e->pool.len));
+    CUDA_TRY(cudaMalloc(&e->pool.top, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(e->pool.top, 0, sizeof(unsigned long long)));
+
+    CUDA_TRY(cudaMalloc(&e->d_items, sizeof(WorkItem) * B));
+    CUDA_TRY(cudaMalloc(&e->d_counters, sizeof(Counters)));
+    CUDA_TRY(cudaMemset(e->d_counters, 0, sizeof(Counters)));
+    CUDA_TRY(cudaMalloc(&e->d_stats, sizeof(MemoStats)));
+    CUDA_TRY(cudaMemset(e->d_stats, 0, sizeof(MemoStats)));
+    CUDA_TRY(cudaMalloc(&e->d_actions, sizeof(ramp_action_t) * B));
+    CUDA_TRY(cudaMalloc(&e->d_step_stats, sizeof(double) * RAMP_STEP_STATS_LEN * B));
+    CUDA_TRY(cudaMalloc(&e->d_n_cluster_steps, sizeof(int32_t) * B));
+    CUDA_TRY(cudaMalloc(&e->d_ep_export, sizeof(double) * RAMP_EP_LEN * B));
+
+    EpisodeState& ep = e->ep;
+    ep.B = B; ep.max_running = cfg.max_running; ep.max_jobs = cfg.max_jobs; ep.n_jobs = 0;
+    ep.n_cluster_workers = cfg.n_cluster_workers; ep.queue_capacity = cfg.job_queue_capacity;
+    ep.eps = cfg.machine_epsilon; ep.max_sim_time = cfg.max_simulation_run_time;
+    CUDA_TRY(cudaMalloc(&ep.ef, sizeof(double) * EF_COUNT * B));
+    CUDA_TRY(cudaMalloc(&ep.ei, sizeof(int32_t) * EI_COUNT * B));
+    CUDA_TRY(cudaMalloc(&ep.rf, sizeof(double) * RF_COUNT * (size_t)cfg.max_running * B));
+    CUDA_TRY(cudaMalloc(&ep.ri, sizeof(int32_t) * RI_COUNT * (size_t)cfg.max_running * B));
+    CUDA_TRY(cudaMalloc(&ep.rec, sizeof(ramp_job_record_t) * (size_t)cfg.max_jobs * B));
+    CUDA_TRY(cudaMalloc(&e->d_arrivals, sizeof(ramp_arrival_t) * (size_t)cfg.max_jobs * B));
+    CUDA_TRY(cudaMemset(ep.ef, 0, sizeof(double) * EF_COUNT * B));
+    CUDA_TRY(cudaMemset(ep.ei, 0, sizeof(int32_t) * EI_COUNT * B));
+    CUDA_TRY(cudaMemset(ep.rec, 0, sizeof(ramp_job_record_t) * (size_t)cfg.max_jobs * B));
+    ep.arr = e->d_arrivals;
+
+    for (int k = 0; k < MAX_EVENT_PAIRS; ++k) {
+        CUDA_TRY(cudaEventCreate(&e->ev_a[k]));
+        CUDA_TRY(cudaEventCreate(&e->ev_b[k]));
+    }
+    *out = e;
+    return RAMP_OK;
+}
+
+int ramp_engine_destroy(ramp_engine_t* e) {
+    if (!e) return RAMP_OK;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    for (auto& t : e->templates) cudaFree(t.blob);
+    cudaFree(e->d_templates); cudaFree(e->d_memo_keys);
+    free_result_slots(e->res); free_result_slots(e->sa_res);
+    cudaFree(e->pool.n_active); cudaFree(e->pool.tick); cudaFree(e->pool.top);
+    cudaFree(e->d_items); cudaFree(e->d_counters); cudaFree(e->d_stats); cudaFree(e->d_actions);
+    cudaFree(e->d_step_stats); cudaFree(e->d_n_cluster_steps); cudaFree(e->d_ep_export);
+    cudaFree(e->ep.ef); cudaFree(e->ep.ei); cudaFree(e->ep.rf); cudaFree(e->ep.ri); cudaFree(e->ep.rec);
+    cudaFree(e->d_arrivals); cudaFree(e->d_scratch); cudaFree(e->sa_items); cudaFree(e->sa_counters);
+    for (int k = 0; k < MAX_EVENT_PAIRS; ++k) { cudaEventDestroy(e->ev_a[k]); cudaEventDestroy(e->ev_b[k]); }
+    cudaStreamDestroy(e->stream);
+    delete e;
+    return RAMP_OK;
+}
+
+void* ramp_engine_stream(ramp_engine_t* e) { return e ? (void*)e->stream : nullptr; }
+
+int ramp_template_count(ramp_engine_t* e) { return e ? (int)e->templates.size() : 0; }
+
+int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_t* id_out) {
+    if (!e || !j || !id_out) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    if ((int)e->templates.size() >= e->cfg.max_templates)
+        return set_error(RAMP_ERR_CAPACITY, "max_templates (%d) reached", e->cfg.max_templates);
+    const int32_t N = j->n_ops, E = j->n_deps, W = j->n_workers, C = j->n_channels;
+    if (N < 1 || E < 0 || W < 1 || C < 0) return set_error(RAMP_ERR_BAD_ARG, "bad template sizes N=%d E=%d W=%d C=%d", N, E, W, C);
+    if (W > 0xFFFF || C >= 0xFFFF) return set_error(RAMP_ERR_BAD_ARG, "too many mounted workers/channels");
+    if (j->model_id < 0 || j->model_id > 0xFFFF || j->degree < 0 || j->degree > 0xFFFF)
+        return set_error(RAMP_ERR_BAD_ARG, "model_id and degree must fit 16 bits");
+    // ---- validate (the reference would KeyError / misbehave on these) ----
+    if (j->row_ptr[0] != 0 || j->row_ptr[N] != E) return set_error(RAMP_ERR_BAD_ARG, "row_ptr is not a CSR offset array");
+    for (int32_t i = 0; i < N; ++i) {
+        if (j->row_ptr[i + 1] < j->row_ptr[i]) return set_error(RAMP_ERR_BAD_ARG, "row_ptr not monotone at %d", i);
+        if (j->op_worker[i] >= W) return set_error(RAMP_ERR_BAD_ARG, "op %d on worker %d >= n_workers %d", i, j->op_worker[i], W);
+        if (!(j->op_cost[i] >= 0.0)) return set_error(RAMP_ERR_BAD_ARG, "op %d has a negative or NaN cost", i);
+    }
+    std::vector<int32_t> in_deg(N, 0);
+    for (int32_t k = 0; k < E; ++k) {
+        if (j->dep_dst[k] < 0 || j->dep_dst[k] >= N) return set_error(RAMP_ERR_BAD_ARG, "dep %d has dst out of range", k);
+        if (j->dep_channel[k] != RAMP_NO_CHANNEL && j->dep_channel[k] >= C)
+            return set_error(RAMP_ERR_BAD_ARG, "dep %d on channel %d >= n_channels %d", k, j->dep_channel[k], C);
+        if (!(j->dep_run_time[k] >= 0.0)) return set_error(RAMP_ERR_BAD_ARG, "dep %d has a negative or NaN run time", k);
+        in_deg[j->dep_dst[k]]++;
+    }
+    // ---- derive ----
+    std::vector<uint32_t> op_key, dep_key;
+    make_rank_keys(j->op_prio, N, op_key);
+    make_rank_keys(j->dep_prio, E, dep_key);
+    std::vector<int32_t> src;
+    for (int32_t i = 0; i < N; ++i) if (in_deg[i] == 0) src.push_back(i);
+    std::vector<double> op_cost(j->op_cost, j->op_cost + N), dep_rt(j->dep_run_time, j->dep_run_time + E);
+    for (auto& x : op_cost) x = x + 0.0;   // -0.0 -> +0.0 so the u64 bit pattern orders like the value
+    for (auto& x : dep_rt) x = x + 0.0;
+
+    // ---- pack one blob ----
+    struct Seg { const void* p; size_t bytes; size_t off; };
+    Seg segs[11] = {
+        {op_cost.data(), sizeof(double) * (size_t)N, 0}, {op_key.data(), sizeof(uint32_t) * (size_t)N, 0},
+        {j->op_worker, sizeof(uint16_t) * (size_t)N, 0}, {j->op_n_parents, sizeof(uint16_t) * (size_t)N, 0},
+        {j->row_ptr, sizeof(int32_t) * (size_t)(N + 1), 0}, {j->dep_dst, sizeof(int32_t) * (size_t)E, 0},
+        {dep_rt.data(), sizeof(double) * (size_t)E, 0}, {dep_key.data(), sizeof(uint32_t) * (size_t)E, 0},
+        {j->dep_channel, sizeof(uint16_t) * (size_t)E, 0}, {j->dep_is_flow, sizeof(uint8_t) * (size_t)E, 0},
+        {src.data(), sizeof(int32_t) * src.size(), 0}};
+    size_t total = 0;
+    for (auto& s : segs) { s.off = total; total += align_up(std::max<size_t>(s.bytes, 1), 256); }
+    HostTemplate ht;
+    ht.bytes.assign(total + 8 * sizeof(int32_t), 0);
+    for (auto& s : segs) if (s.bytes) memcpy(ht.bytes.data() + s.off, s.p, s.bytes);
+    int32_t hdr[8] = {N, E, W, C, j->num_training_steps, 0, 0, (int32_t)src.size()};
+    memcpy(ht.bytes.data() + total, hdr, sizeof(hdr));
+    ht.hash = fnv1a(ht.bytes.data(), ht.bytes.size());
+    int32_t canon = (int32_t)e->templates.size();
+    for (size_t t = 0; t < e->templates.size(); ++t)
+        if (e->templates[t].hash == ht.hash && e->templates[t].bytes == ht.bytes) { canon = e->templates[t].dev.canon_id; break; }
+
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMalloc(&ht.blob, total));
+    CUDA_TRY(cudaMemcpy(ht.blob, ht.bytes.data(), total, cudaMemcpyHostToDevice));
+    unsigned char* base = (unsigned char*)ht.blob;
+    TemplateDev& d = ht.dev;
+    d.n_ops = N; d.n_deps = E; d.n_workers = W; d.n_channels = C;
+    d.num_training_steps = j->num_training_steps; d.model_id = j->model_id; d.degree = j->degree;
+    d.n_src = (int32_t)src.size(); d.canon_id = canon;
+    d.trace_need = (int32_t)std::min<int64_t>((int64_t)N + E + 1, e->cfg.trace_cap);
+    d.op_cost = (const double*)(base + segs[0].off); d.op_key = (const uint32_t*)(base + segs[1].off);
+    d.op_worker = (const uint16_t*)(base + segs[2].off); d.op_n_parents = (const uint16_t*)(base + segs[3].off);
+    d.row_ptr = (const int32_t*)(base + segs[4].off); d.dep_dst = (const int32_t*)(base + segs[5].off);
+    d.dep_run_time = (const double*)(base + segs[6].off); d.dep_key = (const uint32_t*)(base + segs[7].off);
+    d.dep_channel = (const uint16_t*)(base + segs[8].off); d.dep_is_flow = (const uint8_t*)(base + segs[9].off);
+    d.src_ops = (const int32_t*)(base + segs[10].off);
+    d.scratch_bytes = scratch_bytes_for(N, E);
+    d.algorithmic_bytes_static = 20ull * (uint64_t)N + 19ull * (uint64_t)E + 24ull;
+    const int32_t id = (int32_t)e->templates.size();
+    CUDA_TRY(cudaMemcpy(e->d_templates + id, &d, sizeof(TemplateDev), cudaMemcpyHostToDevice));
+    e->max_scratch = std::max(e->max_scratch, d.scratch_bytes);
+    e->max_w = std::max(e->max_w, W);
+    e->max_c = std::max(e->max_c, std::max(C, 1));
+    e->templates.push_back(std::move(ht));
+    *id_out = id;
+    return RAMP_OK;
+}
+
+int ramp_reset(ramp_engine_t* e, const ramp_arrival_t* arrivals, int32_t n_jobs) {
+    if (!e || !arrivals) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    if (n_jobs < 1 || n_jobs > e->cfg.max_jobs) return set_error(RAMP_ERR_BAD_ARG, "n_jobs %d not in [1, max_jobs=%d]", n_jobs, e->cfg.max_jobs);
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    const int B = e->cfg.n_episodes;
+    if (n_jobs == e->cfg.max_jobs) {
+        CUDA_TRY(cudaMemcpyAsync(e->d_arrivals, arrivals, sizeof(ramp_arrival_t) * (size_t)n_jobs * B, cudaMemcpyHostToDevice, e->stream));
+    } else {
+        CUDA_TRY(cudaMemcpy2DAsync(e->d_arrivals, sizeof(ramp_arrival_t) * (size_t)e->cfg.max_jobs, arrivals,
+                                   sizeof(ramp_arrival_t) * (size_t)n_jobs, sizeof(ramp_arrival_t) * (size_t)n_jobs, B,
+                                   cudaMemcpyHostToDevice, e->stream));
+    }
+    e->ep.n_jobs = n_jobs;
+    // memo is per env instance per episode: cleared on reset (RCE:269-275)
+    CUDA_TRY(cudaMemsetAsync(e->d_memo_keys, 0, sizeof(unsigned long long) * e->memo_cap, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->pool.top, 0, sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(MemoStats), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), e->stream));
+    e->la_items_base = 0; e->la_bytes_base = 0;
+    ramp_reset_kernel<<<(B + 127) / 128, 128, 0, e->stream>>>(e->ep);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RAMP_OK;
+}
+
+int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t fuse, double* d_stats_out, int32_t* d_ncs_out) {
+    if (!e || !d_actions) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    if (e->ep.n_jobs < 1) return set_error(RAMP_ERR_BAD_ARG, "ramp_reset must be called before ramp_step");
+    if (e->templates.empty()) {
+        // allowed: every action must then be Action(); still need a scratch-less plan
+    }
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    if (!e->templates.empty()) { int rc = ensure_scratch(e); if (rc != RAMP_OK) return rc; }
+    const int B = e->cfg.n_episodes;
+    cudaStream_t st = e->stream;
+    CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int32_t), st));   // n_work, work_cursor
+    PlanArgs p{};
+    p.actions = d_actions; p.templates = e->d_templates; p.n_templates = (int32_t)e->templates.size();
+    p.ep = e->ep; p.memo.keys = e->d_memo_keys; p.memo.mask = e->memo_cap - 1; p.memo.mode = e->cfg.memo_mode;
+    p.items = e->d_items; p.counters = e->d_counters; p.stats = e->d_stats;
+    ramp_plan_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
+    e->launches++;
+    if (!e->templates.empty()) {
+        if (e->ev_pending >= MAX_EVENT_PAIRS) { CUDA_TRY(cudaStreamSynchronize(st)); int rc = resolve_events(e); if (rc) return rc; }
+        LookaheadArgs a = make_lookahead_args(e, e->d_items, e->d_counters, e->res, true, e->d_stats);
+        CUDA_TRY(cudaEventRecord(e->ev_a[e->ev_pending], st));
+        lookahead_kernel_for(e->nt)<<<e->grid, e->nt, e->smem_bytes, st>>>(a);
+        CUDA_TRY(cudaEventRecord(e->ev_b[e->ev_pending], st));
+        e->ev_pending++;
+        e->launches++;
+    }
+    StepArgs s{};
+    s.actions = d_actions; s.ep = e->ep; s.res = e->res; s.pool = e->pool; s.counters = e->d_counters;
+    s.stats_out = d_stats_out; s.n_cluster_steps_out = d_ncs_out; s.fuse_empty_steps = fuse;
+    ramp_step_kernel<<<(B + 63) / 64, 64, 0, st>>>(s);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAMP_OK;
+}
+
+int ramp_sync(ramp_engine_t* e) {
+    if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return resolve_events(e);
+}
+
+int ramp_step_host(ramp_engine_t* e, const ramp_action_t* actions, int32_t fuse, double* stats_out, int32_t* ncs_out) {
+    if (!e || !actions) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    const int B = e->cfg.n_episodes;
+    CUDA_TRY(cudaMemcpyAsync(e->d_actions, actions, sizeof(ramp_action_t) * B, cudaMemcpyHostToDevice, e->stream));
+    int rc = ramp_step_device(e, e->d_actions, fuse, stats_out ? e->d_step_stats : nullptr, ncs_out ? e->d_n_cluster_steps : nullptr);
+    if (rc != RAMP_OK) return rc;
+    if (stats_out)
+        CUDA_TRY(cudaMemcpyAsync(stats_out, e->d_step_stats, sizeof(double) * RAMP_STEP_STATS_LEN * B, cudaMemcpyDeviceToHost, e->stream));
+    if (ncs_out)
+        CUDA_TRY(cudaMemcpyAsync(ncs_out, e->d_n_cluster_steps, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream));
+    return ramp_sync(e);
+}
+
+int ramp_check_status(ramp_engine_t* e, int32_t* ep_out, int32_t* st_out) {
+    if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    Counters c{};
+    CUDA_TRY(cudaMemcpy(&c, e->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost));
+    if (c.err_episode == 0) { if (ep_out) *ep_out = -1; if (st_out) *st_out = 0; return RAMP_OK; }
+    const int b = c.err_episode - 1;
+    int32_t st = 0;
+    CUDA_TRY(cudaMemcpy(&st, e->ep.ei + (size_t)EI_STATUS * e->cfg.n_episodes + b, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(&e->d_counters->err_episode, 0, sizeof(int32_t)));
+    if (ep_out) *ep_out = b;
+    if (st_out) *st_out = st;
+    const char* what = st == RAMP_ST_INFINITE_TICK ? "ERROR: Last tick was infinite, a bug has occurred somewhere."
+                     : st == RAMP_ST_TRACE_OVERFLOW ? "lookahead needed more ticks than trace_cap (or the trace pool is full)"
+                     : st == RAMP_ST_TABLE_FULL ? "running-job table or memo table is full"
+                     : st == RAMP_ST_NO_QUEUED_JOB ? "an action was given for an episode whose job queue is empty"
+                     : "simulation error";
+    return set_error(RAMP_ERR_SIM, "episode %d: %s (status %d)", b, what, st);
+}
+
+int ramp_get_job_records(ramp_engine_t* e, ramp_job_record_t* out) {
+    if (!e || !out) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaMemcpy(out, e->ep.rec, sizeof(ramp_job_record_t) * (size_t)e->cfg.max_jobs * e->cfg.n_episodes, cudaMemcpyDeviceToHost));
+    return RAMP_OK;
+}
+
+int ramp_episode_state_device(ramp_engine_t* e, double** d_out) {
+    if (!e || !d_out) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    const int B = e->cfg.n_episodes;
+    ramp_export_episode_state_kernel<<<(B + 127) / 128, 128, 0, e->stream>>>(e->ep, e->d_ep_export);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    *d_out = e->d_ep_export;
+    return RAMP_OK;
+}
+
+int ramp_get_episode_state(ramp_engine_t* e, double* out) {
+    double* d = nullptr;
+    int rc = ramp_episode_state_device(e, &d);
+    if (rc != RAMP_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, d, sizeof(double) * RAMP_EP_LEN * e->cfg.n_episodes, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RAMP_OK;
+}
+
+int ramp_get_memo_stats(ramp_engine_t* e, int64_t* lookups, int64_t* hits, int64_t* lookaheads) {
+    if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    MemoStats s{};
+    CUDA_TRY(cudaMemcpy(&s, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost));
+    if (lookups) *lookups = (int64_t)s.lookups;
+    if (hits) *hits = (int64_t)s.hits;
+    if (lookaheads) *lookaheads = (int64_t)s.lookaheads;
+    return RAMP_OK;
+}
+
+int ramp_get_last_lookahead(ramp_engine_t* e, int32_t episode, ramp_lookahead_result_t* res, int32_t* tn, double* tt, int32_t cap) {
+    if (!e || !res) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    if (episode < 0 || episode >= e->cfg.n_episodes) return set_error(RAMP_ERR_BAD_ARG, "episode out of range");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    int32_t slot = -1;
+    CUDA_TRY(cudaMemcpy(&slot, e->ep.ei + (size_t)EI_LAST_SLOT * e->cfg.n_episodes + episode, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (slot < 0) return set_error(RAMP_ERR_BAD_ARG, "episode %d has not mounted a job yet", episode);
+    int64_t off = -1;
+    CUDA_TRY(cudaMemcpy(&res->jct, e->res.jct + slot, sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&res->comm, e->res.comm + slot, sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&res->comp, e->res.comp + slot, sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&res->n_ticks, e->res.n_ticks + slot, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&res->status, e->res.status + slot, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&off, e->res.trace_off + slot, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (tn && tt && off >= 0) {
+        const int32_t n = std::min(std::min(res->n_ticks, cap), e->cfg.trace_cap);
+        CUDA_TRY(cudaMemcpy(tn, e->pool.n_active + off, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(tt, e->pool.tick + off, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    }
+    return RAMP_OK;
+}
+
+int ramp_run_lookaheads(ramp_engine_t* e, const int32_t* template_ids, int32_t n, ramp_lookahead_result_t* results,
+                        int32_t* trace_n, double* trace_tick, int32_t trace_cap, float* kernel_ms_out) {
+    if (!e || !template_ids || !results || n < 0) return set_error(RAMP_ERR_BAD_ARG, "bad argument");
+    if (n == 0) return RAMP_OK;
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    for (int32_t k = 0; k < n; ++k)
+        if (template_ids[k] < 0 || template_ids[k] >= (int32_t)e->templates.size())
+            return set_error(RAMP_ERR_BAD_ARG, "template id %d at %d is not registered", template_ids[k], k);
+    int rc = ensure_scratch(e);
+    if (rc != RAMP_OK) return rc;
+    cudaStream_t st = e->stream;
+    if (n > e->sa_cap) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        free_result_slots(e->sa_res); cudaFree(e->sa_items);
+        if (alloc_result_slots(e->sa_res, n) != RAMP_OK) return RAMP_ERR_CUDA;
+        CUDA_TRY(cudaMalloc(&e->sa_items, sizeof(WorkItem) * n));
+        e->sa_cap = n;
+    }
+    if (!e->sa_counters) CUDA_TRY(cudaMalloc(&e->sa_counters, sizeof(Counters)));
+    std::vector<WorkItem> items(n);
+    for (int32_t k = 0; k < n; ++k) { items[k].template_id = template_ids[k]; items[k].slot = k; items[k].episode = -1; items[k]._pad = 0; }
+    Counters c{}; c.n_work = n;
+    CUDA_TRY(cudaMemcpyAsync(e->sa_items, items.data(), sizeof(WorkItem) * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(e->sa_counters, &c, sizeof(Counters), cudaMemcpyHostToDevice, st));
+    // traces of standalone runs go to a private pool sized n x trace_cap when requested
+    TracePool priv{};
+    const bool want_trace = trace_n && trace_tick && trace_cap > 0;
+    unsigned long long* d_top = nullptr;
+    if (want_trace) {
+        priv.len = (uint64_t)n * (uint64_t)std::min(trace_cap, e->cfg.trace_cap);
+        CUDA_TRY(cudaMalloc(&priv.n_active, sizeof(int32_t) * priv.len));
+        CUDA_TRY(cudaMalloc(&priv.tick, sizeof(double) * priv.len));
+        CUDA_TRY(cudaMalloc(&d_top, sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemsetAsync(d_top, 0, sizeof(unsigned long long), st));
+        priv.top = d_top;
+    }
+    LookaheadArgs a = make_lookahead_args(e, e->sa_items, e->sa_counters, e->sa_res, false, nullptr);
+    if (want_trace) a.pool = priv;
+    cudaEvent_t ea = e->ev_a[MAX_EVENT_PAIRS - 1], eb = e->ev_b[MAX_EVENT_PAIRS - 1];
+    if (e->ev_pending >= MAX_EVENT_PAIRS - 1) { CUDA_TRY(cudaStreamSynchronize(st)); rc = resolve_events(e); if (rc) return rc; }
+    CUDA_TRY(cudaEventRecord(ea, st));
+    lookahead_kernel_for(e->nt)<<<e->grid, e->nt, e->smem_bytes, st>>>(a);
+    CUDA_TRY(cudaEventRecord(eb, st));
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> jct(n), comm(n), comp(n);
+    std::vector<int32_t> nt(n), stt(n);
+    std::vector<int64_t> off(n);
+    CUDA_TRY(cudaMemcpyAsync(jct.data(), e->sa_res.jct, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(comm.data(), e->sa_res.comm, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(comp.data(), e->sa_res.comp, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nt.data(), e->sa_res.n_ticks, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(stt.data(), e->sa_res.status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(off.data(), e->sa_res.trace_off, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (kernel_ms_out) CUDA_TRY(cudaEventElapsedTime(kernel_ms_out, ea, eb));
+    for (int32_t k = 0; k < n; ++k) {
+        results[k].jct = jct[k]; results[k].comm = comm[k]; results[k].comp = comp[k];
+        results[k].n_ticks = nt[k]; results[k].status = stt[k];
+    }
+    if (want_trace) {
+        for (int32_t k = 0; k < n; ++k) {
+            if (off[k] < 0) continue;
+            const int32_t m = std::min(std::min(nt[k], trace_cap), e->cfg.trace_cap);
+            CUDA_TRY(cudaMemcpy(trace_n + (size_t)k * trace_cap, priv.n_active + off[k], sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(trace_tick + (size_t)k * trace_cap, priv.tick + off[k], sizeof(double) * m, cudaMemcpyDeviceToHost));
+        }
+        cudaFree(priv.n_active); cudaFree(priv.tick); cudaFree(d_top);
+    }
+    return RAMP_OK;
+}
+
+int64_t ramp_launch_count(ramp_engine_t* e) { return e ? e->launches : 0; }
+
+int ramp_get_lookahead_kernel_time(ramp_engine_t* e, double* total_ms, int64_t* launches, int64_t* work_items,
+                                   int64_t* alg_bytes, int32_t reset) {
+    if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    int rc = resolve_events(e);
+    if (rc) return rc;
+    MemoStats s{};
+    CUDA_TRY(cudaMemcpy(&s, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost));
+    if (total_ms) *total_ms = e->la_ms_total;
+    if (launches) *launches = e->la_launches;
+    if (work_items) *work_items = (int64_t)(s.lookaheads - e->la_items_base);
+    if (alg_bytes) *alg_bytes = (int64_t)(s.alg_bytes - e->la_bytes_base);
+    if (reset) { e->la_ms_total = 0.0; e->la_launches = 0; e->la_items_base = s.lookaheads; e->la_bytes_base = s.alg_bytes; }
+    return RAMP_OK;
+}
+
+}  // extern "C"
