@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched RAMP cluster simulator hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # product arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on all host threads
+
+One bench "step" = one batched env-step: every one of the B episodes takes one agent decision, i.e. one
+``RampClusterEnvironment.step(action)`` plus the ``step(Action())`` calls until the next job is queued
+(RJPE:300-420).  Episodes are scripted rollouts of L decisions each (ddls_b200/workload.py); every L steps
+all episodes are reset (which clears the per-episode memo tables like RCE:269-275), so the timed region
+contains resets, memo misses (lookaheads executed) and memo hits in the proportion a real rollout has.
+
+Prints ONE JSON line (rank 0).  See README / DESIGN.md for the field definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'env_steps_per_sec'
+UNIT = 'env-steps/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=32)
+    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='cfg3-resnet50-64w')
+    ap.add_argument('--episodes', type=int, default=0, help='episodes per GPU (0 = the config\'s batch size)')
+    ap.add_argument('--segment', type=int, default=8, help='L: agent decisions per scripted episode')
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--cpu-sample', type=int, default=0, help='episodes in the CPU baseline sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--memo-mode', type=int, default=0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0, period=0.2):
+        super().__init__(daemon=True)
+        self.gpu_index, self.period = gpu_index, period
+        self.samples, self._stop_evt = [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+                                      str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def ncu_traffic_per_launch():
+    """dram bytes per lookahead-kernel launch from the committed ncu summary of this bench command, if any."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_lookahead_summary.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get('dram_bytes_per_launch')
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------
+def oracle_jcts(templates):
+    from oracle import oracle
+    oracle.build()
+    return [oracle.run_lookahead(t, trace_cap=0)['jct'] for t in templates]
+
+
+def run_reference_arm(args, rank, world):
+    """The CPU arm: the oracle port (oracle/ramp_oracle.c, the C restatement of the reference's algorithm; the
+    Python reference itself cannot travel to the GPU box) on all host threads, same scripted workload."""
+    if rank != 0:
+        return
+    import ctypes as C
+    from oracle import oracle
+    from ddls_b200 import workload
+    oracle.build()
+    L = args.segment
+    cores = os.cpu_count() or 1
+    # bounded sample: S episodes per step-group, sized from a probe so that the whole run takes ~20-40 s
+    probe_S = min(64, max(cores, 8))
+    wl = workload.generate(args.config, oracle_jcts, n_episodes=probe_S, n_steps=L, seed=args.seed)
+    t0 = time.perf_counter()
+    _oracle_segment(oracle, wl, cores)
+    probe = time.perf_counter() - t0
+    n_groups = max(1, (args.warmup + args.steps + L - 1) // L)
+    budget = 30.0
+    S = int(min(workload.CONFIGS[args.config]['n_episodes'], max(probe_S, probe_S * budget / max(probe * n_groups, 1e-6))))
+    S = max(cores, (S // cores) * cores)
+    wl = workload.generate(args.config, oracle_jcts, n_episodes=S, n_steps=L, seed=args.seed)
+    # warm-up groups, then timed groups; one "step" of this arm = S episode-steps
+    w_groups = (args.warmup + L - 1) // L
+    k_groups = max(1, (args.steps + L - 1) // L)
+    for _ in range(w_groups):
+        _oracle_segment(oracle, wl, cores)
+    t0 = time.perf_counter()
+    for _ in range(k_groups):
+        _oracle_segment(oracle, wl, cores)
+    dt = time.perf_counter() - t0
+    steps_done = k_groups * L
+    value = S * steps_done / dt
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps_done, 'warmup': w_groups * L,
+            'ms_per_step': dt / steps_done * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': args.config, 'episodes_per_step': S, 'segment': L, 'note':
+                       'CPU arm: oracle/ramp_oracle.c (C port of the reference algorithm) on all host threads; '
+                       'bounded sample of the same scripted workload; env-steps/s is per-episode and extrapolates linearly'},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': f'{S} episodes x {steps_done} env-steps ({dt:.1f} s)'},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def _oracle_segment(oracle, wl, n_threads):
+    """Runs every episode of the workload for its L decisions (+ empty steps) through the oracle env, threaded."""
+    import ctypes as C
+    L, B = wl.n_steps, wl.n_episodes
+    lib = oracle.lib()
+    ctemps = (oracle.CLoweredJob * len(wl.templates))(*[oracle.to_c(t) for t in wl.templates])
+    keep = [oracle.to_c(t) for t in wl.templates]   # keep numpy arrays alive
+    # script: per episode the oracle env needs explicit Action() steps between decisions; orc_run_scripted_batch
+    # takes a flat script, so expand each decision into (decision, then up to `pad` empty steps) conservatively:
+    # instead use the dedicated fused driver below
+    tid = np.ascontiguousarray(wl.actions['template_id'].T, dtype=np.int32)          # [B, L]
+    mount = np.zeros((B, L), dtype=oracle.MOUNT_DTYPE)
+    for f in ('max_acceptable_jct', 'part_op_mem', 'part_dep_size', 'flow_size', 'n_mounted_workers', 'n_mounted_channels'):
+        mount[f] = wl.actions[f].T
+    arr = np.ascontiguousarray(wl.arrivals, dtype=oracle.ARRIVAL_DTYPE)
+    n_models = max(wl.template_model) + 1
+    rc = lib.orc_run_scripted_rjpe_batch(ctemps, len(wl.templates), B, L, tid.ctypes.data, mount.ctypes.data,
+                                         arr.ctypes.data, L, float('inf'), wl.shape.n_workers, n_models, 1025,
+                                         None, None, n_threads)
+    assert rc == 0, rc
+    del keep
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_b200_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ddls_b200 import engine, workload
+
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl b200 needs a CUDA device; there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    cfg = workload.CONFIGS[args.config]
+    B = args.episodes or cfg['n_episodes']
+    L = args.segment
+
+    # ---- build templates, get their JCTs from the CUDA path, script the episodes ----
+    eng = engine.RampEngine(n_episodes=B, n_cluster_workers=int(np.prod(cfg['shape'])), max_jobs=L, device=local_rank,
+                            memo_mode=args.memo_mode, trace_cap=4096)
+    tmap = {}
+
+    def engine_jcts(templates):
+        for i, t in enumerate(templates):
+            tmap[i] = eng.register_template(t)
+        res, _ = eng.run_lookaheads([tmap[i] for i in range(len(templates))])
+        assert (res['status'] == 0).all()
+        return res['jct']
+
+    wl = workload.generate(args.config, engine_jcts, n_episodes=B, n_steps=L, seed=args.seed + 1000 * rank)
+    actions_host = []
+    for p in range(L):
+        a = wl.actions[p].copy()
+        placed = a['template_id'] >= 0
+        a['template_id'][placed] = np.array([tmap[int(t)] for t in a['template_id'][placed]], dtype=np.int32)
+        actions_host.append(a)
+    # pinned host copies (e2e path) and device-resident copies (value path)
+    pinned, on_dev = [], []
+    for a in actions_host:
+        t = torch.from_numpy(a.view(np.uint8).reshape(B, -1).copy()).pin_memory()
+        pinned.append(t)
+        on_dev.append(t.cuda())
+    arrivals = wl.arrivals
+    stats_dev = torch.empty((B, engine.STEP_STATS_LEN), dtype=torch.float64, device='cuda')
+    ncs_dev = torch.empty(B, dtype=torch.int32, device='cuda')
+    stats_pinned = torch.empty((B, engine.STEP_STATS_LEN), dtype=torch.float64).pin_memory()
+    ep_dev = torch.empty((B, engine.EP_LEN), dtype=torch.float64, device='cuda')
+    gathered = torch.empty((world * B, engine.EP_LEN), dtype=torch.float64, device='cuda') if world > 1 else None
+    ext = torch.cuda.ExternalStream(eng.stream, device=torch.device('cuda', local_rank))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_metrics():
+        # one all-gather of the per-episode metric rows per batch step; episodes shard with no
+        # other exchange
+        eng.export_episode_state_to(ep_dev.data_ptr())
+        if world > 1:
+            ev = torch.cuda.Event()
+            ev.record(ext)
+            torch.cuda.current_stream().wait_event(ev)
+            dist.all_gather_into_tensor(gathered, ep_dev)
+
+    def device_step(s):
+        p = s % L
+        if p == 0:
+            eng.reset(arrivals)
+        eng.step_device(on_dev[p].data_ptr(), True, stats_dev.data_ptr(), ncs_dev.data_ptr())
+        gather_metrics()
+
+    def host_step(s):
+        p = s % L
+        if p == 0:
+            eng.reset(arrivals)
+        # HOST buffers in, HOST stats out: H2D + D2H inside the call (ramp_step_host)
+        rc = eng._L.ramp_step_host(eng._h, pinned[p].data_ptr(), 1, stats_pinned.data_ptr(), None)
+        if rc != 0:
+            engine._check(rc)
+        gather_metrics()
+        return float(stats_pinned[0, engine.SS['step_end_time']])
+
+    W, K = args.warmup, args.steps
+    # ---- value: inputs resident in HBM ----
+    for s in range(W):
+        device_step(s)
+    barrier()
+    eng.lookahead_kernel_time(reset=True)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(ext)
+    for s in range(W, W + K):
+        device_step(s)
+    e1.record(ext)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count - launches0
+    kt = eng.lookahead_kernel_time(reset=True)
+    memo = eng.memo_stats()
+    eng.check_status()
+    # the episode resets inside the loop synchronise the stream, so wall time ~ device time; use the larger
+    elapsed_ms = max(dev_ms, 0.0)
+    el = torch.tensor([elapsed_ms, t_wall * 1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed_ms, wall_ms = float(el[0]), float(el[1])
+    value = world * B * K / (elapsed_ms / 1e3)
+
+    # ---- e2e: through the host-buffer C-ABI call ----
+    for s in range(W):
+        host_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        host_step(s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / float(e2e_t[0])
+    eng.check_status()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        la_ms = kt['total_ms']
+        achieved = (kt['algorithmic_bytes'] / 1e9) / (la_ms / 1e3) if la_ms > 0 else 0.0
+        traffic = ncu_traffic_per_launch()
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': args.config, 'episodes_per_gpu': B, 'segment': L,
+                       'cluster': 'x'.join(map(str, cfg['shape'])) + ' RAMP', 'degrees': list(cfg['degrees']),
+                       'templates': [[t.n_ops, t.n_deps] for t in wl.templates], 'memo_mode': args.memo_mode,
+                       'agent': 'random partition degree + aligned first-fit blocks (stand-in for the PAC-ML GNN policy)',
+                       'l2': 'per-CTA lookahead scratch working set (%.1f GB) exceeds the 126 MB L2; no explicit flush'
+                             % (eng.n_episodes and _scratch_gb(wl)),
+                       'parallelism': f'episodes sharded x{world}, one NCCL all-gather of episode metrics per step' if world > 1
+                                      else 'single GPU'},
+            'e2e': {'value': e2e_value, 'unit': UNIT,
+                    'h2d_bytes_per_step': int(B * engine.ACTION_DTYPE.itemsize + (arrivals.nbytes / L)),
+                    'd2h_bytes_per_step': int(B * engine.STEP_STATS_LEN * 8)},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'kernel': 'ramp_lookahead_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak if peak else None, 'traffic': traffic, 'peak_source': peak_src,
+                         'kernel_ms_per_launch': la_ms / max(kt['launches'], 1), 'kernel_launches': kt['launches'],
+                         'lookaheads': kt['work_items'], 'kernel_share_of_step': la_ms / elapsed_ms if elapsed_ms else None,
+                         'algorithmic_bytes_per_launch': kt['algorithmic_bytes'] / max(kt['launches'], 1)},
+            'memo': {'lookups': memo['lookups'], 'hits': memo['hits'],
+                     'hit_rate': memo['hits'] / memo['lookups'] if memo['lookups'] else None},
+            'clocks': clocks, 'wall_ms_per_step': wall_ms / K,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline(args, wl)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _scratch_gb(wl):
+    t = max(wl.templates, key=lambda t: t.n_deps)
+    return (20 * t.n_ops + 16 * t.n_deps) * 148 * 8 / 1e9
+
+
+def cpu_baseline(args, wl_gpu):
+    """Oracle port timed on this box's host cores on a bounded sample of the same workload (~10-30 s of CPU work)."""
+    from oracle import oracle
+    from ddls_b200 import workload
+    oracle.build()
+    cores = os.cpu_count() or 1
+    L = args.segment
+    S0 = max(cores, 16)
+    wl = workload.generate(args.config, oracle_jcts, n_episodes=S0, n_steps=L, seed=args.seed)
+    t0 = time.perf_counter()
+    _oracle_segment(oracle, wl, cores)
+    probe = time.perf_counter() - t0
+    S = int(max(S0, min(wl_gpu.n_episodes, S0 * 15.0 / max(probe, 1e-6))))
+    S = max(cores, (S // cores) * cores)
+    wl = workload.generate(args.config, oracle_jcts, n_episodes=S, n_steps=L, seed=args.seed)
+    t0 = time.perf_counter()
+    _oracle_segment(oracle, wl, cores)
+    dt = time.perf_counter() - t0
+    return {'value': S * L / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'{S} episodes x {L} env-steps of {args.config} in {dt:.1f} s wall on {cores} threads (oracle/ramp_oracle.c)'}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+    else:
+        run_b200_arm(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

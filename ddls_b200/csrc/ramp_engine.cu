@@ -507,6 +507,15 @@ int ramp_episode_state_device(ramp_engine_t* e, double** d_out) {
     return RAMP_OK;
 }
 
+int ramp_export_episode_state_to(ramp_engine_t* e, double* d_dst) {
+    if (!e || !d_dst) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    const int B = e->cfg.n_episodes;
+    ramp_export_episode_state_kernel<<<(B + 127) / 128, 128, 0, e->stream>>>(e->ep, d_dst);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAMP_OK;
+}
+
 int ramp_get_episode_state(ramp_engine_t* e, double* out) {
     double* d = nullptr;
     int rc = ramp_episode_state_device(e, &d);

@@ -93,6 +93,7 @@ def load_library():
     L.ramp_get_job_records.argtypes = [C.c_void_p, C.c_void_p]
     L.ramp_get_episode_state.argtypes = [C.c_void_p, C.c_void_p]
     L.ramp_episode_state_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.ramp_export_episode_state_to.argtypes = [C.c_void_p, C.c_void_p]
     L.ramp_get_memo_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ramp_get_last_lookahead.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.ramp_run_lookaheads.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -103,8 +104,8 @@ def load_library():
                                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
     for name in ('ramp_engine_create', 'ramp_engine_destroy', 'ramp_register_template', 'ramp_template_count',
                  'ramp_reset', 'ramp_step_host', 'ramp_step_device', 'ramp_sync', 'ramp_check_status',
-                 'ramp_get_job_records', 'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_get_memo_stats',
-                 'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_get_lookahead_kernel_time'):
+                 'ramp_get_job_records', 'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_export_episode_state_to',
+                 'ramp_get_memo_stats', 'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_get_lookahead_kernel_time'):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -113,7 +114,8 @@ def load_library():
 EXPORTED_SYMBOLS = ['ramp_last_error', 'ramp_engine_create', 'ramp_engine_destroy', 'ramp_engine_stream',
                     'ramp_register_template', 'ramp_template_count', 'ramp_reset', 'ramp_step_host',
                     'ramp_step_device', 'ramp_sync', 'ramp_check_status', 'ramp_get_job_records',
-                    'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_get_memo_stats',
+                    'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_export_episode_state_to',
+                    'ramp_get_memo_stats',
                     'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_launch_count',
                     'ramp_get_lookahead_kernel_time']
 
@@ -226,6 +228,10 @@ class RampEngine:
         p = C.c_void_p()
         _check(self._L.ramp_episode_state_device(self._h, C.byref(p)))
         return p.value
+
+    def export_episode_state_to(self, d_dst_ptr):
+        """Writes [n_episodes, EP_LEN] f64 into a caller-owned device buffer (async on the engine stream)."""
+        _check(self._L.ramp_export_episode_state_to(self._h, d_dst_ptr))
 
     def memo_stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

@@ -187,6 +187,9 @@ enum { RAMP_EP_TIME = 0, RAMP_EP_NEXT_ARRIVAL, RAMP_EP_NUM_ARRIVED, RAMP_EP_NUM_
 int ramp_get_episode_state(ramp_engine_t* eng, double* out);
 /* device pointer of the same table (for NCCL all-gather of episode metrics without a host bounce) */
 int ramp_episode_state_device(ramp_engine_t* eng, double** d_out);
+/* writes the table into a caller-owned DEVICE buffer [n_episodes][RAMP_EP_LEN] (asynchronous on the engine stream),
+ * e.g. a torch tensor that is then all-gathered over NCCL */
+int ramp_export_episode_state_to(ramp_engine_t* eng, double* d_dst);
 /* memo statistics since the last reset: lookups, hits, lookaheads executed */
 int ramp_get_memo_stats(ramp_engine_t* eng, int64_t* lookups, int64_t* hits, int64_t* lookaheads);
 /* the lookahead (memoised or fresh) used by episode `episode`'s most recent mount: result + trace

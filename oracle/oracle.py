@@ -113,6 +113,8 @@ def lib():
         L.orc_run_scripted_batch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_int32]
+        L.orc_run_scripted_rjpe_batch.restype = C.c_int
+        L.orc_run_scripted_rjpe_batch.argtypes = L.orc_run_scripted_batch.argtypes
         _lib = L
     return _lib
 
