@@ -142,7 +142,7 @@ int resolve_events(ramp_engine* e) {
 int ensure_scratch(ramp_engine* e) {
     const uint64_t trace_bytes = align_up((uint64_t)e->cfg.trace_cap * 12, 16);
     const uint64_t stride = align_up(std::max<uint64_t>(e->max_scratch, 16), 256) + align_up(trace_bytes, 256);
-    const size_t smem = sizeof(uint32_t) * ((size_t)e->max_w * 2 + (size_t)e->max_c);
+    const size_t smem = sizeof(uint32_t) * ((size_t)e->max_w + (size_t)e->max_c);
     if (smem > 200 * 1024)
         return set_error(RAMP_ERR_CAPACITY, "a template needs %zu B of shared memory for its worker/channel key arrays (max 200 KiB)", smem);
     if (smem != e->smem_bytes || e->grid == 0) {
@@ -341,14 +341,30 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     for (auto& x : op_cost) x = x + 0.0;   // -0.0 -> +0.0 so the u64 bit pattern orders like the value
     for (auto& x : dep_rt) x = x + 0.0;
 
+    // ---- records in the layout the tick loop streams (see TemplateDev) ----
+    struct OpRec { double cost; uint32_t key; uint32_t worker; };
+    static_assert(sizeof(OpRec) == 16, "op record must be 16 bytes");
+    std::vector<OpRec> op_rec(N);
+    std::vector<int32_t> row_by_key((size_t)(N + 1) * 2, 0);
+    for (int32_t i = 0; i < N; ++i) {
+        op_rec[i] = OpRec{op_cost[i], op_key[i], (uint32_t)j->op_worker[i]};
+        row_by_key[(size_t)op_key[i] * 2] = j->row_ptr[i];
+        row_by_key[(size_t)op_key[i] * 2 + 1] = j->row_ptr[i + 1] - j->row_ptr[i];
+    }
+    std::vector<unsigned long long> dep_km(E);
+    std::vector<int32_t> dst_by_key((size_t)E + 1, 0);
+    for (int32_t k = 0; k < E; ++k) {
+        dep_km[k] = (unsigned long long)dep_key[k] | ((unsigned long long)j->dep_channel[k] << 32)
+                    | ((unsigned long long)(j->dep_is_flow[k] ? 1 : 0) << 48);
+        dst_by_key[dep_key[k]] = j->dep_dst[k];
+    }
+
     // ---- pack one blob ----
     struct Seg { const void* p; size_t bytes; size_t off; };
-    Seg segs[11] = {
-        {op_cost.data(), sizeof(double) * (size_t)N, 0}, {op_key.data(), sizeof(uint32_t) * (size_t)N, 0},
-        {j->op_worker, sizeof(uint16_t) * (size_t)N, 0}, {j->op_n_parents, sizeof(uint16_t) * (size_t)N, 0},
-        {j->row_ptr, sizeof(int32_t) * (size_t)(N + 1), 0}, {j->dep_dst, sizeof(int32_t) * (size_t)E, 0},
-        {dep_rt.data(), sizeof(double) * (size_t)E, 0}, {dep_key.data(), sizeof(uint32_t) * (size_t)E, 0},
-        {j->dep_channel, sizeof(uint16_t) * (size_t)E, 0}, {j->dep_is_flow, sizeof(uint8_t) * (size_t)E, 0},
+    Seg segs[7] = {
+        {op_rec.data(), sizeof(OpRec) * (size_t)N, 0}, {j->op_n_parents, sizeof(uint16_t) * (size_t)N, 0},
+        {row_by_key.data(), sizeof(int32_t) * row_by_key.size(), 0}, {dep_km.data(), sizeof(unsigned long long) * (size_t)E, 0},
+        {dep_rt.data(), sizeof(double) * (size_t)E, 0}, {dst_by_key.data(), sizeof(int32_t) * dst_by_key.size(), 0},
         {src.data(), sizeof(int32_t) * src.size(), 0}};
     size_t total = 0;
     for (auto& s : segs) { s.off = total; total += align_up(std::max<size_t>(s.bytes, 1), 256); }
@@ -371,12 +387,10 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     d.num_training_steps = j->num_training_steps; d.model_id = j->model_id; d.degree = j->degree;
     d.n_src = (int32_t)src.size(); d.canon_id = canon;
     d.trace_need = (int32_t)std::min<int64_t>((int64_t)N + E + 1, e->cfg.trace_cap);
-    d.op_cost = (const double*)(base + segs[0].off); d.op_key = (const uint32_t*)(base + segs[1].off);
-    d.op_worker = (const uint16_t*)(base + segs[2].off); d.op_n_parents = (const uint16_t*)(base + segs[3].off);
-    d.row_ptr = (const int32_t*)(base + segs[4].off); d.dep_dst = (const int32_t*)(base + segs[5].off);
-    d.dep_run_time = (const double*)(base + segs[6].off); d.dep_key = (const uint32_t*)(base + segs[7].off);
-    d.dep_channel = (const uint16_t*)(base + segs[8].off); d.dep_is_flow = (const uint8_t*)(base + segs[9].off);
-    d.src_ops = (const int32_t*)(base + segs[10].off);
+    d.op_rec = (const int4*)(base + segs[0].off); d.op_n_parents = (const uint16_t*)(base + segs[1].off);
+    d.op_row_by_key = (const int2*)(base + segs[2].off); d.dep_km = (const unsigned long long*)(base + segs[3].off);
+    d.dep_rt = (const double*)(base + segs[4].off); d.dep_dst_by_key = (const int32_t*)(base + segs[5].off);
+    d.src_ops = (const int32_t*)(base + segs[6].off);
     d.scratch_bytes = scratch_bytes_for(N, E);
     d.algorithmic_bytes_static = 20ull * (uint64_t)N + 19ull * (uint64_t)E + 24ull;
     const int32_t id = (int32_t)e->templates.size();

@@ -20,23 +20,28 @@ namespace ramp {
 // ---------------------------------------------------------------------------------------------------
 // HBM layout
 
-// One registered lowered job.  All arrays live in one device allocation (256 B aligned segments) and are
-// read-only for the kernels (read through the non-coherent path).
+// One registered lowered job, in the layout the tick loop streams.  All arrays live in one device allocation
+// (256 B aligned segments) and are read-only for the kernels.
+//
+// Priorities are pre-ranked on the host into unique u32 keys (larger wins): sorting by (priority desc, index asc)
+// reproduces "iterate in sorted() order, replace only on strictly greater priority" (RCE:56-66, RCE:672-685), so
+// the per-worker / per-channel arg-max is one 32-bit shared-memory atomicMax per ready item.  Everything a
+// ready item needs every tick is packed next to its key, so frontier entries are self-contained records and
+// the loop never gathers through an index:
+//   op record  = { f64 remaining, u32 key, u32 worker }                       (16 B)
+//   dep record = { f64 remaining } + { u32 key, u16 channel, u16 is_flow }    (8 B + 8 B, SoA)
+// What is only needed when an item completes (child op, out-edge range) is looked up by key.
 struct TemplateDev {
     int32_t n_ops, n_deps, n_workers, n_channels;
     int32_t num_training_steps, model_id, degree, n_src;
     int32_t canon_id;           // id of the first registered byte-identical template (exact memo key)
     int32_t trace_need;         // min(N + E + 1, trace_cap): upper bound on ticks (>= 1 op or dep completes per tick)
-    const double*   op_cost;      // [N]
-    const uint32_t* op_key;       // [N] unique rank key: larger wins; == argmax priority, lowest index on ties (RCE:56-66)
-    const uint16_t* op_worker;    // [N]
-    const uint16_t* op_n_parents; // [N]
-    const int32_t*  row_ptr;      // [N+1]
-    const int32_t*  dep_dst;      // [E]
-    const double*   dep_run_time; // [E]
-    const uint32_t* dep_key;      // [E] unique rank key (RCE:672-685)
-    const uint16_t* dep_channel;  // [E]
-    const uint8_t*  dep_is_flow;  // [E]
+    const int4*     op_rec;       // [N]   by op index: {cost.lo, cost.hi, key, worker}: the record pushed when the op becomes ready
+    const uint16_t* op_n_parents; // [N]   by op index (JOB:508-523)
+    const int2*     op_row_by_key;// [N+1] by op key: {first out-edge, out-degree} (CSR row of the op holding that key)
+    const unsigned long long* dep_km;  // [E] by dep index (CSR order): key | channel << 32 | is_flow << 48
+    const double*   dep_rt;       // [E]   by dep index: init_run_time (RCE:542-560)
+    const int32_t*  dep_dst_by_key; // [E+1] by dep key: child op index
     const int32_t*  src_ops;      // [n_src] ops with in-degree 0: the initial ops_ready (JOB:474-481)
     uint64_t scratch_bytes;       // dynamic state one running lookahead of this template needs
     uint64_t algorithmic_bytes_static; // 20 N + 19 E + 24, + 12 T added per run
@@ -121,36 +126,35 @@ __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x
 
 // dynamic state of one running lookahead, carved out of the CTA's scratch slab
 struct ScratchView {
-    double*   op_rem;           // [N] remaining_run_time of ready/ticking ops (JOB:555), written when an op becomes ready
-    double*   dep_rem;          // [E] remaining_run_time of ready deps (JOB:561), written when a dep becomes ready
-    uint32_t* par_done;         // [N] len(parent_deps_completed) JOB:530
-    int32_t*  ops_list[2];      // ops_ready frontier (ping-pong)
-    int32_t*  deps_list[2];     // deps_ready frontier (ping-pong)
-    int32_t*  tr_n;             // [trace_cap] temp trace
-    double*   tr_tick;          // [trace_cap]
+    uint32_t* par_done;              // [N] len(parent_deps_completed) JOB:530
+    int4*     ops[2];                // ops_ready frontier records (ping-pong, compacted every tick; it is small)
+    unsigned long long* dep_km[2];   // deps_ready frontier: key/channel/flow words, 0 = completed (in place, lazily compacted)
+    double*   dep_rem[2];            // deps_ready frontier: remaining_run_time (JOB:561)
+    int32_t*  tr_n;                  // [trace_cap] temp trace
+    double*   tr_tick;               // [trace_cap]
 };
 
 __host__ __device__ inline uint64_t scratch_bytes_for(int32_t N, int32_t E) {
     uint64_t b = 0;
-    b += align_up((uint64_t)N * 8, 16);
-    b += align_up((uint64_t)E * 8, 16);
     b += align_up((uint64_t)N * 4, 16);
-    b += 2 * align_up((uint64_t)N * 4, 16);
-    b += 2 * align_up((uint64_t)E * 4, 16);
+    b += 2 * align_up((uint64_t)N * 16, 16);
+    b += 2 * align_up((uint64_t)E * 8, 16);
+    b += 2 * align_up((uint64_t)E * 8, 16);
     return b;
 }
 
-__device__ inline ScratchView carve(unsigned char* base, int32_t N, int32_t E, uint64_t trace_region_off) {
+__device__ inline ScratchView carve(unsigned char* base, int32_t N, int32_t E, uint64_t trace_region_off, int32_t trace_cap) {
     ScratchView v;
     uint64_t o = 0;
-    v.op_rem = (double*)(base + o);        o += align_up((uint64_t)N * 8, 16);
-    v.dep_rem = (double*)(base + o);       o += align_up((uint64_t)E * 8, 16);
-    v.par_done = (uint32_t*)(base + o);    o += align_up((uint64_t)N * 4, 16);
-    v.ops_list[0] = (int32_t*)(base + o);  o += align_up((uint64_t)N * 4, 16);
-    v.ops_list[1] = (int32_t*)(base + o);  o += align_up((uint64_t)N * 4, 16);
-    v.deps_list[0] = (int32_t*)(base + o); o += align_up((uint64_t)E * 4, 16);
-    v.deps_list[1] = (int32_t*)(base + o); o += align_up((uint64_t)E * 4, 16);
+    v.par_done = (uint32_t*)(base + o);              o += align_up((uint64_t)N * 4, 16);
+    v.ops[0] = (int4*)(base + o);                    o += align_up((uint64_t)N * 16, 16);
+    v.ops[1] = (int4*)(base + o);                    o += align_up((uint64_t)N * 16, 16);
+    v.dep_km[0] = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
+    v.dep_km[1] = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
+    v.dep_rem[0] = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
+    v.dep_rem[1] = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
     v.tr_tick = (double*)(base + trace_region_off);
+    v.tr_n = (int32_t*)(v.tr_tick + trace_cap);
     return v;
 }
 
@@ -201,36 +205,39 @@ __device__ __forceinline__ int warp_sum_i32(int v) {
 // ---------------------------------------------------------------------------------------------------
 // _run_lookahead (RCE:379-467): one CTA per lookahead, persistent CTAs pull work items.
 //
-// Per tick (letters as in SURVEY.md 3.3):
-//   A  per-worker arg-max over ready ops         -> atomicMax of unique rank keys into smem wkey[]
-//   C  any ready non-flow dep?                    -> __syncthreads_or
-//   D  per-channel arg-max over ready deps        -> atomicMax into smem ckey[]   (skipped if C)
-//   B/D min remaining over the winners           -> warp shuffles + one smem atomicMin per warp (u64 bit pattern
-//                                                   of non-negative doubles is order preserving)
-//   E  tick = min(t_op, t_comm)
-//   G  winners: rem -= min(tick, rem); == 0 -> completed, out-edges appended to the next dep frontier
-//   H  deps of the pre-tick snapshot: same; completed -> atomicAdd on the child's parent counter, == n_parents
-//      -> child appended to the next op frontier
-//   I,J thread 0 accumulates t / comm / comp and the trace in tick order
+// Per tick, three phases separated by block barriers (letters as in SURVEY.md 3.3):
+//   P1  A  per-worker arg-max over ready ops   -> atomicMax of rank keys into smem wkey[]
+//       C  any ready non-flow dep?              -> folded into the barrier (__syncthreads_or)
+//       D  per-channel arg-max over ready deps  -> atomicMax into smem ckey[] (speculative; unused if C)
+//   P2  B/D.iii  min remaining over the winners -> warp shuffles + one smem atomicMin per warp (the u64 bit pattern
+//                                                   of a non-negative double is order preserving)
+//   P3  E  tick = min(t_op, t_comm)
+//       G  winners: rem -= min(tick, rem); == 0 -> completed: its CSR row of dep records is copied (coalesced, by the
+//          whole warp) to the tail of the dep frontier -- visible from the next tick on, i.e. the RCE:429 snapshot
+//       H  every dep of the snapshot (only the non-flows if C): same; completed -> marked dead in place, atomicAdd on
+//          the child's parent counter, == n_parents -> child's op record appended to the next op frontier
+//       I,J  thread 0 accumulates t / comm / comp and the trace in tick order
+// The dep frontier is updated in place (a tick in which flows are frozen writes nothing) and compacted only when
+// more than half of it is dead.
 template <int NT>
 __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* wkey = reinterpret_cast<uint32_t*>(smem_raw);        // [w_cap] best rank key per worker this tick
     uint32_t* ckey = wkey + a.w_cap;                               // [c_cap] best rank key per channel this tick
-    int32_t* doneq = reinterpret_cast<int32_t*>(ckey + a.c_cap);   // [w_cap] ops completed this tick (<= 1 per worker)
 
     __shared__ int s_work;
-    __shared__ int s_n_ops[2], s_n_deps[2];
-    __shared__ int s_doneq_n;
+    __shared__ int s_n_ops[2];            // op frontier sizes (ping-pong)
+    __shared__ int s_tail[2];             // dep frontier append tail of the current tick (by tick parity)
+    __shared__ int s_dead[2];             // deps completed in the current tick (by tick parity)
+    __shared__ int s_ctail;               // compaction cursor
     __shared__ int s_ops_completed, s_deps_completed;
     __shared__ unsigned long long s_min_op[2], s_min_dep[2];
     __shared__ int s_n_active[2];
-    __shared__ int s_stop;                                         // 0 continue, 1 finished, 2 error
+    __shared__ long long s_trace_off;
+    __shared__ int s_n_rec;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
-    constexpr int NW = NT / 32;
 
     unsigned char* slab = a.scratch + (uint64_t)blockIdx.x * a.scratch_stride;
     const uint64_t trace_region = a.scratch_stride - align_up((uint64_t)a.trace_cap * 12, 16);
@@ -243,35 +250,26 @@ __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs 
         const WorkItem item = a.items[wi];
         const TemplateDev& T = a.templates[item.template_id];
         const int N = T.n_ops, E = T.n_deps, W = T.n_workers, C = T.n_channels;
-        ScratchView sv = carve(slab, N, E, trace_region);
-        sv.tr_n = reinterpret_cast<int32_t*>(sv.tr_tick + a.trace_cap);
+        const ScratchView sv = carve(slab, N, E, trace_region, a.trace_cap);
 
-        const double* __restrict__ op_cost = T.op_cost;
-        const uint32_t* __restrict__ op_key = T.op_key;
-        const uint16_t* __restrict__ op_worker = T.op_worker;
-        const uint16_t* __restrict__ op_n_parents = T.op_n_parents;
-        const int32_t* __restrict__ row_ptr = T.row_ptr;
-        const int32_t* __restrict__ dep_dst = T.dep_dst;
-        const double* __restrict__ dep_run_time = T.dep_run_time;
-        const uint32_t* __restrict__ dep_key = T.dep_key;
-        const uint16_t* __restrict__ dep_channel = T.dep_channel;
-        const uint8_t* __restrict__ dep_is_flow = T.dep_is_flow;
+        const int4* __restrict__ t_op_rec = T.op_rec;
+        const uint16_t* __restrict__ t_n_parents = T.op_n_parents;
+        const int2* __restrict__ t_row_by_key = T.op_row_by_key;
+        const unsigned long long* __restrict__ t_dep_km = T.dep_km;
+        const double* __restrict__ t_dep_rt = T.dep_rt;
+        const int32_t* __restrict__ t_dst_by_key = T.dep_dst_by_key;
 
         // ---- init (JOB:432-484) ----
         for (int i = tid; i < N; i += NT) sv.par_done[i] = 0u;
         for (int i = tid; i < W; i += NT) wkey[i] = 0u;
         for (int i = tid; i < C; i += NT) ckey[i] = 0u;
-        for (int k = tid; k < T.n_src; k += NT) {
-            const int op = __ldg(&T.src_ops[k]);
-            sv.ops_list[0][k] = op;
-            sv.op_rem[op] = __ldg(&op_cost[op]);                  // RCE:1334
-        }
+        for (int k = tid; k < T.n_src; k += NT) sv.ops[0][k] = __ldg(&t_op_rec[__ldg(&T.src_ops[k])]);   // RCE:1334
         if (tid == 0) {
-            s_n_ops[0] = T.n_src; s_n_ops[1] = 0; s_n_deps[0] = 0; s_n_deps[1] = 0;
-            s_doneq_n = 0; s_ops_completed = 0; s_deps_completed = 0;
+            s_n_ops[0] = T.n_src; s_n_ops[1] = 0;
+            s_tail[0] = s_tail[1] = 0; s_dead[0] = s_dead[1] = 0; s_ctail = 0;
+            s_ops_completed = 0; s_deps_completed = 0;
             s_min_op[0] = s_min_op[1] = RAMP_INF_BITS; s_min_dep[0] = s_min_dep[1] = RAMP_INF_BITS;
             s_n_active[0] = s_n_active[1] = 0;
-            s_stop = 0;
         }
         __syncthreads();
 
@@ -279,55 +277,63 @@ __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs 
         double t = 0.0, comm = 0.0, comp = 0.0;
         int tick_no = 0;
         int status = RAMP_ST_OK;
-        int cur = 0;
+        int cur = 0;      // tick parity
+        // frontier buffers are kept as plain pointers that are swapped (no dynamically indexed pointer arrays)
+        int4* ops_a = sv.ops[0];
+        int4* ops_b = sv.ops[1];
+        unsigned long long* fkm = sv.dep_km[0];
+        unsigned long long* fkm_alt = sv.dep_km[1];
+        double* frem = sv.dep_rem[0];
+        double* frem_alt = sv.dep_rem[1];
+        int nF = 0;       // dep frontier length incl. dead entries (uniform across the CTA)
+        int live0 = 0;    // live entries in the dep frontier (uniform)
 
         for (;;) {
             const int nxt = cur ^ 1;
-            const int nO = s_n_ops[cur], nD = s_n_deps[cur];
-            const int32_t* ops = sv.ops_list[cur];      // written in other ticks: coherent loads
-            const int32_t* deps = sv.deps_list[cur];
-            int32_t* ops_n = sv.ops_list[nxt];
-            int32_t* deps_n = sv.deps_list[nxt];
+            const int nO = s_n_ops[cur];
+            const bool big_ops = nO > 32 * NT;            // more op iterations per thread than win_mask has bits
+            const int4* ops = ops_a;
+            int4* ops_n = ops_b;
 
-            // ---- A: highest-priority ready op per worker (RCE:562-590, 44-67) ----
+            // ---- P1: arg-max keys (RCE:562-590, 44-67; RCE:608-629, 665-689) and the non-flow test (RCE:520-540) ----
             for (int k = tid; k < nO; k += NT) {
-                const int i = ops[k];
-                atomicMax(&wkey[__ldg(&op_worker[i])], __ldg(&op_key[i]));
+                const int4 r = ops[k];
+                atomicMax(&wkey[r.w], (uint32_t)r.z);
             }
-            // ---- C: any ready non-flow dep? (RCE:520-540) ----
             int nf = 0;
-            for (int k = tid; k < nD; k += NT) nf |= (__ldg(&dep_is_flow[deps[k]]) == 0);
+            for (int k = tid; k < nF; k += NT) {
+                const unsigned long long km = fkm[k];
+                if (km != 0ull) {
+                    const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
+                    nf |= ((km >> 48) == 0ull);
+                    if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km);
+                }
+            }
             const int any_nf = __syncthreads_or(nf);
 
-            // ---- D: highest-priority ready dep per channel (RCE:608-629, 665-689) ----
-            if (!any_nf) {
-                for (int k = tid; k < nD; k += NT) {
-                    const int e = deps[k];
-                    const uint32_t c = __ldg(&dep_channel[e]);
-                    if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], __ldg(&dep_key[e]));
-                }
-                __syncthreads();
-            }
-
-            // ---- B / D.iii: shortest remaining time over the winners (RCE:592-606, 653-663) ----
+            // ---- P2: shortest remaining time over the winners (RCE:592-606, 653-663) ----
+            uint32_t win_mask = 0u;      // which of this thread's op iterations hold their worker's winner
             {
                 double mo = __longlong_as_double(RAMP_INF_BITS), md = mo;
-                int na = 0;
-                for (int k = tid; k < nO; k += NT) {
-                    const int i = ops[k];
-                    if (wkey[__ldg(&op_worker[i])] == __ldg(&op_key[i])) {
+                int na = 0, j = 0;
+                for (int k = tid; k < nO; k += NT, ++j) {
+                    const int4 r = ops[k];
+                    if (wkey[r.w] == (uint32_t)r.z) {
+                        if (j < 32) win_mask |= 1u << j;
                         ++na;
-                        const double r = sv.op_rem[i];
-                        mo = (r < mo) ? r : mo;
+                        const double rem = __hiloint2double(r.y, r.x);
+                        mo = (rem < mo) ? rem : mo;
                     }
                 }
                 if (!any_nf) {
-                    for (int k = tid; k < nD; k += NT) {
-                        const int e = deps[k];
-                        const uint32_t c = __ldg(&dep_channel[e]);
-                        if (c != RAMP_NO_CHANNEL && ckey[c] == __ldg(&dep_key[e])) {
-                            const double r = sv.dep_rem[e];
-                            md = (r < md) ? r : md;
+                    for (int k = tid; k < nF; k += NT) {
+                        const unsigned long long km = fkm[k];
+                        if (km != 0ull) {
+                            const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
+                            if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km) {
+                                const double rem = frem[k];
+                                md = (rem < md) ? rem : md;
+                            }
                         }
                     }
                 }
@@ -350,84 +356,10 @@ __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs 
             const double tick = (t_comm < t_op) ? t_comm : t_op;
             const int n_active = s_n_active[cur];
 
-            // ---- G: tick the winners (RCE:691-716, JOB:553-557, 492-501) ----
-            int done_local = 0;
-            for (int kb = 0; kb < nO; kb += NT) {
-                const int k = kb + tid;
-                const bool valid = k < nO;
-                int i = 0;
-                bool done = false;
-                if (valid) {
-                    i = ops[k];
-                    if (wkey[__ldg(&op_worker[i])] == __ldg(&op_key[i])) {
-                        const double r = tick_down(sv.op_rem[i], tick);
-                        if (r == 0.0) done = true; else sv.op_rem[i] = r;
-                    }
-                }
-                warp_push(ops_n, &s_n_ops[nxt], valid && !done, i);    // still ready next tick
-                warp_push(doneq, &s_doneq_n, done, i);                  // completed: expand out-edges below
-                done_local += done ? 1 : 0;
-            }
-            // ---- H: tick the deps of the pre-tick snapshot (RCE:718-775, JOB:559-563, 525-536) ----
-            int ddone_local = 0;
-            for (int kb = 0; kb < nD; kb += NT) {
-                const int k = kb + tid;
-                const bool valid = k < nD;
-                int e = 0, child = 0;
-                bool done = false, readied = false;
-                if (valid) {
-                    e = deps[k];
-                    const bool ticked = !(any_nf && __ldg(&dep_is_flow[e]));     // RCE:434-439
-                    if (!any_nf) {                                               // release this tick's channel winner slot
-                        const uint32_t c = __ldg(&dep_channel[e]);
-                        if (c != RAMP_NO_CHANNEL) ckey[c] = 0u;
-                    }
-                    if (ticked) {
-                        const double r = tick_down(sv.dep_rem[e], tick);
-                        if (r == 0.0) {
-                            done = true;
-                            child = __ldg(&dep_dst[e]);
-                            const uint32_t cnt = atomicAdd(&sv.par_done[child], 1u) + 1u;   // JOB:530
-                            readied = (cnt == (uint32_t)__ldg(&op_n_parents[child]));        // JOB:531 (fires once)
-                        } else {
-                            sv.dep_rem[e] = r;
-                        }
-                    }
-                }
-                warp_push(deps_n, &s_n_deps[nxt], valid && !done, e);
-                if (readied) sv.op_rem[child] = __ldg(&op_cost[child]);
-                warp_push(ops_n, &s_n_ops[nxt], readied, child);
-                ddone_local += done ? 1 : 0;
-            }
-            done_local = warp_sum_i32(done_local);
-            ddone_local = warp_sum_i32(ddone_local);
-            if (lane == 0) {
-                if (done_local) atomicAdd(&s_ops_completed, done_local);
-                if (ddone_local) atomicAdd(&s_deps_completed, ddone_local);
-            }
-            __syncthreads();
-
-            // ---- G (cont.): out-edges of completed ops become ready next tick (JOB:496-506), one warp per op,
-            //      contiguous dep indices -> coalesced writes ----
-            {
-                const int nq = s_doneq_n;
-                for (int q = warp; q < nq; q += NW) {
-                    const int i = doneq[q];
-                    const int start = __ldg(&row_ptr[i]), deg = __ldg(&row_ptr[i + 1]) - start;
-                    int base = 0;
-                    if (lane == 0 && deg > 0) base = atomicAdd(&s_n_deps[nxt], deg);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    for (int j = lane; j < deg; j += 32) {
-                        deps_n[base + j] = start + j;
-                        sv.dep_rem[start + j] = __ldg(&dep_run_time[start + j]);     // RCE:542-560
-                    }
-                }
-                for (int i = tid; i < W; i += NT) wkey[i] = 0u;
-            }
-            // ---- I, J, K, L: serial bookkeeping in tick order (RCE:442-465, 777-791) ----
+            // ---- I, J: serial bookkeeping in tick order (RCE:442-445, 777-791); overlaps with P3 of the other threads ----
             if (tid == 0) {
                 const bool ticked_ops = n_active > 0;
-                const bool ticked_flows = (!any_nf) && (nD > 0);
+                const bool ticked_flows = (!any_nf) && (live0 > 0);
                 if (ticked_ops && ticked_flows) { comm = __dadd_rn(comm, tick); comp = __dadd_rn(comp, tick); }
                 else if (ticked_flows) comm = __dadd_rn(comm, tick);
                 else if (ticked_ops) comp = __dadd_rn(comp, tick);
@@ -435,21 +367,152 @@ __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs 
                 if (tick_no < a.trace_cap) { sv.tr_n[tick_no] = n_active; sv.tr_tick[tick_no] = tick; }
                 else status = RAMP_ST_TRACE_OVERFLOW;
                 ++tick_no;
-                // reset this tick's reduction cells and frontier counters for their next use
                 s_min_op[nxt] = RAMP_INF_BITS; s_min_dep[nxt] = RAMP_INF_BITS; s_n_active[nxt] = 0;
-                s_min_op[cur] = RAMP_INF_BITS; s_min_dep[cur] = RAMP_INF_BITS; s_n_active[cur] = 0;
-                s_n_ops[cur] = 0; s_n_deps[cur] = 0;
-                if (s_ops_completed == N && s_deps_completed == E) s_stop = 1;                    // JOB:549-551
-                else if (isinf(tick)) { s_stop = 2; status = RAMP_ST_INFINITE_TICK; }              // RCE:462
+                s_ctail = 0;
+            }
+
+            // ---- P3.G: tick the winners (RCE:691-716, JOB:553-557, 492-501) ----
+            int done_local = 0;
+            {
+                int j = 0;
+                for (int kb = 0; kb < nO; kb += NT, ++j) {
+                    const int k = kb + tid;
+                    const bool valid = k < nO;
+                    int4 r = make_int4(0, 0, 0, 0);
+                    bool done = false;
+                    if (valid) {
+                        r = ops[k];
+                        bool win;
+                        if (big_ops) win = wkey[r.w] == (uint32_t)r.z;      // keys are cleared after the barrier instead
+                        else { win = ((win_mask >> j) & 1u) != 0u; wkey[r.w] = 0u; }   // release this tick's winner slot
+                        if (win) {
+                            const double rem = tick_down(__hiloint2double(r.y, r.x), tick);
+                            if (rem == 0.0) done = true;
+                            else { r.x = __double2loint(rem); r.y = __double2hiint(rem); }
+                        }
+                    }
+                    // survivors stay ready
+                    {
+                        const bool keep = valid && !done;
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);
+                        if (m) {
+                            const int leader = __ffs(m) - 1;
+                            int base = 0;
+                            if (lane == leader) base = atomicAdd(&s_n_ops[nxt], __popc(m));
+                            base = __shfl_sync(0xffffffffu, base, leader);
+                            if (keep) ops_n[base + __popc(m & ((1u << lane) - 1u))] = r;
+                        }
+                    }
+                    // completed: the op's out-edges become ready (JOB:496-506); the whole warp copies each CSR row
+                    unsigned dm = __ballot_sync(0xffffffffu, done);
+                    done_local += done ? 1 : 0;
+                    while (dm) {
+                        const int src = __ffs(dm) - 1;
+                        dm &= dm - 1u;
+                        const int key = __shfl_sync(0xffffffffu, r.z, src);
+                        const int2 row = __ldg(&t_row_by_key[key]);
+                        int base = 0;
+                        if (lane == 0 && row.y > 0) base = atomicAdd(&s_tail[cur], row.y);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        for (int q = lane; q < row.y; q += 32) {
+                            fkm[base + q] = __ldg(&t_dep_km[row.x + q]);
+                            frem[base + q] = __ldg(&t_dep_rt[row.x + q]);       // RCE:542-560
+                        }
+                    }
+                }
+            }
+            // ---- P3.H: tick the deps of the pre-tick snapshot [0, nF) (RCE:718-775, JOB:559-563, 525-536) ----
+            int ddone_local = 0;
+            for (int kb = 0; kb < nF; kb += NT) {
+                const int k = kb + tid;
+                bool readied = false;
+                int child = 0;
+                if (k < nF) {
+                    const unsigned long long km = fkm[k];
+                    if (km != 0ull) {
+                        const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
+                        const bool is_flow = (km >> 48) != 0ull;
+                        if (c != RAMP_NO_CHANNEL) ckey[c] = 0u;             // release this tick's channel winner slot
+                        if (!(any_nf && is_flow)) {                         // RCE:434-439
+                            const double rem = tick_down(frem[k], tick);
+                            if (rem == 0.0) {
+                                fkm[k] = 0ull;                              // completed: dead in place
+                                ++ddone_local;
+                                child = __ldg(&t_dst_by_key[(uint32_t)km]);
+                                const uint32_t cnt = atomicAdd(&sv.par_done[child], 1u) + 1u;      // JOB:530
+                                readied = (cnt == (uint32_t)__ldg(&t_n_parents[child]));           // JOB:531 (fires once)
+                            } else {
+                                frem[k] = rem;
+                            }
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, readied);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&s_n_ops[nxt], __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (readied) ops_n[base + __popc(m & ((1u << lane) - 1u))] = __ldg(&t_op_rec[child]);
+                }
+            }
+            done_local = warp_sum_i32(done_local);
+            ddone_local = warp_sum_i32(ddone_local);
+            if (lane == 0) {
+                if (done_local) atomicAdd(&s_ops_completed, done_local);
+                if (ddone_local) { atomicAdd(&s_deps_completed, ddone_local); atomicAdd(&s_dead[cur], ddone_local); }
             }
             __syncthreads();
-            if (tid == 0) s_doneq_n = 0;
+
+            // ---- K, L + frontier bookkeeping: every thread derives the same values from the shared counters ----
+            const int nF2 = s_tail[cur];                  // snapshot + deps made ready this tick
+            const int live = live0 - s_dead[cur] + (nF2 - nF);
+            const bool finished = (s_ops_completed == N) && (s_deps_completed == E);     // JOB:549-551
+            const bool stop = finished || isinf(tick);                                    // RCE:462
+            const bool compact = !stop && (nF2 > 2 * live + NT);
+            if (big_ops) {
+                for (int i = tid; i < W; i += NT) wkey[i] = 0u;
+                __syncthreads();
+            }
+            if (compact) {
+                // copy the live entries to the other buffer (order is irrelevant: the arg-max is by key)
+                unsigned long long* gkm = fkm_alt;
+                double* grem = frem_alt;
+                for (int kb = 0; kb < nF2; kb += NT) {
+                    const int k = kb + tid;
+                    unsigned long long km = 0ull;
+                    if (k < nF2) km = fkm[k];
+                    const bool keep = km != 0ull;
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(&s_ctail, __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (keep) {
+                            const int p = base + __popc(m & ((1u << lane) - 1u));
+                            gkm[p] = km;
+                            grem[p] = frem[k];
+                        }
+                    }
+                }
+                fkm_alt = fkm; frem_alt = frem; fkm = gkm; frem = grem;
+                __syncthreads();
+            }
+            nF = compact ? live : nF2;
+            live0 = live;
+            if (tid == 0) {
+                // next tick's append tail / completion counter (first touched two barriers from now)
+                s_tail[nxt] = nF; s_dead[nxt] = 0;
+                s_n_ops[cur] = 0;
+                if (!finished && isinf(tick)) status = RAMP_ST_INFINITE_TICK;
+            }
             cur = nxt;
-            if (s_stop) break;
+            { int4* tmp = ops_a; ops_a = ops_b; ops_b = tmp; }
+            if (stop) break;
         }
 
         // ---- results (RCE:450-452): copy the trace to an exactly-sized pool allocation ----
-        __shared__ long long s_trace_off;
         if (tid == 0) {
             const double steps = (double)T.num_training_steps;
             a.res.jct[item.slot] = __dmul_rn(t, steps);
@@ -466,7 +529,7 @@ __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs 
             a.res.trace_off[item.slot] = off;
             a.res.status[item.slot] = status;
             s_trace_off = off;
-            s_n_ops[0] = n_rec;
+            s_n_rec = n_rec;
             if (a.stats) {
                 atomicAdd(&a.stats->lookaheads, 1ull);
                 atomicAdd(&a.stats->alg_bytes, (unsigned long long)(T.algorithmic_bytes_static + 12ull * (unsigned long long)tick_no));
@@ -474,7 +537,7 @@ __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs 
         }
         __syncthreads();
         if (s_trace_off >= 0) {
-            const int n_rec = s_n_ops[0];
+            const int n_rec = s_n_rec;
             for (int k = tid; k < n_rec; k += NT) {
                 a.pool.n_active[s_trace_off + k] = sv.tr_n[k];
                 a.pool.tick[s_trace_off + k] = sv.tr_tick[k];

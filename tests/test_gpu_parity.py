@@ -104,7 +104,8 @@ def test_episode_replay_vs_reference_golden(fname, memo_mode, eng_mod):
                     a, c = stats[b, SS[k]], ref[s, SS[k]]
                     assert a == pytest.approx(c, rel=1e-6, abs=0), (fname, s, b, k, a, c)
         else:
-            assert (stats == stats[0]).all()
+            cols = [i for k, i in SS.items() if k != 'lookahead_ran']   # in exact mode one episode per key runs it
+            assert (stats[:, cols] == stats[0, cols]).all()
     if memo_mode != 0:
         eng.close()
         return
