@@ -43,12 +43,12 @@ constexpr int MAX_EVENT_PAIRS = 64;
 // The lookahead kernel is instantiated for several CTA sizes; small CTAs (1-2 warps) keep more lookaheads
 // resident per SM and waste fewer lanes on the small per-tick frontiers, large CTAs finish one lookahead sooner.
 using LookaheadKernel = void (*)(const LookaheadArgs);
-LookaheadKernel lookahead_kernel_for(int nt) {
+LookaheadKernel lookahead_kernel_for(int nt) {   // nt = threads per CTA = 32 x (independent lookahead warps per CTA)
     switch (nt) {
-        case 32: return ramp_lookahead_kernel<32>;
-        case 64: return ramp_lookahead_kernel<64>;
-        case 128: return ramp_lookahead_kernel<128>;
-        case 256: return ramp_lookahead_kernel<256>;
+        case 32: return ramp_lookahead_kernel<1>;
+        case 64: return ramp_lookahead_kernel<2>;
+        case 128: return ramp_lookahead_kernel<4>;
+        case 256: return ramp_lookahead_kernel<8>;
         default: return nullptr;
     }
 }
@@ -93,7 +93,7 @@ struct ramp_engine {
     uint64_t scratch_stride = 0;
     int scratch_grid = 0;
     int grid = 0;
-    int nt = 64;                 // threads per lookahead CTA (RAMP_LOOKAHEAD_THREADS overrides)
+    int nt = 128;                // threads per lookahead CTA = 32 x warps, one lookahead per warp (RAMP_LOOKAHEAD_THREADS overrides)
     int max_ctas_per_sm = 0;     // optional cap (RAMP_LOOKAHEAD_CTAS_PER_SM)
     size_t smem_bytes = 0;
     // standalone lookahead buffers
@@ -142,7 +142,7 @@ int resolve_events(ramp_engine* e) {
 int ensure_scratch(ramp_engine* e) {
     const uint64_t trace_bytes = align_up((uint64_t)e->cfg.trace_cap * 12, 16);
     const uint64_t stride = align_up(std::max<uint64_t>(e->max_scratch, 16), 256) + align_up(trace_bytes, 256);
-    const size_t smem = sizeof(uint32_t) * ((size_t)e->max_w + (size_t)e->max_c);
+    const size_t smem = lookahead_smem_per_warp(e->max_w, e->max_c) * (size_t)(e->nt / 32);
     if (smem > 200 * 1024)
         return set_error(RAMP_ERR_CAPACITY, "a template needs %zu B of shared memory for its worker/channel key arrays (max 200 KiB)", smem);
     if (smem != e->smem_bytes || e->grid == 0) {
@@ -159,7 +159,7 @@ int ensure_scratch(ramp_engine* e) {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (e->d_scratch) cudaFree(e->d_scratch);
         e->d_scratch = nullptr;
-        CUDA_TRY(cudaMalloc(&e->d_scratch, stride * (uint64_t)e->grid));
+        CUDA_TRY(cudaMalloc(&e->d_scratch, stride * (uint64_t)e->grid * (uint64_t)(e->nt / 32)));   // one slab per warp
         e->scratch_stride = stride;
         e->scratch_grid = e->grid;
     }
@@ -345,26 +345,23 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     struct OpRec { double cost; uint32_t key; uint32_t worker; };
     static_assert(sizeof(OpRec) == 16, "op record must be 16 bytes");
     std::vector<OpRec> op_rec(N);
-    std::vector<int32_t> row_by_key((size_t)(N + 1) * 2, 0);
+    std::vector<int32_t> op_row((size_t)N * 2, 0);
     for (int32_t i = 0; i < N; ++i) {
         op_rec[i] = OpRec{op_cost[i], op_key[i], (uint32_t)j->op_worker[i]};
-        row_by_key[(size_t)op_key[i] * 2] = j->row_ptr[i];
-        row_by_key[(size_t)op_key[i] * 2 + 1] = j->row_ptr[i + 1] - j->row_ptr[i];
+        op_row[(size_t)i * 2] = j->row_ptr[i];
+        op_row[(size_t)i * 2 + 1] = j->row_ptr[i + 1] - j->row_ptr[i];
     }
     std::vector<unsigned long long> dep_km(E);
-    std::vector<int32_t> dst_by_key((size_t)E + 1, 0);
-    for (int32_t k = 0; k < E; ++k) {
+    for (int32_t k = 0; k < E; ++k)
         dep_km[k] = (unsigned long long)dep_key[k] | ((unsigned long long)j->dep_channel[k] << 32)
                     | ((unsigned long long)(j->dep_is_flow[k] ? 1 : 0) << 48);
-        dst_by_key[dep_key[k]] = j->dep_dst[k];
-    }
 
     // ---- pack one blob ----
     struct Seg { const void* p; size_t bytes; size_t off; };
     Seg segs[7] = {
         {op_rec.data(), sizeof(OpRec) * (size_t)N, 0}, {j->op_n_parents, sizeof(uint16_t) * (size_t)N, 0},
-        {row_by_key.data(), sizeof(int32_t) * row_by_key.size(), 0}, {dep_km.data(), sizeof(unsigned long long) * (size_t)E, 0},
-        {dep_rt.data(), sizeof(double) * (size_t)E, 0}, {dst_by_key.data(), sizeof(int32_t) * dst_by_key.size(), 0},
+        {op_row.data(), sizeof(int32_t) * op_row.size(), 0}, {dep_km.data(), sizeof(unsigned long long) * (size_t)E, 0},
+        {dep_rt.data(), sizeof(double) * (size_t)E, 0}, {j->dep_dst, sizeof(int32_t) * (size_t)E, 0},
         {src.data(), sizeof(int32_t) * src.size(), 0}};
     size_t total = 0;
     for (auto& s : segs) { s.off = total; total += align_up(std::max<size_t>(s.bytes, 1), 256); }
@@ -388,8 +385,8 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     d.n_src = (int32_t)src.size(); d.canon_id = canon;
     d.trace_need = (int32_t)std::min<int64_t>((int64_t)N + E + 1, e->cfg.trace_cap);
     d.op_rec = (const int4*)(base + segs[0].off); d.op_n_parents = (const uint16_t*)(base + segs[1].off);
-    d.op_row_by_key = (const int2*)(base + segs[2].off); d.dep_km = (const unsigned long long*)(base + segs[3].off);
-    d.dep_rt = (const double*)(base + segs[4].off); d.dep_dst_by_key = (const int32_t*)(base + segs[5].off);
+    d.op_row = (const int2*)(base + segs[2].off); d.dep_km = (const unsigned long long*)(base + segs[3].off);
+    d.dep_rt = (const double*)(base + segs[4].off); d.dep_dst = (const int32_t*)(base + segs[5].off);
     d.src_ops = (const int32_t*)(base + segs[6].off);
     d.scratch_bytes = scratch_bytes_for(N, E);
     d.algorithmic_bytes_static = 20ull * (uint64_t)N + 19ull * (uint64_t)E + 24ull;

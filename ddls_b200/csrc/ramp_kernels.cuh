@@ -25,25 +25,23 @@ namespace ramp {
 //
 // Priorities are pre-ranked on the host into unique u32 keys (larger wins): sorting by (priority desc, index asc)
 // reproduces "iterate in sorted() order, replace only on strictly greater priority" (RCE:56-66, RCE:672-685), so
-// the per-worker / per-channel arg-max is one 32-bit shared-memory atomicMax per ready item.  Everything a
-// ready item needs every tick is packed next to its key, so frontier entries are self-contained records and
-// the loop never gathers through an index:
-//   op record  = { f64 remaining, u32 key, u32 worker }                       (16 B)
-//   dep record = { f64 remaining } + { u32 key, u16 channel, u16 is_flow }    (8 B + 8 B, SoA)
-// What is only needed when an item completes (child op, out-edge range) is looked up by key.
+// the per-worker / per-channel arg-max is one 32-bit shared-memory atomicMax per item.  Everything a ready
+// item needs is packed into a self-contained record, so the tick loop never gathers through an index:
+//   op record  = { f64 remaining, u32 key, u32 worker } + { i32 first out-edge, i32 out-degree }   (24 B)
+//   dep record = { u32 key | u16 channel | u16 is_flow } + { f64 remaining } + { i32 child op }    (20 B)
 struct TemplateDev {
     int32_t n_ops, n_deps, n_workers, n_channels;
     int32_t num_training_steps, model_id, degree, n_src;
     int32_t canon_id;           // id of the first registered byte-identical template (exact memo key)
     int32_t trace_need;         // min(N + E + 1, trace_cap): upper bound on ticks (>= 1 op or dep completes per tick)
-    const int4*     op_rec;       // [N]   by op index: {cost.lo, cost.hi, key, worker}: the record pushed when the op becomes ready
-    const uint16_t* op_n_parents; // [N]   by op index (JOB:508-523)
-    const int2*     op_row_by_key;// [N+1] by op key: {first out-edge, out-degree} (CSR row of the op holding that key)
+    const int4*     op_rec;       // [N] by op index: {cost.lo, cost.hi, key, worker}
+    const int2*     op_row;       // [N] by op index: {first out-edge, out-degree} (CSR row)
+    const uint16_t* op_n_parents; // [N] by op index (JOB:508-523)
     const unsigned long long* dep_km;  // [E] by dep index (CSR order): key | channel << 32 | is_flow << 48
-    const double*   dep_rt;       // [E]   by dep index: init_run_time (RCE:542-560)
-    const int32_t*  dep_dst_by_key; // [E+1] by dep key: child op index
+    const double*   dep_rt;       // [E] by dep index: init_run_time (RCE:542-560)
+    const int32_t*  dep_dst;      // [E] by dep index: child op index
     const int32_t*  src_ops;      // [n_src] ops with in-degree 0: the initial ops_ready (JOB:474-481)
-    uint64_t scratch_bytes;       // dynamic state one running lookahead of this template needs
+    uint64_t scratch_bytes;       // HBM-side dynamic state one running lookahead of this template may need
     uint64_t algorithmic_bytes_static; // 20 N + 19 E + 24, + 12 T added per run
 };
 
@@ -124,12 +122,16 @@ struct LookaheadArgs {
 
 __host__ __device__ inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
-// dynamic state of one running lookahead, carved out of the CTA's scratch slab
+// HBM-side dynamic state of one running lookahead, carved out of the owning warp's scratch slab.  The hot state
+// (op frontier, the first RAMP_F_CAP entries of the dep frontier, per-worker / per-channel winners) lives in
+// shared memory; HBM holds the parent counters, the overflow of the two frontiers and the tick trace.
 struct ScratchView {
     uint32_t* par_done;              // [N] len(parent_deps_completed) JOB:530
-    int4*     ops[2];                // ops_ready frontier records (ping-pong, compacted every tick; it is small)
-    unsigned long long* dep_km[2];   // deps_ready frontier: key/channel/flow words, 0 = completed (in place, lazily compacted)
-    double*   dep_rem[2];            // deps_ready frontier: remaining_run_time (JOB:561)
+    int4*     ops_a_ovf[2];          // [N] overflow of the shared-memory op frontier (ping-pong)
+    int2*     ops_b_ovf[2];          // [N]
+    unsigned long long* f_km_ovf;    // [E] overflow of the shared-memory dep frontier
+    double*   f_rem_ovf;             // [E]
+    int32_t*  f_dst_ovf;             // [E]
     int32_t*  tr_n;                  // [trace_cap] temp trace
     double*   tr_tick;               // [trace_cap]
 };
@@ -138,8 +140,9 @@ __host__ __device__ inline uint64_t scratch_bytes_for(int32_t N, int32_t E) {
     uint64_t b = 0;
     b += align_up((uint64_t)N * 4, 16);
     b += 2 * align_up((uint64_t)N * 16, 16);
+    b += 2 * align_up((uint64_t)N * 8, 16);
     b += 2 * align_up((uint64_t)E * 8, 16);
-    b += 2 * align_up((uint64_t)E * 8, 16);
+    b += align_up((uint64_t)E * 4, 16);
     return b;
 }
 
@@ -147,12 +150,13 @@ __device__ inline ScratchView carve(unsigned char* base, int32_t N, int32_t E, u
     ScratchView v;
     uint64_t o = 0;
     v.par_done = (uint32_t*)(base + o);              o += align_up((uint64_t)N * 4, 16);
-    v.ops[0] = (int4*)(base + o);                    o += align_up((uint64_t)N * 16, 16);
-    v.ops[1] = (int4*)(base + o);                    o += align_up((uint64_t)N * 16, 16);
-    v.dep_km[0] = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
-    v.dep_km[1] = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
-    v.dep_rem[0] = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
-    v.dep_rem[1] = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
+    v.ops_a_ovf[0] = (int4*)(base + o);              o += align_up((uint64_t)N * 16, 16);
+    v.ops_a_ovf[1] = (int4*)(base + o);              o += align_up((uint64_t)N * 16, 16);
+    v.ops_b_ovf[0] = (int2*)(base + o);              o += align_up((uint64_t)N * 8, 16);
+    v.ops_b_ovf[1] = (int2*)(base + o);              o += align_up((uint64_t)N * 8, 16);
+    v.f_km_ovf = (unsigned long long*)(base + o);    o += align_up((uint64_t)E * 8, 16);
+    v.f_rem_ovf = (double*)(base + o);               o += align_up((uint64_t)E * 8, 16);
+    v.f_dst_ovf = (int32_t*)(base + o);              o += align_up((uint64_t)E * 4, 16);
     v.tr_tick = (double*)(base + trace_region_off);
     v.tr_n = (int32_t*)(v.tr_tick + trace_cap);
     return v;
@@ -203,324 +207,384 @@ __device__ __forceinline__ int warp_sum_i32(int v) {
 #define RAMP_INF_BITS 0x7FF0000000000000ull
 
 // ---------------------------------------------------------------------------------------------------
-// _run_lookahead (RCE:379-467): one CTA per lookahead, persistent CTAs pull work items.
+// _run_lookahead (RCE:379-467): ONE WARP per lookahead; WPB independent warps per CTA; persistent warps pull
+// work items from a device-side cursor.  No block barriers: per-tick frontiers are tens to hundreds of
+// items, so a warp keeps its lanes busy and all cross-lane traffic is shuffles / ballots / shared atomics.
+// A lone warp is bound by dependent memory round trips, so the ready frontiers are staged in shared memory
+// (HBM only on overflow) and the remaining global phases issue a whole batch of loads before consuming any.
 //
-// Per tick, three phases separated by block barriers (letters as in SURVEY.md 3.3):
-//   P1  A  per-worker arg-max over ready ops   -> atomicMax of rank keys into smem wkey[]
-//       C  any ready non-flow dep?              -> folded into the barrier (__syncthreads_or)
-//       D  per-channel arg-max over ready deps  -> atomicMax into smem ckey[] (speculative; unused if C)
-//   P2  B/D.iii  min remaining over the winners -> warp shuffles + one smem atomicMin per warp (the u64 bit pattern
-//                                                   of a non-negative double is order preserving)
-//   P3  E  tick = min(t_op, t_comm)
-//       G  winners: rem -= min(tick, rem); == 0 -> completed: its CSR row of dep records is copied (coalesced, by the
-//          whole warp) to the tail of the dep frontier -- visible from the next tick on, i.e. the RCE:429 snapshot
-//       H  every dep of the snapshot (only the non-flows if C): same; completed -> marked dead in place, atomicAdd on
-//          the child's parent counter, == n_parents -> child's op record appended to the next op frontier
-//       I,J  thread 0 accumulates t / comm / comp and the trace in tick order
-// The dep frontier is updated in place (a tick in which flows are frozen writes nothing) and compacted only when
-// more than half of it is dead.
-template <int NT>
-__global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs a) {
+// Per tick (letters as in SURVEY.md 3.3):
+//   A  per-worker arg-max over ready ops           -> atomicMax of rank keys into smem wkey[]      (RCE:562-590, 44-67)
+//   B  t_op = min remaining over the op winners    -> butterfly shuffles                            (RCE:592-606)
+//   C  any ready non-flow dep?                      -> a counter kept up to date as deps arrive / complete (RCE:520-540)
+//   D  t_comm = min remaining over the per-channel winners.  The per-channel arg-max (RCE:608-629, 665-689) is
+//      maintained INCREMENTALLY: ckey[c] is the best key among the ready flows on channel c and crem[c] that
+//      flow's remaining time.  A flow that becomes ready does one atomicMax; when a completing flow held its
+//      channel's slot the slots are recomputed from the ready deps.  The tick only scans the C slots. (RCE:653-663)
+//   E  tick = min(t_op, t_comm)                                                                     (RCE:426)
+//   H  every dep of the pre-tick snapshot (only the non-flows if C): rem -= min(tick, rem); == 0 -> completed:
+//      atomicAdd on the child's parent counter, == n_parents -> child's op record appended to the next op
+//      frontier.  Survivors are slid down in place, so the frontier never holds dead entries.     (RCE:718-775)
+//   G  op winners: same; completed -> the CSR rows of all ops completed in this tick are appended to the dep
+//      frontier as one flattened, coalesced copy (first ticked next tick == the RCE:429 snapshot). (RCE:691-716)
+//   I,J lane 0 accumulates t / comm / comp and the trace in tick order                              (RCE:442-445, 777-791)
+#define RAMP_U 4            // batch depth: independent loads in flight per lane per phase
+#define RAMP_OPS_CAP 48     // op-frontier records kept in shared memory per buffer (overflow goes to HBM)
+#define RAMP_F_CAP 512      // dep-frontier records kept in shared memory (overflow goes to HBM)
+
+struct OpsView { int4* a_sm; int2* b_sm; int4* a_ovf; int2* b_ovf; };
+__device__ __forceinline__ void ops_get(const OpsView& v, int k, int4& ra, int2& rb) {
+    if (k < RAMP_OPS_CAP) { ra = v.a_sm[k]; rb = v.b_sm[k]; } else { ra = v.a_ovf[k - RAMP_OPS_CAP]; rb = v.b_ovf[k - RAMP_OPS_CAP]; }
+}
+__device__ __forceinline__ void ops_put(const OpsView& v, int k, const int4 ra, const int2 rb) {
+    if (k < RAMP_OPS_CAP) { v.a_sm[k] = ra; v.b_sm[k] = rb; } else { v.a_ovf[k - RAMP_OPS_CAP] = ra; v.b_ovf[k - RAMP_OPS_CAP] = rb; }
+}
+struct FrontView { unsigned long long* km_sm; double* rem_sm; int32_t* dst_sm; unsigned long long* km_ovf; double* rem_ovf; int32_t* dst_ovf; };
+__device__ __forceinline__ void f_get(const FrontView& v, int k, unsigned long long& km, double& rem, int& dst) {
+    if (k < RAMP_F_CAP) { km = v.km_sm[k]; rem = v.rem_sm[k]; dst = v.dst_sm[k]; }
+    else { km = v.km_ovf[k - RAMP_F_CAP]; rem = v.rem_ovf[k - RAMP_F_CAP]; dst = v.dst_ovf[k - RAMP_F_CAP]; }
+}
+__device__ __forceinline__ void f_put(const FrontView& v, int k, unsigned long long km, double rem, int dst) {
+    if (k < RAMP_F_CAP) { v.km_sm[k] = km; v.rem_sm[k] = rem; v.dst_sm[k] = dst; }
+    else { v.km_ovf[k - RAMP_F_CAP] = km; v.rem_ovf[k - RAMP_F_CAP] = rem; v.dst_ovf[k - RAMP_F_CAP] = dst; }
+}
+__device__ __forceinline__ void f_get_km_rem(const FrontView& v, int k, unsigned long long& km, double& rem) {
+    if (k < RAMP_F_CAP) { km = v.km_sm[k]; rem = v.rem_sm[k]; } else { km = v.km_ovf[k - RAMP_F_CAP]; rem = v.rem_ovf[k - RAMP_F_CAP]; }
+}
+
+// bytes of shared memory one lookahead warp needs
+__host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap) {
+    size_t b = 0;
+    b += (size_t)RAMP_F_CAP * 8 * 2;             // km, rem
+    b += (size_t)c_cap * 8;                      // crem
+    b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
+    b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
+    b += (size_t)RAMP_F_CAP * 4;                 // dst
+    b += (size_t)(w_cap + c_cap) * 4;            // wkey, ckey
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const LookaheadArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* wkey = reinterpret_cast<uint32_t*>(smem_raw);        // [w_cap] best rank key per worker this tick
-    uint32_t* ckey = wkey + a.w_cap;                               // [c_cap] best rank key per channel this tick
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned char* my_smem = smem_raw + (size_t)warp * lookahead_smem_per_warp(a.w_cap, a.c_cap);
+    FrontView fr;
+    fr.km_sm = reinterpret_cast<unsigned long long*>(my_smem);
+    fr.rem_sm = reinterpret_cast<double*>(fr.km_sm + RAMP_F_CAP);
+    double* crem = fr.rem_sm + RAMP_F_CAP;                               // [c_cap] remaining time of the channel's winner
+    int4* ops_a_sm0 = reinterpret_cast<int4*>(crem + a.c_cap);
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);
+    fr.dst_sm = reinterpret_cast<int32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);
+    uint32_t* wkey = reinterpret_cast<uint32_t*>(fr.dst_sm + RAMP_F_CAP);   // [w_cap] best key among the ready ops on the worker
+    uint32_t* ckey = wkey + a.w_cap;                                         // [c_cap] best key among the ready flows on the channel
 
-    __shared__ int s_work;
-    __shared__ int s_n_ops[2];            // op frontier sizes (ping-pong)
-    __shared__ int s_tail[2];             // dep frontier append tail of the current tick (by tick parity)
-    __shared__ int s_dead[2];             // deps completed in the current tick (by tick parity)
-    __shared__ int s_ctail;               // compaction cursor
-    __shared__ int s_ops_completed, s_deps_completed;
-    __shared__ unsigned long long s_min_op[2], s_min_dep[2];
-    __shared__ int s_n_active[2];
-    __shared__ long long s_trace_off;
-    __shared__ int s_n_rec;
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-
-    unsigned char* slab = a.scratch + (uint64_t)blockIdx.x * a.scratch_stride;
+    unsigned char* slab = a.scratch + (uint64_t)(blockIdx.x * WPB + warp) * a.scratch_stride;
     const uint64_t trace_region = a.scratch_stride - align_up((uint64_t)a.trace_cap * 12, 16);
+    const double INF = __longlong_as_double(RAMP_INF_BITS);
 
     for (;;) {
-        if (tid == 0) s_work = atomicAdd(a.cursor, 1);
-        __syncthreads();
-        const int wi = s_work;
+        int wi = 0;
+        if (lane == 0) wi = atomicAdd(a.cursor, 1);
+        wi = __shfl_sync(FULL, wi, 0);
         if (wi >= *a.n_work) break;
         const WorkItem item = a.items[wi];
         const TemplateDev& T = a.templates[item.template_id];
         const int N = T.n_ops, E = T.n_deps, W = T.n_workers, C = T.n_channels;
         const ScratchView sv = carve(slab, N, E, trace_region, a.trace_cap);
+        fr.km_ovf = sv.f_km_ovf; fr.rem_ovf = sv.f_rem_ovf; fr.dst_ovf = sv.f_dst_ovf;
 
         const int4* __restrict__ t_op_rec = T.op_rec;
+        const int2* __restrict__ t_op_row = T.op_row;
         const uint16_t* __restrict__ t_n_parents = T.op_n_parents;
-        const int2* __restrict__ t_row_by_key = T.op_row_by_key;
         const unsigned long long* __restrict__ t_dep_km = T.dep_km;
         const double* __restrict__ t_dep_rt = T.dep_rt;
-        const int32_t* __restrict__ t_dst_by_key = T.dep_dst_by_key;
+        const int32_t* __restrict__ t_dep_dst = T.dep_dst;
+        uint32_t* par_done = sv.par_done;
 
         // ---- init (JOB:432-484) ----
-        for (int i = tid; i < N; i += NT) sv.par_done[i] = 0u;
-        for (int i = tid; i < W; i += NT) wkey[i] = 0u;
-        for (int i = tid; i < C; i += NT) ckey[i] = 0u;
-        for (int k = tid; k < T.n_src; k += NT) sv.ops[0][k] = __ldg(&t_op_rec[__ldg(&T.src_ops[k])]);   // RCE:1334
-        if (tid == 0) {
-            s_n_ops[0] = T.n_src; s_n_ops[1] = 0;
-            s_tail[0] = s_tail[1] = 0; s_dead[0] = s_dead[1] = 0; s_ctail = 0;
-            s_ops_completed = 0; s_deps_completed = 0;
-            s_min_op[0] = s_min_op[1] = RAMP_INF_BITS; s_min_dep[0] = s_min_dep[1] = RAMP_INF_BITS;
-            s_n_active[0] = s_n_active[1] = 0;
+        for (int i = lane; i < N; i += 32) par_done[i] = 0u;
+        for (int i = lane; i < W; i += 32) wkey[i] = 0u;
+        for (int i = lane; i < C; i += 32) ckey[i] = 0u;
+        OpsView ops, ops_n;
+        ops.a_sm = ops_a_sm0; ops.b_sm = ops_b_sm0; ops.a_ovf = sv.ops_a_ovf[0]; ops.b_ovf = sv.ops_b_ovf[0];
+        ops_n.a_sm = ops_a_sm0 + RAMP_OPS_CAP; ops_n.b_sm = ops_b_sm0 + RAMP_OPS_CAP; ops_n.a_ovf = sv.ops_a_ovf[1]; ops_n.b_ovf = sv.ops_b_ovf[1];
+        for (int k = lane; k < T.n_src; k += 32) {
+            const int op = __ldg(&T.src_ops[k]);
+            ops_put(ops, k, __ldg(&t_op_rec[op]), __ldg(&t_op_row[op]));          // RCE:1334
         }
-        __syncthreads();
+        __syncwarp();
 
-        // thread-0 private accumulators (Stopwatch UT:485-496, JOB:170-171)
-        double t = 0.0, comm = 0.0, comp = 0.0;
+        // warp-uniform state
+        int nO = T.n_src;          // ready ops
+        int nF = 0;                // ready deps (the frontier holds no dead entries)
+        int n_nonflow = 0;         // ready non-flow deps
+        int ops_completed = 0, deps_completed = 0;
         int tick_no = 0;
         int status = RAMP_ST_OK;
-        int cur = 0;      // tick parity
-        // frontier buffers are kept as plain pointers that are swapped (no dynamically indexed pointer arrays)
-        int4* ops_a = sv.ops[0];
-        int4* ops_b = sv.ops[1];
-        unsigned long long* fkm = sv.dep_km[0];
-        unsigned long long* fkm_alt = sv.dep_km[1];
-        double* frem = sv.dep_rem[0];
-        double* frem_alt = sv.dep_rem[1];
-        int nF = 0;       // dep frontier length incl. dead entries (uniform across the CTA)
-        int live0 = 0;    // live entries in the dep frontier (uniform)
+        double t = 0.0, comm = 0.0, comp = 0.0;   // lane 0: Stopwatch UT:485-496, JOB:170-171
 
         for (;;) {
-            const int nxt = cur ^ 1;
-            const int nO = s_n_ops[cur];
-            const bool big_ops = nO > 32 * NT;            // more op iterations per thread than win_mask has bits
-            const int4* ops = ops_a;
-            int4* ops_n = ops_b;
+            const bool big_ops = nO > 32 * 32;          // more op iterations per lane than win_mask has bits
 
-            // ---- P1: arg-max keys (RCE:562-590, 44-67; RCE:608-629, 665-689) and the non-flow test (RCE:520-540) ----
-            for (int k = tid; k < nO; k += NT) {
-                const int4 r = ops[k];
-                atomicMax(&wkey[r.w], (uint32_t)r.z);
+            // ---- A ----
+            for (int k = lane; k < nO; k += 32) {
+                int4 ra; int2 rb;
+                ops_get(ops, k, ra, rb);
+                atomicMax(&wkey[ra.w], (uint32_t)ra.z);
             }
-            int nf = 0;
-            for (int k = tid; k < nF; k += NT) {
-                const unsigned long long km = fkm[k];
-                if (km != 0ull) {
-                    const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
-                    nf |= ((km >> 48) == 0ull);
-                    if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km);
-                }
-            }
-            const int any_nf = __syncthreads_or(nf);
+            __syncwarp();
 
-            // ---- P2: shortest remaining time over the winners (RCE:592-606, 653-663) ----
-            uint32_t win_mask = 0u;      // which of this thread's op iterations hold their worker's winner
+            // ---- B ----
+            uint32_t win_mask = 0u;
+            double mo = INF;
+            int na = 0;
             {
-                double mo = __longlong_as_double(RAMP_INF_BITS), md = mo;
-                int na = 0, j = 0;
-                for (int k = tid; k < nO; k += NT, ++j) {
-                    const int4 r = ops[k];
-                    if (wkey[r.w] == (uint32_t)r.z) {
+                int j = 0;
+                for (int k = lane; k < nO; k += 32, ++j) {
+                    int4 ra; int2 rb;
+                    ops_get(ops, k, ra, rb);
+                    if (wkey[ra.w] == (uint32_t)ra.z) {
                         if (j < 32) win_mask |= 1u << j;
                         ++na;
-                        const double rem = __hiloint2double(r.y, r.x);
+                        const double rem = __hiloint2double(ra.y, ra.x);
                         mo = (rem < mo) ? rem : mo;
                     }
                 }
-                if (!any_nf) {
-                    for (int k = tid; k < nF; k += NT) {
-                        const unsigned long long km = fkm[k];
-                        if (km != 0ull) {
-                            const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
-                            if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km) {
-                                const double rem = frem[k];
-                                md = (rem < md) ? rem : md;
-                            }
-                        }
+            }
+            const double t_op = warp_min_f64(mo);
+            const int n_active = warp_sum_i32(na);
+
+            // ---- C, D ----
+            const bool any_nf = n_nonflow > 0;
+            double t_comm = 0.0;
+            if (!any_nf) {
+                double md = INF;
+                for (int c = lane; c < C; c += 32) {
+                    if (ckey[c] != 0u) {
+                        const double rem = crem[c];
+                        md = (rem < md) ? rem : md;
                     }
                 }
-                mo = warp_min_f64(mo);
-                md = warp_min_f64(md);
-                na = warp_sum_i32(na);
-                if (lane == 0) {
-                    const unsigned long long bo = (unsigned long long)__double_as_longlong(mo);
-                    const unsigned long long bd = (unsigned long long)__double_as_longlong(md);
-                    if (bo != RAMP_INF_BITS) atomicMin(&s_min_op[cur], bo);
-                    if (bd != RAMP_INF_BITS) atomicMin(&s_min_dep[cur], bd);
-                    if (na) atomicAdd(&s_n_active[cur], na);
-                }
+                t_comm = warp_min_f64(md);
             }
-            __syncthreads();
-
-            // ---- E: tick (RCE:426) ----
-            const double t_op = __longlong_as_double((long long)s_min_op[cur]);
-            const double t_comm = any_nf ? 0.0 : __longlong_as_double((long long)s_min_dep[cur]);
+            // ---- E ----
             const double tick = (t_comm < t_op) ? t_comm : t_op;
-            const int n_active = s_n_active[cur];
 
-            // ---- I, J: serial bookkeeping in tick order (RCE:442-445, 777-791); overlaps with P3 of the other threads ----
-            if (tid == 0) {
+            // ---- I, J ----
+            if (lane == 0) {
                 const bool ticked_ops = n_active > 0;
-                const bool ticked_flows = (!any_nf) && (live0 > 0);
+                const bool ticked_flows = (!any_nf) && (nF > 0);
                 if (ticked_ops && ticked_flows) { comm = __dadd_rn(comm, tick); comp = __dadd_rn(comp, tick); }
                 else if (ticked_flows) comm = __dadd_rn(comm, tick);
                 else if (ticked_ops) comp = __dadd_rn(comp, tick);
                 t = __dadd_rn(t, tick);
                 if (tick_no < a.trace_cap) { sv.tr_n[tick_no] = n_active; sv.tr_tick[tick_no] = tick; }
                 else status = RAMP_ST_TRACE_OVERFLOW;
-                ++tick_no;
-                s_min_op[nxt] = RAMP_INF_BITS; s_min_dep[nxt] = RAMP_INF_BITS; s_n_active[nxt] = 0;
-                s_ctail = 0;
             }
+            ++tick_no;
 
-            // ---- P3.G: tick the winners (RCE:691-716, JOB:553-557, 492-501) ----
-            int done_local = 0;
-            {
-                int j = 0;
-                for (int kb = 0; kb < nO; kb += NT, ++j) {
-                    const int k = kb + tid;
-                    const bool valid = k < nO;
-                    int4 r = make_int4(0, 0, 0, 0);
-                    bool done = false;
-                    if (valid) {
-                        r = ops[k];
-                        bool win;
-                        if (big_ops) win = wkey[r.w] == (uint32_t)r.z;      // keys are cleared after the barrier instead
-                        else { win = ((win_mask >> j) & 1u) != 0u; wkey[r.w] = 0u; }   // release this tick's winner slot
-                        if (win) {
-                            const double rem = tick_down(__hiloint2double(r.y, r.x), tick);
-                            if (rem == 0.0) done = true;
-                            else { r.x = __double2loint(rem); r.y = __double2hiint(rem); }
-                        }
-                    }
-                    // survivors stay ready
-                    {
-                        const bool keep = valid && !done;
-                        const unsigned m = __ballot_sync(0xffffffffu, keep);
-                        if (m) {
-                            const int leader = __ffs(m) - 1;
-                            int base = 0;
-                            if (lane == leader) base = atomicAdd(&s_n_ops[nxt], __popc(m));
-                            base = __shfl_sync(0xffffffffu, base, leader);
-                            if (keep) ops_n[base + __popc(m & ((1u << lane) - 1u))] = r;
-                        }
-                    }
-                    // completed: the op's out-edges become ready (JOB:496-506); the whole warp copies each CSR row
-                    unsigned dm = __ballot_sync(0xffffffffu, done);
-                    done_local += done ? 1 : 0;
-                    while (dm) {
-                        const int src = __ffs(dm) - 1;
-                        dm &= dm - 1u;
-                        const int key = __shfl_sync(0xffffffffu, r.z, src);
-                        const int2 row = __ldg(&t_row_by_key[key]);
-                        int base = 0;
-                        if (lane == 0 && row.y > 0) base = atomicAdd(&s_tail[cur], row.y);
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        for (int q = lane; q < row.y; q += 32) {
-                            fkm[base + q] = __ldg(&t_dep_km[row.x + q]);
-                            frem[base + q] = __ldg(&t_dep_rt[row.x + q]);       // RCE:542-560
-                        }
-                    }
+            // ---- H: the deps of the pre-tick snapshot [0, nF); survivors slide down to [0, p) ----
+            int nO_next = 0;
+            int p = 0;
+            int ddone = 0, nf_done = 0;
+            bool rescan = false;
+            for (int kb = 0; kb < nF; kb += 32 * RAMP_U) {
+                unsigned long long km[RAMP_U];
+                int child[RAMP_U];
+                double rem[RAMP_U];
+#pragma unroll
+                for (int u = 0; u < RAMP_U; ++u) {
+                    const int k = kb + u * 32 + lane;
+                    km[u] = 0ull; child[u] = 0; rem[u] = 1.0;
+                    if (k < nF) f_get(fr, k, km[u], rem[u], child[u]);
                 }
-            }
-            // ---- P3.H: tick the deps of the pre-tick snapshot [0, nF) (RCE:718-775, JOB:559-563, 525-536) ----
-            int ddone_local = 0;
-            for (int kb = 0; kb < nF; kb += NT) {
-                const int k = kb + tid;
-                bool readied = false;
-                int child = 0;
-                if (k < nF) {
-                    const unsigned long long km = fkm[k];
-                    if (km != 0ull) {
-                        const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
-                        const bool is_flow = (km >> 48) != 0ull;
-                        if (c != RAMP_NO_CHANNEL) ckey[c] = 0u;             // release this tick's channel winner slot
-                        if (!(any_nf && is_flow)) {                         // RCE:434-439
-                            const double rem = tick_down(frem[k], tick);
-                            if (rem == 0.0) {
-                                fkm[k] = 0ull;                              // completed: dead in place
-                                ++ddone_local;
-                                child = __ldg(&t_dst_by_key[(uint32_t)km]);
-                                const uint32_t cnt = atomicAdd(&sv.par_done[child], 1u) + 1u;      // JOB:530
-                                readied = (cnt == (uint32_t)__ldg(&t_n_parents[child]));           // JOB:531 (fires once)
-                            } else {
-                                frem[k] = rem;
+                __syncwarp();          // every lane has read this batch before any survivor is written over it
+                uint32_t cnt[RAMP_U];
+                uint32_t np[RAMP_U];
+                int4 reca[RAMP_U];
+                int2 recb[RAMP_U];
+                bool done[RAMP_U];
+#pragma unroll
+                for (int u = 0; u < RAMP_U; ++u) {
+                    done[u] = false; cnt[u] = 0u; np[u] = 1u; reca[u] = make_int4(0, 0, 0, 0); recb[u] = make_int2(0, 0);
+                    if (km[u] != 0ull) {
+                        const bool is_flow = (km[u] >> 48) != 0ull;
+                        if (!(any_nf && is_flow)) {                                              // RCE:434-439
+                            const double r2 = tick_down(rem[u], tick);                           // JOB:561
+                            rem[u] = r2;
+                            if (r2 == 0.0) {                                                     // JOB:562, 525-536
+                                done[u] = true;
+                                cnt[u] = atomicAdd(&par_done[child[u]], 1u) + 1u;               // JOB:530
+                                np[u] = (uint32_t)__ldg(&t_n_parents[child[u]]);
+                                reca[u] = __ldg(&t_op_rec[child[u]]);
+                                recb[u] = __ldg(&t_op_row[child[u]]);
                             }
                         }
                     }
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, readied);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    int base = 0;
-                    if (lane == leader) base = atomicAdd(&s_n_ops[nxt], __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (readied) ops_n[base + __popc(m & ((1u << lane) - 1u))] = __ldg(&t_op_rec[child]);
-                }
-            }
-            done_local = warp_sum_i32(done_local);
-            ddone_local = warp_sum_i32(ddone_local);
-            if (lane == 0) {
-                if (done_local) atomicAdd(&s_ops_completed, done_local);
-                if (ddone_local) { atomicAdd(&s_deps_completed, ddone_local); atomicAdd(&s_dead[cur], ddone_local); }
-            }
-            __syncthreads();
-
-            // ---- K, L + frontier bookkeeping: every thread derives the same values from the shared counters ----
-            const int nF2 = s_tail[cur];                  // snapshot + deps made ready this tick
-            const int live = live0 - s_dead[cur] + (nF2 - nF);
-            const bool finished = (s_ops_completed == N) && (s_deps_completed == E);     // JOB:549-551
-            const bool stop = finished || isinf(tick);                                    // RCE:462
-            const bool compact = !stop && (nF2 > 2 * live + NT);
-            if (big_ops) {
-                for (int i = tid; i < W; i += NT) wkey[i] = 0u;
-                __syncthreads();
-            }
-            if (compact) {
-                // copy the live entries to the other buffer (order is irrelevant: the arg-max is by key)
-                unsigned long long* gkm = fkm_alt;
-                double* grem = frem_alt;
-                for (int kb = 0; kb < nF2; kb += NT) {
-                    const int k = kb + tid;
-                    unsigned long long km = 0ull;
-                    if (k < nF2) km = fkm[k];
-                    const bool keep = km != 0ull;
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);
-                    if (m) {
-                        const int leader = __ffs(m) - 1;
-                        int base = 0;
-                        if (lane == leader) base = atomicAdd(&s_ctail, __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, leader);
-                        if (keep) {
-                            const int p = base + __popc(m & ((1u << lane) - 1u));
-                            gkm[p] = km;
-                            grem[p] = frem[k];
+#pragma unroll
+                for (int u = 0; u < RAMP_U; ++u) {
+                    bool readied = false;
+                    const bool keep = (km[u] != 0ull) && !done[u];
+                    if (km[u] != 0ull && (km[u] >> 48) != 0ull) {
+                        const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
+                        if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km[u]) {
+                            if (done[u]) rescan = true;            // the channel's winner completed: recompute the slots
+                            else crem[c] = rem[u];                 // keep the winner's remaining time current
                         }
                     }
+                    if (done[u]) {
+                        ++ddone;
+                        if ((km[u] >> 48) == 0ull) ++nf_done;
+                        readied = (cnt[u] == np[u]);                                             // JOB:531 (fires once)
+                    }
+                    const unsigned mk = __ballot_sync(FULL, keep);
+                    if (keep) f_put(fr, p + __popc(mk & lt_mask), km[u], rem[u], child[u]);
+                    p += __popc(mk);
+                    const unsigned m = __ballot_sync(FULL, readied);
+                    if (readied) ops_put(ops_n, nO_next + __popc(m & lt_mask), reca[u], recb[u]);
+                    nO_next += __popc(m);
                 }
-                fkm_alt = fkm; frem_alt = frem; fkm = gkm; frem = grem;
-                __syncthreads();
             }
-            nF = compact ? live : nF2;
-            live0 = live;
-            if (tid == 0) {
-                // next tick's append tail / completion counter (first touched two barriers from now)
-                s_tail[nxt] = nF; s_dead[nxt] = 0;
-                s_n_ops[cur] = 0;
-                if (!finished && isinf(tick)) status = RAMP_ST_INFINITE_TICK;
+            ddone = warp_sum_i32(ddone);
+            nf_done = warp_sum_i32(nf_done);
+            rescan = __any_sync(FULL, rescan);
+            deps_completed += ddone;
+
+            // ---- G: tick the op winners; rows of the completed ops are appended at [p, tail) ----
+            int tail = p;
+            int arr_nonflow = 0;                // lane-local count of arriving non-flow deps
+            {
+                int j = 0;
+                for (int kb = 0; kb < nO; kb += 32, ++j) {
+                    const int k = kb + lane;
+                    const bool valid = k < nO;
+                    int4 ra = make_int4(0, 0, 0, 0);
+                    int2 rb = make_int2(0, 0);
+                    bool done = false;
+                    if (valid) {
+                        ops_get(ops, k, ra, rb);
+                        bool win;
+                        if (big_ops) win = wkey[ra.w] == (uint32_t)ra.z;
+                        else { win = ((win_mask >> j) & 1u) != 0u; wkey[ra.w] = 0u; }   // release the winner slot
+                        if (win) {
+                            const double rem = tick_down(__hiloint2double(ra.y, ra.x), tick);   // JOB:555
+                            if (rem == 0.0) done = true;                                        // JOB:556
+                            else { ra.x = __double2loint(rem); ra.y = __double2hiint(rem); }
+                        }
+                    }
+                    const bool keep = valid && !done;
+                    const unsigned km_ = __ballot_sync(FULL, keep);
+                    if (keep) ops_put(ops_n, nO_next + __popc(km_ & lt_mask), ra, rb);
+                    nO_next += __popc(km_);
+                    const unsigned dm = __ballot_sync(FULL, done);
+                    if (dm) {
+                        // JOB:496-506: the out-edges of every op completed here become ready: the rows are copied as ONE
+                        // flattened range so that all template loads of a batch are in flight together.
+                        ops_completed += __popc(dm);
+                        const int deg = done ? rb.y : 0;
+                        int inc = deg;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(FULL, inc, o);
+                            if (lane >= o) inc += v;
+                        }
+                        const int total = __shfl_sync(FULL, inc, 31);
+                        const int exc = inc - deg;
+                        for (int jb = 0; jb < total; jb += 32 * RAMP_U) {
+                            unsigned long long km[RAMP_U];
+                            double rt[RAMP_U];
+                            int dst[RAMP_U];
+#pragma unroll
+                            for (int u = 0; u < RAMP_U; ++u) {
+                                const int jf = jb + u * 32 + lane;
+                                const int jc = jf < total ? jf : total - 1;
+                                int lo = 0;                 // owner = first lane whose inclusive prefix exceeds jc
+#pragma unroll
+                                for (int step = 16; step > 0; step >>= 1) {
+                                    const int v = __shfl_sync(FULL, inc, lo + step - 1);
+                                    if (v <= jc) lo += step;
+                                }
+                                const int o_start = __shfl_sync(FULL, rb.x, lo);
+                                const int o_exc = __shfl_sync(FULL, exc, lo);
+                                const int e = o_start + (jc - o_exc);
+                                km[u] = 0ull; rt[u] = 0.0; dst[u] = 0;
+                                if (jf < total) {
+                                    km[u] = __ldg(&t_dep_km[e]);
+                                    rt[u] = __ldg(&t_dep_rt[e]);                                // RCE:542-560
+                                    dst[u] = __ldg(&t_dep_dst[e]);
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < RAMP_U; ++u) {
+                                const int jf = jb + u * 32 + lane;
+                                if (jf < total) {
+                                    f_put(fr, tail + jf, km[u], rt[u], dst[u]);
+                                    if ((km[u] >> 48) == 0ull) ++arr_nonflow;
+                                    else if (!rescan) {
+                                        const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
+                                        if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km[u]);
+                                    }
+                                }
+                            }
+                        }
+                        tail += total;
+                    }
+                }
             }
-            cur = nxt;
-            { int4* tmp = ops_a; ops_a = ops_b; ops_b = tmp; }
-            if (stop) break;
+            if (big_ops) { __syncwarp(); for (int i = lane; i < W; i += 32) wkey[i] = 0u; }
+            arr_nonflow = warp_sum_i32(arr_nonflow);
+            n_nonflow += arr_nonflow - nf_done;
+            __syncwarp();
+
+            // ---- channel winner slots ----
+            if (rescan) {
+                // a completed flow held its channel's slot: recompute the per-channel arg-max from the ready deps (RCE:665-689)
+                for (int c = lane; c < C; c += 32) ckey[c] = 0u;
+                __syncwarp();
+                for (int k = lane; k < tail; k += 32) {
+                    unsigned long long w; double r;
+                    f_get_km_rem(fr, k, w, r);
+                    if ((w >> 48) != 0ull) {
+                        const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
+                        if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)w);
+                    }
+                }
+                __syncwarp();
+            }
+            // remaining time of (possibly new) winners: all ready deps after a rescan, else only this tick's arrivals
+            for (int k = (rescan ? 0 : p) + lane; k < tail; k += 32) {
+                unsigned long long w; double r;
+                f_get_km_rem(fr, k, w, r);
+                if ((w >> 48) != 0ull) {
+                    const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
+                    if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)w) crem[c] = r;
+                }
+            }
+            __syncwarp();
+
+            // ---- K, L ----
+            const bool finished = (ops_completed == N) && (deps_completed == E);     // JOB:549-551
+            if (!finished && isinf(tick)) status = RAMP_ST_INFINITE_TICK;             // RCE:462
+            if (finished || isinf(tick)) break;
+            nF = tail;
+            nO = nO_next;
+            { const OpsView tmp = ops; ops = ops_n; ops_n = tmp; }
         }
 
         // ---- results (RCE:450-452): copy the trace to an exactly-sized pool allocation ----
-        if (tid == 0) {
+        const int n_rec = tick_no < a.trace_cap ? tick_no : a.trace_cap;
+        long long off = -1;
+        if (lane == 0) {
             const double steps = (double)T.num_training_steps;
             a.res.jct[item.slot] = __dmul_rn(t, steps);
             a.res.comm[item.slot] = __dmul_rn(comm, steps);
             a.res.comp[item.slot] = __dmul_rn(comp, steps);
             a.res.n_ticks[item.slot] = tick_no;
-            const int n_rec = tick_no < a.trace_cap ? tick_no : a.trace_cap;
-            long long off = -1;
             if (a.pool.top != nullptr) {
                 const unsigned long long o = atomicAdd(a.pool.top, (unsigned long long)n_rec);
                 if (o + (unsigned long long)n_rec <= a.pool.len) off = (long long)o;
@@ -528,22 +592,20 @@ __global__ void __launch_bounds__(NT) ramp_lookahead_kernel(const LookaheadArgs 
             }
             a.res.trace_off[item.slot] = off;
             a.res.status[item.slot] = status;
-            s_trace_off = off;
-            s_n_rec = n_rec;
             if (a.stats) {
                 atomicAdd(&a.stats->lookaheads, 1ull);
                 atomicAdd(&a.stats->alg_bytes, (unsigned long long)(T.algorithmic_bytes_static + 12ull * (unsigned long long)tick_no));
             }
         }
-        __syncthreads();
-        if (s_trace_off >= 0) {
-            const int n_rec = s_n_rec;
-            for (int k = tid; k < n_rec; k += NT) {
-                a.pool.n_active[s_trace_off + k] = sv.tr_n[k];
-                a.pool.tick[s_trace_off + k] = sv.tr_tick[k];
+        off = __shfl_sync(FULL, off, 0);
+        __syncwarp();
+        if (off >= 0) {
+            for (int k = lane; k < n_rec; k += 32) {
+                a.pool.n_active[off + k] = sv.tr_n[k];
+                a.pool.tick[off + k] = sv.tr_tick[k];
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 

@@ -33,7 +33,7 @@ if __name__ == '__main__':
     n = sys.argv[1] if len(sys.argv) > 1 else '4096'
     degree = sys.argv[2] if len(sys.argv) > 2 else '16'
     for nt in (32, 64, 128, 256):
-        for cps in (0, 8):
+        for cps in (0,):
             env = dict(os.environ, RAMP_LOOKAHEAD_THREADS=str(nt))
             if cps:
                 env['RAMP_LOOKAHEAD_CTAS_PER_SM'] = str(cps)
