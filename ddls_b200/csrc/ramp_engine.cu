@@ -426,6 +426,17 @@ int ramp_reset(ramp_engine_t* e, const ramp_arrival_t* arrivals, int32_t n_jobs)
     return RAMP_OK;
 }
 
+int ramp_set_arrivals(ramp_engine_t* e, int32_t episode, int32_t first_job, const ramp_arrival_t* rows, int32_t n) {
+    if (!e || !rows) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    if (episode < 0 || episode >= e->cfg.n_episodes || first_job < 0 || n < 0 || first_job + n > e->cfg.max_jobs)
+        return set_error(RAMP_ERR_BAD_ARG, "arrival rows [%d, %d) of episode %d out of range (max_jobs=%d)", first_job, first_job + n, episode, e->cfg.max_jobs);
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(e->d_arrivals + (size_t)episode * e->cfg.max_jobs + first_job, rows, sizeof(ramp_arrival_t) * (size_t)n,
+                             cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RAMP_OK;
+}
+
 int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t fuse, double* d_stats_out, int32_t* d_ncs_out) {
     if (!e || !d_actions) return set_error(RAMP_ERR_BAD_ARG, "null argument");
     if (e->ep.n_jobs < 1) return set_error(RAMP_ERR_BAD_ARG, "ramp_reset must be called before ramp_step");

@@ -86,6 +86,7 @@ def load_library():
     L.ramp_register_template.argtypes = [C.c_void_p, C.POINTER(_LoweredJob), C.POINTER(C.c_int32)]
     L.ramp_template_count.argtypes = [C.c_void_p]
     L.ramp_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.ramp_set_arrivals.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
     L.ramp_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.ramp_step_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.ramp_sync.argtypes = [C.c_void_p]
@@ -103,7 +104,7 @@ def load_library():
     L.ramp_get_lookahead_kernel_time.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
     for name in ('ramp_engine_create', 'ramp_engine_destroy', 'ramp_register_template', 'ramp_template_count',
-                 'ramp_reset', 'ramp_step_host', 'ramp_step_device', 'ramp_sync', 'ramp_check_status',
+                 'ramp_reset', 'ramp_set_arrivals', 'ramp_step_host', 'ramp_step_device', 'ramp_sync', 'ramp_check_status',
                  'ramp_get_job_records', 'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_export_episode_state_to',
                  'ramp_get_memo_stats', 'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_get_lookahead_kernel_time'):
         getattr(L, name).restype = C.c_int
@@ -112,7 +113,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ['ramp_last_error', 'ramp_engine_create', 'ramp_engine_destroy', 'ramp_engine_stream',
-                    'ramp_register_template', 'ramp_template_count', 'ramp_reset', 'ramp_step_host',
+                    'ramp_register_template', 'ramp_template_count', 'ramp_reset', 'ramp_set_arrivals', 'ramp_step_host',
                     'ramp_step_device', 'ramp_sync', 'ramp_check_status', 'ramp_get_job_records',
                     'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_export_episode_state_to',
                     'ramp_get_memo_stats',
@@ -186,6 +187,10 @@ class RampEngine:
         assert arr.ndim == 2 and arr.shape[0] == self.n_episodes
         _check(self._L.ramp_reset(self._h, arr.ctypes.data, arr.shape[1]))
         self.n_jobs = arr.shape[1]
+
+    def set_arrivals(self, episode, first_job, rows):
+        rows = np.ascontiguousarray(rows, dtype=ARRIVAL_DTYPE).reshape(-1)
+        _check(self._L.ramp_set_arrivals(self._h, episode, first_job, rows.ctypes.data, len(rows)))
 
     def make_actions(self):
         a = np.zeros(self.n_episodes, dtype=ACTION_DTYPE)

@@ -163,6 +163,11 @@ int ramp_template_count(ramp_engine_t* eng);
 /* RCE:202-295 for every episode.  arrivals: HOST [n_episodes][n_jobs]; clears the memo (RCE:269-275). */
 int ramp_reset(ramp_engine_t* eng, const ramp_arrival_t* arrivals, int32_t n_jobs);
 
+/* Overwrites arrival rows [first_job, first_job + n) of one episode (HOST rows).  Lets a host-driven caller (the
+ * drop-in RampClusterEnvironment, whose JobsGenerator samples the next job only when needed, RCE:351-377) stream
+ * the arrival process instead of fixing it at reset. */
+int ramp_set_arrivals(ramp_engine_t* eng, int32_t episode, int32_t first_job, const ramp_arrival_t* rows, int32_t n);
+
 /* One RampClusterEnvironment.step for every episode.  HOST buffers; the host<->device copies are issued
  * on the engine stream inside the call:  actions [n_episodes] in,  stats [n_episodes][RAMP_STEP_STATS_LEN]
  * out (may be NULL).  fuse_empty_steps != 0 additionally runs, per episode, the RJPE:394-395 loop
