@@ -272,15 +272,16 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned char* my_smem = smem_raw + (size_t)warp * lookahead_smem_per_warp(a.w_cap, a.c_cap);
+    // layout by decreasing alignment: int4 | 8-byte arrays | 4-byte arrays (c_cap may be odd)
+    int4* ops_a_sm0 = reinterpret_cast<int4*>(my_smem);                                  // [2][RAMP_OPS_CAP]
     FrontView fr;
-    fr.km_sm = reinterpret_cast<unsigned long long*>(my_smem);
-    fr.rem_sm = reinterpret_cast<double*>(fr.km_sm + RAMP_F_CAP);
-    double* crem = fr.rem_sm + RAMP_F_CAP;                               // [c_cap] remaining time of the channel's winner
-    int4* ops_a_sm0 = reinterpret_cast<int4*>(crem + a.c_cap);
-    int2* ops_b_sm0 = reinterpret_cast<int2*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);
-    fr.dst_sm = reinterpret_cast<int32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);
-    uint32_t* wkey = reinterpret_cast<uint32_t*>(fr.dst_sm + RAMP_F_CAP);   // [w_cap] best key among the ready ops on the worker
-    uint32_t* ckey = wkey + a.w_cap;                                         // [c_cap] best key among the ready flows on the channel
+    fr.km_sm = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);      // [RAMP_F_CAP]
+    fr.rem_sm = reinterpret_cast<double*>(fr.km_sm + RAMP_F_CAP);                        // [RAMP_F_CAP]
+    double* crem = fr.rem_sm + RAMP_F_CAP;                                               // [c_cap] remaining time of the channel's winner
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(crem + a.c_cap);                           // [2][RAMP_OPS_CAP]
+    fr.dst_sm = reinterpret_cast<int32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);                // [RAMP_F_CAP]
+    uint32_t* wkey = reinterpret_cast<uint32_t*>(fr.dst_sm + RAMP_F_CAP);                // [w_cap] best key among the ready ops on the worker
+    uint32_t* ckey = wkey + a.w_cap;                                                     // [c_cap] best key among the ready flows on the channel
 
     unsigned char* slab = a.scratch + (uint64_t)(blockIdx.x * WPB + warp) * a.scratch_stride;
     const uint64_t trace_region = a.scratch_stride - align_up((uint64_t)a.trace_cap * 12, 16);

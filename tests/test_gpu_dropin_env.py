@@ -36,7 +36,11 @@ def test_dropin_env_replays_reference_episode(fname):
     # needs an original job per arrival
     jobs = [synthetic.build_original_job(job_id=100 + k, model='m', orig_op_mem=float(arr[k, 1]), orig_dep_size=float(arr[k, 2]),
                                          frac=0.5, seq_time=1000.0, num_training_steps=50) for k in range(n_jobs)]
-    gaps = [float(x) for x in arr[:-1, 0]]          # gap drawn when job k arrives (k < last)
+    gaps = [float(x) for x in arr[:, 0] if np.isfinite(x)]       # gap drawn when job k arrives
+    if np.isfinite(arr[-1, 0]):
+        # the reference's generator still held jobs when the episode ended (max_simulation_run_time): keep ours non-empty too
+        jobs += [synthetic.build_original_job(900 + k, 'm', 1.0, 1.0, 0.5, 1000.0, 50) for k in range(2)]
+        gaps += [float(arr[-1, 0])] * 2
     gen = synthetic.SyntheticJobsGenerator(jobs, gaps)
     env = _make_env(g)
     env.reset(gen, max_simulation_run_time=g.max_sim_time)
@@ -46,7 +50,12 @@ def test_dropin_env_replays_reference_episode(fname):
         if tmpl is not None:
             queued = list(env.job_queue.jobs.values())[0]
             tmpl.model_id = 0
-            action, _ = synthetic.build_action(tmpl, queued, env)
+            # the fixtures do not store global worker ids: give the job any free workers (the reference's own run had
+            # as many free at this point, the dynamics being identical)
+            w2n = env.topology.graph.graph['worker_to_node']
+            free = [w for w in sorted(w2n) if len(env.topology.graph.nodes[w2n[w]]['workers'][w].mounted_job_idx_to_ops) == 0]
+            assert len(free) >= tmpl.n_workers
+            action, _ = synthetic.build_action(tmpl, queued, env, worker_ids=free[:tmpl.n_workers])
             # the fixture's memo key is (model, degree); reproduce the model identity through the job's model name
             action.actions['op_partition'].partitioned_jobs[queued.job_id].details['model'] = f'model{g.templates[int(g.d["step_tid"][s])].model_id}'
         else:
@@ -95,9 +104,10 @@ def test_dropin_env_enforces_ramp_rule_one_job_per_worker():
     t.mount = copy.copy(t.mount)
     t.mount.max_acceptable_jct = float('inf')
     q = list(env.job_queue.jobs.values())[0]
-    a, _ = synthetic.build_action(t, q, env)
+    w = sorted(env.topology.graph.graph['worker_to_node'])[:t.n_workers]
+    a, _ = synthetic.build_action(t, q, env, worker_ids=w)
     env.step(a)                       # job 0 now runs on its workers; job 1 arrives 1 time unit later
     q = list(env.job_queue.jobs.values())[0]
-    a, _ = synthetic.build_action(t, q, env)
+    a, _ = synthetic.build_action(t, q, env, worker_ids=w)
     with pytest.raises(Exception, match='one_job_per_worker'):
         env.step(a)
