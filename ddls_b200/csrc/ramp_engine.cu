@@ -53,6 +53,14 @@ LookaheadKernel lookahead_kernel_for(int nt) {   // nt = threads per CTA = 32 x 
     }
 }
 
+LookaheadKernel lookahead_cta_kernel_for(int nt) {   // one CTA of nt threads per lookahead
+    switch (nt) {
+        case 64: return ramp_lookahead_cta_kernel<2>;
+        case 128: return ramp_lookahead_cta_kernel<4>;
+        default: return nullptr;
+    }
+}
+
 struct HostTemplate {
     TemplateDev dev;             // copy of what sits in the device array
     void* blob = nullptr;        // single device allocation holding all arrays
@@ -96,6 +104,13 @@ struct ramp_engine {
     int nt = 128;                // threads per lookahead CTA = 32 x warps, one lookahead per warp (RAMP_LOOKAHEAD_THREADS overrides)
     int max_ctas_per_sm = 0;     // optional cap (RAMP_LOOKAHEAD_CTAS_PER_SM)
     size_t smem_bytes = 0;
+    // CTA-per-lookahead variant (lower latency; used when a launch has fewer work items than warp slots)
+    int cta_nt = 0;              // 0 = pick 128 or 64 threads per launch; RAMP_LOOKAHEAD_CTA_THREADS forces one
+    int cta_grid = 0;            // resident CTAs of the 128-thread variant
+    int cta64_grid = 0;          // resident CTAs of the 64-thread variant
+    size_t cta_smem_bytes = 0;
+    int mode = 0;                // 0 auto, 1 warp-per-lookahead, 2 CTA-per-lookahead (RAMP_LOOKAHEAD_MODE)
+    int32_t* h_n_work = nullptr; // pinned
     // standalone lookahead buffers
     ResultSlots sa_res{};
     int32_t sa_cap = 0;
@@ -155,13 +170,28 @@ int ensure_scratch(ramp_engine* e) {
         e->grid = e->sm_count * occ;     // persistent CTAs: a whole number of waves (148 SMs x resident CTAs per SM)
         e->smem_bytes = smem;
     }
-    if (stride != e->scratch_stride || e->grid != e->scratch_grid || e->d_scratch == nullptr) {
+    const size_t cta_smem = lookahead_cta_smem(e->max_w, e->max_c);
+    if (cta_smem > 200 * 1024)
+        return set_error(RAMP_ERR_CAPACITY, "a template needs %zu B of shared memory (max 200 KiB)", cta_smem);
+    if (cta_smem != e->cta_smem_bytes || e->cta_grid == 0) {
+        for (int nt : {128, 64}) {
+            LookaheadKernel kern = lookahead_cta_kernel_for(nt);
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
+            int occ = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, cta_smem));
+            if (occ < 1) occ = 1;
+            (nt == 128 ? e->cta_grid : e->cta64_grid) = e->sm_count * occ;
+        }
+        e->cta_smem_bytes = cta_smem;
+    }
+    const int n_slabs = std::max(e->grid * (e->nt / 32), std::max(e->cta_grid, e->cta64_grid));   // one slab per lookahead in flight
+    if (stride != e->scratch_stride || n_slabs != e->scratch_grid || e->d_scratch == nullptr) {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (e->d_scratch) cudaFree(e->d_scratch);
         e->d_scratch = nullptr;
-        CUDA_TRY(cudaMalloc(&e->d_scratch, stride * (uint64_t)e->grid * (uint64_t)(e->nt / 32)));   // one slab per warp
+        CUDA_TRY(cudaMalloc(&e->d_scratch, stride * (uint64_t)n_slabs));
         e->scratch_stride = stride;
-        e->scratch_grid = e->grid;
+        e->scratch_grid = n_slabs;
     }
     return RAMP_OK;
 }
@@ -183,6 +213,27 @@ LookaheadArgs make_lookahead_args(ramp_engine* e, const WorkItem* items, Counter
     a.c_cap = e->max_c;
     a.stats = stats;
     return a;
+}
+
+// Launches the lookahead kernel for n_items work items: one CTA per lookahead when the items fit in about one wave of
+// CTAs (latency-bound regime), one warp per lookahead otherwise (instruction-efficiency regime).
+void launch_lookahead(ramp_engine* e, const LookaheadArgs& a, int n_items, cudaStream_t st) {
+    // measured on B200 (profiles/r1_tune_cta.txt, ResNet-50-like degree-16 lookahead): 128-thread CTAs 4.3 ms each while
+    // they all fit in one wave, 64-thread CTAs 6.0 ms, one warp 7.7 ms but the most lookaheads per SM
+    int cta_nt = 0;
+    if (e->mode != 1) {
+        if (e->cta_nt) { if (e->mode == 2 || n_items <= (e->cta_nt == 128 ? e->cta_grid : e->cta64_grid)) cta_nt = e->cta_nt; }
+        else if (n_items <= e->cta_grid) cta_nt = 128;
+        else if (n_items <= e->cta64_grid || e->mode == 2) cta_nt = 64;
+    }
+    if (cta_nt) {
+        const int grid = std::max(1, std::min(cta_nt == 128 ? e->cta_grid : e->cta64_grid, n_items));
+        lookahead_cta_kernel_for(cta_nt)<<<grid, cta_nt, e->cta_smem_bytes, st>>>(a);
+    } else {
+        const int wpb = e->nt / 32;
+        const int grid = std::max(1, std::min(e->grid, (n_items + wpb - 1) / wpb));
+        lookahead_kernel_for(e->nt)<<<grid, e->nt, e->smem_bytes, st>>>(a);
+    }
 }
 
 uint64_t fnv1a(const unsigned char* p, size_t n) {
@@ -231,6 +282,12 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
         e->nt = nt;
     }
     if (const char* v = getenv("RAMP_LOOKAHEAD_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
+    if (const char* v = getenv("RAMP_LOOKAHEAD_CTA_THREADS")) {
+        const int nt = atoi(v);
+        if (lookahead_cta_kernel_for(nt) == nullptr) { delete e; return set_error(RAMP_ERR_BAD_ARG, "RAMP_LOOKAHEAD_CTA_THREADS must be 64 or 128"); }
+        e->cta_nt = nt;
+    }
+    if (const char* v = getenv("RAMP_LOOKAHEAD_MODE")) e->mode = !strcmp(v, "warp") ? 1 : !strcmp(v, "cta") ? 2 : 0;
     cudaDeviceProp prop{};
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg.device));
     e->sm_count = prop.multiProcessorCount;
@@ -261,6 +318,7 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     CUDA_TRY(cudaMalloc(&e->d_step_stats, sizeof(double) * RAMP_STEP_STATS_LEN * B));
     CUDA_TRY(cudaMalloc(&e->d_n_cluster_steps, sizeof(int32_t) * B));
     CUDA_TRY(cudaMalloc(&e->d_ep_export, sizeof(double) * RAMP_EP_LEN * B));
+    CUDA_TRY(cudaMallocHost(&e->h_n_work, sizeof(int32_t)));
 
     EpisodeState& ep = e->ep;
     ep.B = B; ep.max_running = cfg.max_running; ep.max_jobs = cfg.max_jobs; ep.n_jobs = 0;
@@ -296,7 +354,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     cudaFree(e->d_items); cudaFree(e->d_counters); cudaFree(e->d_stats); cudaFree(e->d_actions);
     cudaFree(e->d_step_stats); cudaFree(e->d_n_cluster_steps); cudaFree(e->d_ep_export);
     cudaFree(e->ep.ef); cudaFree(e->ep.ei); cudaFree(e->ep.rf); cudaFree(e->ep.ri); cudaFree(e->ep.rec);
-    cudaFree(e->d_arrivals); cudaFree(e->d_scratch); cudaFree(e->sa_items); cudaFree(e->sa_counters);
+    cudaFree(e->d_arrivals); cudaFree(e->d_scratch); cudaFree(e->sa_items); cudaFree(e->sa_counters); cudaFreeHost(e->h_n_work);
     for (int k = 0; k < MAX_EVENT_PAIRS; ++k) { cudaEventDestroy(e->ev_a[k]); cudaEventDestroy(e->ev_b[k]); }
     cudaStreamDestroy(e->stream);
     delete e;
@@ -457,11 +515,17 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
     if (!e->templates.empty()) {
         if (e->ev_pending >= MAX_EVENT_PAIRS) { CUDA_TRY(cudaStreamSynchronize(st)); int rc = resolve_events(e); if (rc) return rc; }
         LookaheadArgs a = make_lookahead_args(e, e->d_items, e->d_counters, e->res, true, e->d_stats);
-        CUDA_TRY(cudaEventRecord(e->ev_a[e->ev_pending], st));
-        lookahead_kernel_for(e->nt)<<<e->grid, e->nt, e->smem_bytes, st>>>(a);
-        CUDA_TRY(cudaEventRecord(e->ev_b[e->ev_pending], st));
-        e->ev_pending++;
-        e->launches++;
+        // the number of memo misses decides the kernel shape: a 4-byte read-back (~10 us) against a multi-ms kernel
+        CUDA_TRY(cudaMemcpyAsync(e->h_n_work, &e->d_counters->n_work, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const int n_items = *e->h_n_work;
+        if (n_items > 0) {
+            CUDA_TRY(cudaEventRecord(e->ev_a[e->ev_pending], st));
+            launch_lookahead(e, a, n_items, st);
+            CUDA_TRY(cudaEventRecord(e->ev_b[e->ev_pending], st));
+            e->ev_pending++;
+            e->launches++;
+        }
     }
     StepArgs s{};
     s.actions = d_actions; s.ep = e->ep; s.res = e->res; s.pool = e->pool; s.counters = e->d_counters;
@@ -621,7 +685,7 @@ int ramp_run_lookaheads(ramp_engine_t* e, const int32_t* template_ids, int32_t n
     cudaEvent_t ea = e->ev_a[MAX_EVENT_PAIRS - 1], eb = e->ev_b[MAX_EVENT_PAIRS - 1];
     if (e->ev_pending >= MAX_EVENT_PAIRS - 1) { CUDA_TRY(cudaStreamSynchronize(st)); rc = resolve_events(e); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(ea, st));
-    lookahead_kernel_for(e->nt)<<<e->grid, e->nt, e->smem_bytes, st>>>(a);
+    launch_lookahead(e, a, n, st);
     CUDA_TRY(cudaEventRecord(eb, st));
     e->launches++;
     CUDA_TRY(cudaGetLastError());

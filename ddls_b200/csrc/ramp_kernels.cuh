@@ -132,6 +132,9 @@ struct ScratchView {
     unsigned long long* f_km_ovf;    // [E] overflow of the shared-memory dep frontier
     double*   f_rem_ovf;             // [E]
     int32_t*  f_dst_ovf;             // [E]
+    unsigned long long* f_km_ovf2;   // [E] second buffer (CTA-per-lookahead kernel compacts by ping-pong)
+    double*   f_rem_ovf2;            // [E]
+    int32_t*  f_dst_ovf2;            // [E]
     int32_t*  tr_n;                  // [trace_cap] temp trace
     double*   tr_tick;               // [trace_cap]
 };
@@ -141,8 +144,8 @@ __host__ __device__ inline uint64_t scratch_bytes_for(int32_t N, int32_t E) {
     b += align_up((uint64_t)N * 4, 16);
     b += 2 * align_up((uint64_t)N * 16, 16);
     b += 2 * align_up((uint64_t)N * 8, 16);
-    b += 2 * align_up((uint64_t)E * 8, 16);
-    b += align_up((uint64_t)E * 4, 16);
+    b += 4 * align_up((uint64_t)E * 8, 16);
+    b += 2 * align_up((uint64_t)E * 4, 16);
     return b;
 }
 
@@ -157,6 +160,9 @@ __device__ inline ScratchView carve(unsigned char* base, int32_t N, int32_t E, u
     v.f_km_ovf = (unsigned long long*)(base + o);    o += align_up((uint64_t)E * 8, 16);
     v.f_rem_ovf = (double*)(base + o);               o += align_up((uint64_t)E * 8, 16);
     v.f_dst_ovf = (int32_t*)(base + o);              o += align_up((uint64_t)E * 4, 16);
+    v.f_km_ovf2 = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
+    v.f_rem_ovf2 = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
+    v.f_dst_ovf2 = (int32_t*)(base + o);             o += align_up((uint64_t)E * 4, 16);
     v.tr_tick = (double*)(base + trace_region_off);
     v.tr_n = (int32_t*)(v.tr_tick + trace_cap);
     return v;
@@ -609,6 +615,10 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
         __syncwarp();
     }
 }
+
+}  // namespace ramp
+#include "ramp_lookahead_cta.cuh"
+namespace ramp {
 
 // ---------------------------------------------------------------------------------------------------
 // memo lookup / insert + work-list construction (RCE:469-518)

@@ -1,0 +1,481 @@
+// ramp_lookahead_cta.cuh -- _run_lookahead (RCE:379-467) with ONE CTA (NW warps) per lookahead.
+//
+// Same algorithm, records and shared-memory staging as the warp-per-lookahead kernel in ramp_kernels.cuh; the per-tick
+// passes are spread over the CTA's warps so a single lookahead finishes sooner.  The engine picks this kernel when a
+// step has fewer un-memoised lookaheads than the GPU has warp slots (latency matters) and the warp-per-lookahead
+// kernel when there are many (instruction efficiency matters).
+//
+// The dep frontier is one list updated IN PLACE (completed entries are marked dead, ticks that freeze the flows write
+// nothing) and compacted into the other buffer only when more than half of it is dead; newly ready deps are appended
+// at its tail (first ticked next tick: the RCE:429 snapshot).  Per-tick counters live in parity-indexed shared cells
+// so that no thread can reset a cell another thread still has to read.
+#pragma once
+
+namespace ramp {
+
+#ifndef RAMP_CTA_F_CAP
+#define RAMP_CTA_F_CAP 512     // dep-frontier records per buffer kept in shared memory (x2 buffers)
+#endif
+#ifndef RAMP_CTA_MIN_WARPS
+#define RAMP_CTA_MIN_WARPS 16  // resident warps per SM the register allocation must allow
+#endif
+
+struct CtaCells {              // written during tick with parity p, read after that tick's barrier, reset one tick later
+    int n_ops_next;            // op frontier being built for the next tick
+    int tail;                  // dep frontier append cursor
+    int ddone, nf_done, arr_nf, ops_done, rescan, dq_n, n_active;
+    unsigned long long min_op, min_dep;
+};
+
+__host__ __device__ inline size_t lookahead_cta_smem(int w_cap, int c_cap) {
+    size_t b = 0;
+    b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
+    b += (size_t)2 * RAMP_CTA_F_CAP * 8 * 2;     // km, rem (two buffers)
+    b += (size_t)c_cap * 8;                      // crem
+    b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
+    b += (size_t)w_cap * 8;                      // done queue: {row start, degree}
+    b += (size_t)2 * RAMP_CTA_F_CAP * 4;         // dst (two buffers)
+    b += (size_t)(w_cap + c_cap) * 4;            // wkey, ckey
+    return (b + 15) & ~(size_t)15;
+}
+
+struct FrontBuf { unsigned long long* km_sm; double* rem_sm; int32_t* dst_sm; unsigned long long* km_ovf; double* rem_ovf; int32_t* dst_ovf; };
+__device__ __forceinline__ unsigned long long fb_km(const FrontBuf& v, int k) { return (k < RAMP_CTA_F_CAP) ? v.km_sm[k] : v.km_ovf[k - RAMP_CTA_F_CAP]; }
+__device__ __forceinline__ double fb_rem(const FrontBuf& v, int k) { return (k < RAMP_CTA_F_CAP) ? v.rem_sm[k] : v.rem_ovf[k - RAMP_CTA_F_CAP]; }
+__device__ __forceinline__ int fb_dst(const FrontBuf& v, int k) { return (k < RAMP_CTA_F_CAP) ? v.dst_sm[k] : v.dst_ovf[k - RAMP_CTA_F_CAP]; }
+__device__ __forceinline__ void fb_set_km(const FrontBuf& v, int k, unsigned long long x) { if (k < RAMP_CTA_F_CAP) v.km_sm[k] = x; else v.km_ovf[k - RAMP_CTA_F_CAP] = x; }
+__device__ __forceinline__ void fb_set_rem(const FrontBuf& v, int k, double x) { if (k < RAMP_CTA_F_CAP) v.rem_sm[k] = x; else v.rem_ovf[k - RAMP_CTA_F_CAP] = x; }
+__device__ __forceinline__ void fb_put(const FrontBuf& v, int k, unsigned long long km, double rem, int dst) {
+    if (k < RAMP_CTA_F_CAP) { v.km_sm[k] = km; v.rem_sm[k] = rem; v.dst_sm[k] = dst; }
+    else { v.km_ovf[k - RAMP_CTA_F_CAP] = km; v.rem_ovf[k - RAMP_CTA_F_CAP] = rem; v.dst_ovf[k - RAMP_CTA_F_CAP] = dst; }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahead_cta_kernel(const LookaheadArgs a) {
+    constexpr int NT = NW * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // layout by decreasing alignment
+    int4* ops_a_sm0 = reinterpret_cast<int4*>(smem_raw);                                  // [2][RAMP_OPS_CAP]
+    unsigned long long* km_sm0 = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);   // [2][F_CAP]
+    double* rem_sm0 = reinterpret_cast<double*>(km_sm0 + 2 * RAMP_CTA_F_CAP);            // [2][F_CAP]
+    double* crem = rem_sm0 + 2 * RAMP_CTA_F_CAP;                                          // [c_cap]
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(crem + a.c_cap);                            // [2][RAMP_OPS_CAP]
+    int2* doneq = ops_b_sm0 + 2 * RAMP_OPS_CAP;                                           // [w_cap] rows of ops completed this tick
+    int32_t* dst_sm0 = reinterpret_cast<int32_t*>(doneq + a.w_cap);                       // [2][F_CAP]
+    uint32_t* wkey = reinterpret_cast<uint32_t*>(dst_sm0 + 2 * RAMP_CTA_F_CAP);           // [w_cap]
+    uint32_t* ckey = wkey + a.w_cap;                                                      // [c_cap]
+
+    __shared__ CtaCells cells[2];
+    __shared__ int s_n_ops[2];
+    __shared__ int s_ctail;
+    __shared__ int s_work;
+    __shared__ long long s_trace_off;
+
+    unsigned char* slab = a.scratch + (uint64_t)blockIdx.x * a.scratch_stride;
+    const uint64_t trace_region = a.scratch_stride - align_up((uint64_t)a.trace_cap * 12, 16);
+    const double INF = __longlong_as_double(RAMP_INF_BITS);
+
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(a.cursor, 1);
+        __syncthreads();
+        const int wi = s_work;
+        if (wi >= *a.n_work) break;
+        const WorkItem item = a.items[wi];
+        const TemplateDev& T = a.templates[item.template_id];
+        const int N = T.n_ops, E = T.n_deps, W = T.n_workers, C = T.n_channels;
+        const ScratchView sv = carve(slab, N, E, trace_region, a.trace_cap);
+
+        const int4* __restrict__ t_op_rec = T.op_rec;
+        const int2* __restrict__ t_op_row = T.op_row;
+        const uint16_t* __restrict__ t_n_parents = T.op_n_parents;
+        const unsigned long long* __restrict__ t_dep_km = T.dep_km;
+        const double* __restrict__ t_dep_rt = T.dep_rt;
+        const int32_t* __restrict__ t_dep_dst = T.dep_dst;
+        uint32_t* par_done = sv.par_done;
+
+        FrontBuf F, Falt;
+        F.km_sm = km_sm0; F.rem_sm = rem_sm0; F.dst_sm = dst_sm0;
+        F.km_ovf = sv.f_km_ovf; F.rem_ovf = sv.f_rem_ovf; F.dst_ovf = sv.f_dst_ovf;
+        Falt.km_sm = km_sm0 + RAMP_CTA_F_CAP; Falt.rem_sm = rem_sm0 + RAMP_CTA_F_CAP; Falt.dst_sm = dst_sm0 + RAMP_CTA_F_CAP;
+        Falt.km_ovf = sv.f_km_ovf2; Falt.rem_ovf = sv.f_rem_ovf2; Falt.dst_ovf = sv.f_dst_ovf2;
+        OpsView ops, ops_n;
+        ops.a_sm = ops_a_sm0; ops.b_sm = ops_b_sm0; ops.a_ovf = sv.ops_a_ovf[0]; ops.b_ovf = sv.ops_b_ovf[0];
+        ops_n.a_sm = ops_a_sm0 + RAMP_OPS_CAP; ops_n.b_sm = ops_b_sm0 + RAMP_OPS_CAP; ops_n.a_ovf = sv.ops_a_ovf[1]; ops_n.b_ovf = sv.ops_b_ovf[1];
+
+        // ---- init (JOB:432-484) ----
+        for (int i = tid; i < N; i += NT) par_done[i] = 0u;
+        for (int i = tid; i < W; i += NT) wkey[i] = 0u;
+        for (int i = tid; i < C; i += NT) ckey[i] = 0u;
+        for (int k = tid; k < T.n_src; k += NT) {
+            const int op = __ldg(&T.src_ops[k]);
+            ops_put(ops, k, __ldg(&t_op_rec[op]), __ldg(&t_op_row[op]));          // RCE:1334
+        }
+        if (tid == 0) {
+            for (int q = 0; q < 2; ++q) {
+                cells[q].n_ops_next = 0; cells[q].tail = 0; cells[q].ddone = 0; cells[q].nf_done = 0; cells[q].arr_nf = 0;
+                cells[q].ops_done = 0; cells[q].rescan = 0; cells[q].dq_n = 0; cells[q].n_active = 0;
+                cells[q].min_op = RAMP_INF_BITS; cells[q].min_dep = RAMP_INF_BITS;
+            }
+            s_ctail = 0;
+        }
+        __syncthreads();
+
+        // CTA-uniform state (every thread holds the same values)
+        int nO = T.n_src, nF = 0, live = 0, n_nonflow = 0, ops_completed = 0, deps_completed = 0;
+        int tick_no = 0, status = RAMP_ST_OK, par = 0;
+        double t = 0.0, comm = 0.0, comp = 0.0;      // thread 0
+
+        for (;;) {
+            CtaCells& cc = cells[par];
+            const bool big_ops = nO > 32 * NT;
+
+            // ---- A ----
+            for (int k = tid; k < nO; k += NT) {
+                int4 ra; int2 rb;
+                ops_get(ops, k, ra, rb);
+                atomicMax(&wkey[ra.w], (uint32_t)ra.z);
+            }
+            __syncthreads();
+
+            // ---- B, C, D ----
+            const bool any_nf = n_nonflow > 0;
+            uint32_t win_mask = 0u;
+            {
+                double mo = INF, md = INF;
+                int na = 0, j = 0;
+                for (int k = tid; k < nO; k += NT, ++j) {
+                    int4 ra; int2 rb;
+                    ops_get(ops, k, ra, rb);
+                    if (wkey[ra.w] == (uint32_t)ra.z) {
+                        if (j < 32) win_mask |= 1u << j;
+                        ++na;
+                        const double rem = __hiloint2double(ra.y, ra.x);
+                        mo = (rem < mo) ? rem : mo;
+                    }
+                }
+                if (!any_nf) {
+                    for (int c = tid; c < C; c += NT) {
+                        if (ckey[c] != 0u) { const double rem = crem[c]; md = (rem < md) ? rem : md; }
+                    }
+                }
+                mo = warp_min_f64(mo);
+                md = warp_min_f64(md);
+                na = warp_sum_i32(na);
+                if (lane == 0) {
+                    const unsigned long long bo = (unsigned long long)__double_as_longlong(mo);
+                    const unsigned long long bd = (unsigned long long)__double_as_longlong(md);
+                    if (bo != RAMP_INF_BITS) atomicMin(&cc.min_op, bo);
+                    if (bd != RAMP_INF_BITS) atomicMin(&cc.min_dep, bd);
+                    if (na) atomicAdd(&cc.n_active, na);
+                }
+            }
+            __syncthreads();
+
+            // ---- E ----
+            const double t_op = __longlong_as_double((long long)cc.min_op);
+            const double t_comm = any_nf ? 0.0 : __longlong_as_double((long long)cc.min_dep);
+            const double tick = (t_comm < t_op) ? t_comm : t_op;
+            const int n_active = cc.n_active;
+
+            // ---- I, J (thread 0) + reset of the other parity's cells (last read one barrier ago) ----
+            if (tid == 0) {
+                const bool ticked_ops = n_active > 0;
+                const bool ticked_flows = (!any_nf) && (live > 0);
+                if (ticked_ops && ticked_flows) { comm = __dadd_rn(comm, tick); comp = __dadd_rn(comp, tick); }
+                else if (ticked_flows) comm = __dadd_rn(comm, tick);
+                else if (ticked_ops) comp = __dadd_rn(comp, tick);
+                t = __dadd_rn(t, tick);
+                if (tick_no < a.trace_cap) { sv.tr_n[tick_no] = n_active; sv.tr_tick[tick_no] = tick; }
+                else status = RAMP_ST_TRACE_OVERFLOW;
+                CtaCells& o = cells[par ^ 1];
+                o.ddone = 0; o.nf_done = 0; o.arr_nf = 0; o.ops_done = 0; o.rescan = 0; o.dq_n = 0; o.n_active = 0;
+                o.min_op = RAMP_INF_BITS; o.min_dep = RAMP_INF_BITS;
+                s_ctail = 0;
+            }
+            ++tick_no;
+
+            // ---- H: deps of the pre-tick snapshot [0, nF), batches dealt round-robin to the warps (last warps first) ----
+            {
+                int ddone = 0, nf_done = 0;
+                bool rescan = false;
+                const int n_batches = (nF + 32 * RAMP_U - 1) / (32 * RAMP_U);
+                for (int bi = NW - 1 - warp; bi < n_batches; bi += NW) {
+                    const int kb = bi * 32 * RAMP_U;
+                    unsigned long long km[RAMP_U];
+                    double rem[RAMP_U];
+                    int child[RAMP_U];
+#pragma unroll
+                    for (int u = 0; u < RAMP_U; ++u) {
+                        const int k = kb + u * 32 + lane;
+                        km[u] = 0ull; rem[u] = 1.0; child[u] = 0;
+                        if (k < nF) {
+                            km[u] = fb_km(F, k);
+                            if (km[u] != 0ull && any_nf && (km[u] >> 48) != 0ull) km[u] = 0ull;    // flows are frozen (RCE:434-439)
+                            if (km[u] != 0ull) { rem[u] = fb_rem(F, k); child[u] = fb_dst(F, k); }
+                        }
+                    }
+                    uint32_t cnt[RAMP_U], np[RAMP_U];
+                    int4 reca[RAMP_U];
+                    int2 recb[RAMP_U];
+                    bool done[RAMP_U];
+#pragma unroll
+                    for (int u = 0; u < RAMP_U; ++u) {
+                        done[u] = false; cnt[u] = 0u; np[u] = 1u; reca[u] = make_int4(0, 0, 0, 0); recb[u] = make_int2(0, 0);
+                        if (km[u] != 0ull) {
+                            const int k = kb + u * 32 + lane;
+                            const double r2 = tick_down(rem[u], tick);                               // JOB:561
+                            const bool is_flow = (km[u] >> 48) != 0ull;
+                            const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
+                            const bool winner = is_flow && c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km[u];
+                            if (r2 == 0.0) {                                                         // JOB:562, 525-536
+                                done[u] = true;
+                                fb_set_km(F, k, 0ull);
+                                if (winner) rescan = true;           // the channel's winner completed: recompute the slots
+                                if (!is_flow) ++nf_done;
+                                ++ddone;
+                                cnt[u] = atomicAdd(&par_done[child[u]], 1u) + 1u;                   // JOB:530
+                                np[u] = (uint32_t)__ldg(&t_n_parents[child[u]]);
+                                reca[u] = __ldg(&t_op_rec[child[u]]);
+                                recb[u] = __ldg(&t_op_row[child[u]]);
+                            } else {
+                                fb_set_rem(F, k, r2);
+                                if (winner) crem[c] = r2;            // keep the winner's remaining time current
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < RAMP_U; ++u) {
+                        const bool readied = done[u] && (cnt[u] == np[u]);                           // JOB:531 (fires once)
+                        const unsigned m = __ballot_sync(FULL, readied);
+                        if (m) {
+                            const int leader = __ffs(m) - 1;
+                            int base = 0;
+                            if (lane == leader) base = atomicAdd(&cc.n_ops_next, __popc(m));
+                            base = __shfl_sync(FULL, base, leader);
+                            if (readied) ops_put(ops_n, base + __popc(m & lt_mask), reca[u], recb[u]);
+                        }
+                    }
+                }
+                ddone = warp_sum_i32(ddone);
+                nf_done = warp_sum_i32(nf_done);
+                rescan = __any_sync(FULL, rescan);
+                if (lane == 0) {
+                    if (ddone) atomicAdd(&cc.ddone, ddone);
+                    if (nf_done) atomicAdd(&cc.nf_done, nf_done);
+                    if (rescan) cc.rescan = 1;
+                }
+            }
+            // ---- G: tick the op winners (RCE:691-716); rows of completed ops are queued for the cooperative copy below ----
+            {
+                int j = 0, done_local = 0;
+                for (int kb = 0; kb < nO; kb += NT, ++j) {
+                    const int k = kb + tid;
+                    const bool valid = k < nO;
+                    int4 ra = make_int4(0, 0, 0, 0);
+                    int2 rb = make_int2(0, 0);
+                    bool done = false;
+                    if (valid) {
+                        ops_get(ops, k, ra, rb);
+                        bool win;
+                        if (big_ops) win = wkey[ra.w] == (uint32_t)ra.z;
+                        else { win = ((win_mask >> j) & 1u) != 0u; wkey[ra.w] = 0u; }
+                        if (win) {
+                            const double rem = tick_down(__hiloint2double(ra.y, ra.x), tick);   // JOB:555
+                            if (rem == 0.0) done = true;                                        // JOB:556
+                            else { ra.x = __double2loint(rem); ra.y = __double2hiint(rem); }
+                        }
+                    }
+                    const bool keep = valid && !done;
+                    const unsigned mk = __ballot_sync(FULL, keep);
+                    if (mk) {
+                        const int leader = __ffs(mk) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(&cc.n_ops_next, __popc(mk));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (keep) ops_put(ops_n, base + __popc(mk & lt_mask), ra, rb);
+                    }
+                    const unsigned dm = __ballot_sync(FULL, done);
+                    if (dm) {
+                        const int leader = __ffs(dm) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(&cc.dq_n, __popc(dm));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (done) doneq[base + __popc(dm & lt_mask)] = rb;      // <= 1 completed op per worker per tick
+                        done_local += __popc(dm);
+                    }
+                }
+                if (lane == 0 && done_local) atomicAdd(&cc.ops_done, done_local);
+            }
+            __syncthreads();
+
+            // ---- G (cont.): JOB:496-506 out-edges of the completed ops become ready: each warp takes every NW-th queued row
+            //      and copies its rows as one flattened range (all template loads of a batch in flight together) ----
+            const int nq = cc.dq_n;
+            if (nq > 0) {
+                if (big_ops) for (int i = tid; i < W; i += NT) wkey[i] = 0u;
+                int arr_nf = 0;
+                for (int qb = 0; qb < nq; qb += 32 * NW) {
+                    const int q = qb + lane * NW + warp;
+                    int2 row = make_int2(0, 0);
+                    if (q < nq) row = doneq[q];
+                    int inc = row.y;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    const int total = __shfl_sync(FULL, inc, 31);
+                    const int exc = inc - row.y;
+                    int base = 0;
+                    if (lane == 0 && total > 0) base = atomicAdd(&cc.tail, total);
+                    base = __shfl_sync(FULL, base, 0);
+                    for (int jb = 0; jb < total; jb += 32 * RAMP_U) {
+                        unsigned long long km[RAMP_U];
+                        double rt[RAMP_U];
+                        int dst[RAMP_U];
+#pragma unroll
+                        for (int u = 0; u < RAMP_U; ++u) {
+                            const int jf = jb + u * 32 + lane;
+                            const int jc = jf < total ? jf : total - 1;
+                            int lo = 0;
+#pragma unroll
+                            for (int step = 16; step > 0; step >>= 1) {
+                                const int v = __shfl_sync(FULL, inc, lo + step - 1);
+                                if (v <= jc) lo += step;
+                            }
+                            const int o_start = __shfl_sync(FULL, row.x, lo);
+                            const int o_exc = __shfl_sync(FULL, exc, lo);
+                            const int e = o_start + (jc - o_exc);
+                            km[u] = 0ull; rt[u] = 0.0; dst[u] = 0;
+                            if (jf < total) {
+                                km[u] = __ldg(&t_dep_km[e]);
+                                rt[u] = __ldg(&t_dep_rt[e]);                                    // RCE:542-560
+                                dst[u] = __ldg(&t_dep_dst[e]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < RAMP_U; ++u) {
+                            const int jf = jb + u * 32 + lane;
+                            if (jf < total) {
+                                fb_put(F, base + jf, km[u], rt[u], dst[u]);
+                                if ((km[u] >> 48) == 0ull) ++arr_nf;
+                                else {
+                                    const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
+                                    if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km[u]);
+                                }
+                            }
+                        }
+                    }
+                }
+                arr_nf = warp_sum_i32(arr_nf);
+                if (lane == 0 && arr_nf) atomicAdd(&cc.arr_nf, arr_nf);
+                __syncthreads();
+            } else if (big_ops) {
+                for (int i = tid; i < W; i += NT) wkey[i] = 0u;
+            }
+
+            // ---- K, L + frontier bookkeeping: every thread derives the same values from the shared cells ----
+            const int nF2 = cc.tail;                              // snapshot + this tick's arrivals
+            deps_completed += cc.ddone;
+            ops_completed += cc.ops_done;
+            live += (nF2 - nF) - cc.ddone;
+            n_nonflow += cc.arr_nf - cc.nf_done;
+            const bool rescan = cc.rescan != 0;
+            const int nO_next = cc.n_ops_next;
+            const bool finished = (ops_completed == N) && (deps_completed == E);     // JOB:549-551
+            if (!finished && isinf(tick) && tid == 0) status = RAMP_ST_INFINITE_TICK; // RCE:462
+            if (finished || isinf(tick)) break;
+
+            // channel winner slots
+            if (rescan) {
+                for (int c = tid; c < C; c += NT) ckey[c] = 0u;
+                __syncthreads();
+                for (int k = tid; k < nF2; k += NT) {
+                    const unsigned long long w = fb_km(F, k);
+                    if (w != 0ull && (w >> 48) != 0ull) {
+                        const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
+                        if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)w);
+                    }
+                }
+                __syncthreads();
+            }
+            for (int k = (rescan ? 0 : nF) + tid; k < nF2; k += NT) {
+                const unsigned long long w = fb_km(F, k);
+                if (w != 0ull && (w >> 48) != 0ull) {
+                    const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
+                    if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)w) crem[c] = fb_rem(F, k);
+                }
+            }
+            // compaction when more than half of the frontier is dead (order is irrelevant: arg-max is by key)
+            const bool compact = nF2 > 2 * live + NT;
+            if (compact) {
+                for (int kb = 0; kb < nF2; kb += NT) {
+                    const int k = kb + tid;
+                    unsigned long long w = 0ull;
+                    if (k < nF2) w = fb_km(F, k);
+                    const bool keep = w != 0ull;
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(&s_ctail, __popc(m));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (keep) fb_put(Falt, base + __popc(m & lt_mask), w, fb_rem(F, k), fb_dst(F, k));
+                    }
+                }
+                { const FrontBuf tmp = F; F = Falt; Falt = tmp; }
+                nF = live;
+            } else {
+                nF = nF2;
+            }
+            if (tid == 0) {
+                // only the OTHER parity's cells may be written here: slower threads may still be reading cc.* above
+                cells[par ^ 1].tail = nF;            // next tick's append cursor
+                cells[par ^ 1].n_ops_next = 0;
+            }
+            nO = nO_next;
+            { const OpsView tmp = ops; ops = ops_n; ops_n = tmp; }
+            par ^= 1;
+            __syncthreads();
+        }
+
+        // ---- results (RCE:450-452) ----
+        const int n_rec = tick_no < a.trace_cap ? tick_no : a.trace_cap;
+        if (tid == 0) {
+            const double steps = (double)T.num_training_steps;
+            a.res.jct[item.slot] = __dmul_rn(t, steps);
+            a.res.comm[item.slot] = __dmul_rn(comm, steps);
+            a.res.comp[item.slot] = __dmul_rn(comp, steps);
+            a.res.n_ticks[item.slot] = tick_no;
+            long long off = -1;
+            if (a.pool.top != nullptr) {
+                const unsigned long long o = atomicAdd(a.pool.top, (unsigned long long)n_rec);
+                if (o + (unsigned long long)n_rec <= a.pool.len) off = (long long)o;
+                else if (status == RAMP_ST_OK) status = RAMP_ST_TRACE_OVERFLOW;
+            }
+            a.res.trace_off[item.slot] = off;
+            a.res.status[item.slot] = status;
+            s_trace_off = off;
+            if (a.stats) {
+                atomicAdd(&a.stats->lookaheads, 1ull);
+                atomicAdd(&a.stats->alg_bytes, (unsigned long long)(T.algorithmic_bytes_static + 12ull * (unsigned long long)tick_no));
+            }
+        }
+        __syncthreads();
+        if (s_trace_off >= 0) {
+            for (int k = tid; k < n_rec; k += NT) {
+                a.pool.n_active[s_trace_off + k] = sv.tr_n[k];
+                a.pool.tick[s_trace_off + k] = sv.tr_tick[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace ramp

@@ -27,19 +27,28 @@ def eng_mod():
     return engine
 
 
-def _run_all_templates(engine, templates, n_cluster_workers=64, repeat=1):
-    eng = engine.RampEngine(n_episodes=1, n_cluster_workers=n_cluster_workers, max_jobs=1, trace_cap=1 << 16)
+MODES = ['warp', 'cta']      # both lookahead kernels: one warp per lookahead / one CTA per lookahead
+
+
+def _run_all_templates(engine, templates, n_cluster_workers=64, repeat=1, mode='auto'):
+    import os
+    os.environ['RAMP_LOOKAHEAD_MODE'] = mode
+    try:
+        eng = engine.RampEngine(n_episodes=1, n_cluster_workers=n_cluster_workers, max_jobs=1, trace_cap=1 << 16)
+    finally:
+        os.environ.pop('RAMP_LOOKAHEAD_MODE', None)
     tids = [eng.register_template(t) for t in templates]
     res, ms, tn, tt = eng.run_lookaheads(np.repeat(tids, repeat), want_trace=True)
     eng.close()
     return res, tn, tt
 
 
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('fname', FILES)
-def test_lookahead_vs_reference_golden(fname, eng_mod):
+def test_lookahead_vs_reference_golden(fname, mode, eng_mod):
     """_run_lookahead RCE:379-467: (jct, comm, comp) and the whole tick trace equal the reference's, bit for bit."""
     g = Golden(fname)
-    res, tn, tt = _run_all_templates(eng_mod, g.templates, g.n_cluster_workers)
+    res, tn, tt = _run_all_templates(eng_mod, g.templates, g.n_cluster_workers, mode=mode)
     assert (res['status'] == 0).all()
     for i in range(g.n_lookaheads):
         la = g.lookahead(i)
@@ -51,11 +60,12 @@ def test_lookahead_vs_reference_golden(fname, eng_mod):
         assert res['jct'][k] == la['jct'] and res['comm'][k] == la['comm'] and res['comp'][k] == la['comp']
 
 
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('fname', FILES)
-def test_lookahead_vs_oracle_all_templates(fname, eng_mod, oracle_lib):
+def test_lookahead_vs_oracle_all_templates(fname, mode, eng_mod, oracle_lib):
     """Every lowered Action in the fixtures (not only the un-memoised ones) against the CPU oracle."""
     g = Golden(fname)
-    res, tn, tt = _run_all_templates(eng_mod, g.templates, g.n_cluster_workers, repeat=3)
+    res, tn, tt = _run_all_templates(eng_mod, g.templates, g.n_cluster_workers, repeat=3, mode=mode)
     for k, t in enumerate(g.templates):
         o = oracle_lib.run_lookahead(t)
         for rep in range(3):
@@ -198,14 +208,15 @@ def test_fused_empty_steps_match_separate_steps(eng_mod):
     e1.close(); e2.close()
 
 
-def test_random_templates_vs_oracle(eng_mod, oracle_lib):
+@pytest.mark.parametrize('mode', MODES)
+def test_random_templates_vs_oracle(mode, eng_mod, oracle_lib):
     """Adversarial random lowered jobs: priority ties, zero-cost ops, zero-time flows, flows without a channel,
     mutual edges, deadlocks (status INFINITE_TICK must match too)."""
     from ddls_b200.template_builder import random_dag_template
     rng = np.random.default_rng(1234)
     templates = [random_dag_template(rng, int(n), n_workers=int(w)) for n, w in
                  zip(rng.integers(2, 400, size=60), rng.integers(1, 9, size=60))]
-    res, tn, tt = _run_all_templates(eng_mod, templates)
+    res, tn, tt = _run_all_templates(eng_mod, templates, mode=mode)
     n_err = 0
     for k, t in enumerate(templates):
         o = oracle_lib.run_lookahead(t)
@@ -220,14 +231,15 @@ def test_random_templates_vs_oracle(eng_mod, oracle_lib):
     assert n_err < len(templates)
 
 
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('degree', [2, 8, 16])
-def test_baseline_sized_template_vs_oracle(degree, eng_mod, oracle_lib):
+def test_baseline_sized_template_vs_oracle(degree, mode, eng_mod, oracle_lib):
     """BASELINE.json config 2/3 shape: ResNet-50-like job partitioned to `degree` on a 64-worker RAMP."""
     from ddls_b200 import synth
     from ddls_b200.template_builder import build_template, RampShape
     t = build_template(synth.resnet_like_graph(), degree, RampShape(4, 4, 4))
     o = oracle_lib.run_lookahead(t)
-    res, tn, tt = _run_all_templates(eng_mod, [t], repeat=8)
+    res, tn, tt = _run_all_templates(eng_mod, [t], repeat=8, mode=mode)
     for rep in range(8):
         assert res['status'][rep] == 0 and res['n_ticks'][rep] == o['n_ticks']
         assert res['jct'][rep] == o['jct'] and res['comm'][rep] == o['comm'] and res['comp'][rep] == o['comp']
@@ -255,4 +267,35 @@ def test_infinite_tick_raises_like_reference(eng_mod):
     eng.step(a)
     with pytest.raises(Exception, match='Last tick was infinite'):
         eng.check_status()
+    eng.close()
+
+
+@pytest.mark.parametrize('mode,cta_threads', [('warp', '0'), ('cta', '64'), ('cta', '128'), ('auto', '0')])
+def test_many_mixed_items_per_launch(mode, cta_threads, eng_mod, oracle_lib):
+    """Hundreds of lookaheads of four very different sizes in one launch, persistent CTAs/warps processing several items
+    each: every result equals the oracle's (this configuration once exposed a shared-memory race in the CTA kernel)."""
+    import os
+    from ddls_b200 import synth
+    from ddls_b200.template_builder import build_template, RampShape
+    g = synth.resnet_like_graph(n_blocks=4, name='res4')
+    ts = [build_template(g, d, RampShape(4, 4, 4)) for d in (2, 4, 8, 16)]
+    want = [oracle_lib.run_lookahead(t) for t in ts]
+    os.environ['RAMP_LOOKAHEAD_MODE'] = mode
+    if cta_threads != '0':
+        os.environ['RAMP_LOOKAHEAD_CTA_THREADS'] = cta_threads
+    try:
+        eng = eng_mod.RampEngine(n_episodes=1, n_cluster_workers=64, max_jobs=1, trace_cap=4096)
+    finally:
+        os.environ.pop('RAMP_LOOKAHEAD_MODE', None)
+        os.environ.pop('RAMP_LOOKAHEAD_CTA_THREADS', None)
+    tids = [eng.register_template(t) for t in ts]
+    rng = np.random.default_rng(7)
+    for n in (700, 2500, 6000):
+        pick = rng.integers(0, 4, size=n)
+        res, _ = eng.run_lookaheads(np.array(tids, dtype=np.int32)[pick])
+        assert (res['status'] == 0).all()
+        for d in range(4):
+            sel = pick == d
+            assert (res['jct'][sel] == want[d]['jct']).all() and (res['comm'][sel] == want[d]['comm']).all()
+            assert (res['comp'][sel] == want[d]['comp']).all() and (res['n_ticks'][sel] == want[d]['n_ticks']).all()
     eng.close()
