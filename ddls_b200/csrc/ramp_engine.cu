@@ -39,6 +39,7 @@ int set_error(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int MAX_EVENT_PAIRS = 64;
+constexpr int RAMP_SMEM_CARVEOUT = 100;   // percent of the unified L1/shared array given to shared memory
 
 // The lookahead kernel is instantiated for several CTA sizes; small CTAs (1-2 warps) keep more lookaheads
 // resident per SM and waste fewer lanes on the small per-tick frontiers, large CTAs finish one lookahead sooner.
@@ -79,6 +80,7 @@ struct ramp_engine {
     TemplateDev* d_templates = nullptr;
     uint64_t max_scratch = 0;
     int32_t max_w = 1, max_c = 1;
+    int32_t par_cap = 0;         // bytes of shared-memory parent counters per lookahead
     // memo + results
     uint32_t memo_cap = 0;
     unsigned long long* d_memo_keys = nullptr;
@@ -109,8 +111,14 @@ struct ramp_engine {
     int cta_grid = 0;            // resident CTAs of the 128-thread variant
     int cta64_grid = 0;          // resident CTAs of the 64-thread variant
     size_t cta_smem_bytes = 0;
+    int debug = 0;               // RAMP_DEBUG=1 prints the per-step launch decisions to stderr
     int mode = 0;                // 0 auto, 1 warp-per-lookahead, 2 CTA-per-lookahead (RAMP_LOOKAHEAD_MODE)
-    int32_t* h_n_work = nullptr; // pinned
+    int32_t* h_n_work = nullptr; // pinned [4]
+    int64_t big_threshold = 60000;   // N + E from which one CTA per lookahead beats one warp (RAMP_BIG_THRESHOLD); measured
+                                     // on B200: N+E=35k 3.4 vs 3.8 ms, N+E=137k 8.4 vs 4.5 ms (profiles/r1_latency_by_degree.txt)
+    WorkItem* d_items_big = nullptr;
+    cudaStream_t stream2 = nullptr;  // big lookaheads run concurrently with the small ones
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // standalone lookahead buffers
     ResultSlots sa_res{};
     int32_t sa_cap = 0;
@@ -157,12 +165,15 @@ int resolve_events(ramp_engine* e) {
 int ensure_scratch(ramp_engine* e) {
     const uint64_t trace_bytes = align_up((uint64_t)e->cfg.trace_cap * 12, 16);
     const uint64_t stride = align_up(std::max<uint64_t>(e->max_scratch, 16), 256) + align_up(trace_bytes, 256);
-    const size_t smem = lookahead_smem_per_warp(e->max_w, e->max_c) * (size_t)(e->nt / 32);
+    const size_t smem = lookahead_smem_per_warp(e->max_w, e->max_c, e->par_cap) * (size_t)(e->nt / 32);
     if (smem > 200 * 1024)
         return set_error(RAMP_ERR_CAPACITY, "a template needs %zu B of shared memory for its worker/channel key arrays (max 200 KiB)", smem);
     if (smem != e->smem_bytes || e->grid == 0) {
         LookaheadKernel kern = lookahead_kernel_for(e->nt);
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // all lookahead kernels ask for the same L1/shared split: kernels with different carve-outs cannot share an SM,
+        // which would serialise the CTA kernel and the warp kernel when they are launched side by side
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, RAMP_SMEM_CARVEOUT));
         int occ = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, e->nt, smem));
         if (occ < 1) occ = 1;
@@ -170,13 +181,14 @@ int ensure_scratch(ramp_engine* e) {
         e->grid = e->sm_count * occ;     // persistent CTAs: a whole number of waves (148 SMs x resident CTAs per SM)
         e->smem_bytes = smem;
     }
-    const size_t cta_smem = lookahead_cta_smem(e->max_w, e->max_c);
+    const size_t cta_smem = lookahead_cta_smem(e->max_w, e->max_c, e->par_cap);
     if (cta_smem > 200 * 1024)
         return set_error(RAMP_ERR_CAPACITY, "a template needs %zu B of shared memory (max 200 KiB)", cta_smem);
     if (cta_smem != e->cta_smem_bytes || e->cta_grid == 0) {
         for (int nt : {128, 64}) {
             LookaheadKernel kern = lookahead_cta_kernel_for(nt);
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, RAMP_SMEM_CARVEOUT));
             int occ = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, cta_smem));
             if (occ < 1) occ = 1;
@@ -184,7 +196,8 @@ int ensure_scratch(ramp_engine* e) {
         }
         e->cta_smem_bytes = cta_smem;
     }
-    const int n_slabs = std::max(e->grid * (e->nt / 32), std::max(e->cta_grid, e->cta64_grid));   // one slab per lookahead in flight
+    // one slab per lookahead in flight; the warp kernel and the 128-thread CTA kernel may run side by side
+    const int n_slabs = std::max(e->grid * (e->nt / 32) + e->cta_grid, e->cta64_grid);
     if (stride != e->scratch_stride || n_slabs != e->scratch_grid || e->d_scratch == nullptr) {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (e->d_scratch) cudaFree(e->d_scratch);
@@ -202,6 +215,8 @@ LookaheadArgs make_lookahead_args(ramp_engine* e, const WorkItem* items, Counter
     a.templates = e->d_templates;
     a.items = items;
     a.n_work = &counters->n_work;
+    a.items_b = nullptr;
+    a.n_work_b = nullptr;
     a.cursor = &counters->work_cursor;
     a.scratch = e->d_scratch;
     a.scratch_stride = e->scratch_stride;
@@ -211,6 +226,7 @@ LookaheadArgs make_lookahead_args(ramp_engine* e, const WorkItem* items, Counter
     a.trace_cap = e->cfg.trace_cap;
     a.w_cap = e->max_w;
     a.c_cap = e->max_c;
+    a.par_cap = e->par_cap;
     a.stats = stats;
     return a;
 }
@@ -288,6 +304,8 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
         e->cta_nt = nt;
     }
     if (const char* v = getenv("RAMP_LOOKAHEAD_MODE")) e->mode = !strcmp(v, "warp") ? 1 : !strcmp(v, "cta") ? 2 : 0;
+    if (const char* v = getenv("RAMP_BIG_THRESHOLD")) e->big_threshold = atoll(v);
+    if (const char* v = getenv("RAMP_DEBUG")) e->debug = atoi(v);
     cudaDeviceProp prop{};
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg.device));
     e->sm_count = prop.multiProcessorCount;
@@ -310,6 +328,10 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     CUDA_TRY(cudaMemset(e->pool.top, 0, sizeof(unsigned long long)));
 
     CUDA_TRY(cudaMalloc(&e->d_items, sizeof(WorkItem) * B));
+    CUDA_TRY(cudaMalloc(&e->d_items_big, sizeof(WorkItem) * B));
+    CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc(&e->d_counters, sizeof(Counters)));
     CUDA_TRY(cudaMemset(e->d_counters, 0, sizeof(Counters)));
     CUDA_TRY(cudaMalloc(&e->d_stats, sizeof(MemoStats)));
@@ -318,7 +340,7 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     CUDA_TRY(cudaMalloc(&e->d_step_stats, sizeof(double) * RAMP_STEP_STATS_LEN * B));
     CUDA_TRY(cudaMalloc(&e->d_n_cluster_steps, sizeof(int32_t) * B));
     CUDA_TRY(cudaMalloc(&e->d_ep_export, sizeof(double) * RAMP_EP_LEN * B));
-    CUDA_TRY(cudaMallocHost(&e->h_n_work, sizeof(int32_t)));
+    CUDA_TRY(cudaMallocHost(&e->h_n_work, sizeof(int32_t) * 4));
 
     EpisodeState& ep = e->ep;
     ep.B = B; ep.max_running = cfg.max_running; ep.max_jobs = cfg.max_jobs; ep.n_jobs = 0;
@@ -351,7 +373,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     cudaFree(e->d_templates); cudaFree(e->d_memo_keys);
     free_result_slots(e->res); free_result_slots(e->sa_res);
     cudaFree(e->pool.n_active); cudaFree(e->pool.tick); cudaFree(e->pool.top);
-    cudaFree(e->d_items); cudaFree(e->d_counters); cudaFree(e->d_stats); cudaFree(e->d_actions);
+    cudaFree(e->d_items); cudaFree(e->d_items_big); cudaStreamDestroy(e->stream2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaFree(e->d_counters); cudaFree(e->d_stats); cudaFree(e->d_actions);
     cudaFree(e->d_step_stats); cudaFree(e->d_n_cluster_steps); cudaFree(e->d_ep_export);
     cudaFree(e->ep.ef); cudaFree(e->ep.ei); cudaFree(e->ep.rf); cudaFree(e->ep.ri); cudaFree(e->ep.rec);
     cudaFree(e->d_arrivals); cudaFree(e->d_scratch); cudaFree(e->sa_items); cudaFree(e->sa_counters); cudaFreeHost(e->h_n_work);
@@ -441,7 +463,13 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     d.n_ops = N; d.n_deps = E; d.n_workers = W; d.n_channels = C;
     d.num_training_steps = j->num_training_steps; d.model_id = j->model_id; d.degree = j->degree;
     d.n_src = (int32_t)src.size(); d.canon_id = canon;
-    d.trace_need = (int32_t)std::min<int64_t>((int64_t)N + E + 1, e->cfg.trace_cap);
+    d.size_class = ((int64_t)N + (int64_t)E >= e->big_threshold) ? 1 : 0;
+    {
+        int32_t max_in = 0;
+        for (int32_t i = 0; i < N; ++i) max_in = std::max(max_in, in_deg[i]);
+        d.par_in_smem = (max_in <= 255 && N <= 8192) ? 1 : 0;       // byte counters in shared memory
+        d._pad0 = 0;
+    }
     d.op_rec = (const int4*)(base + segs[0].off); d.op_n_parents = (const uint16_t*)(base + segs[1].off);
     d.op_row = (const int2*)(base + segs[2].off); d.dep_km = (const unsigned long long*)(base + segs[3].off);
     d.dep_rt = (const double*)(base + segs[4].off); d.dep_dst = (const int32_t*)(base + segs[5].off);
@@ -453,6 +481,7 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     e->max_scratch = std::max(e->max_scratch, d.scratch_bytes);
     e->max_w = std::max(e->max_w, W);
     e->max_c = std::max(e->max_c, std::max(C, 1));
+    if (d.par_in_smem) e->par_cap = std::max(e->par_cap, (int32_t)align_up((uint64_t)N, 16));
     e->templates.push_back(std::move(ht));
     *id_out = id;
     return RAMP_OK;
@@ -505,26 +534,61 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
     if (!e->templates.empty()) { int rc = ensure_scratch(e); if (rc != RAMP_OK) return rc; }
     const int B = e->cfg.n_episodes;
     cudaStream_t st = e->stream;
-    CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int32_t), st));   // n_work, work_cursor
+    CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(int32_t), st));   // both work lists' counts and cursors
     PlanArgs p{};
     p.actions = d_actions; p.templates = e->d_templates; p.n_templates = (int32_t)e->templates.size();
     p.ep = e->ep; p.memo.keys = e->d_memo_keys; p.memo.mask = e->memo_cap - 1; p.memo.mode = e->cfg.memo_mode;
-    p.items = e->d_items; p.counters = e->d_counters; p.stats = e->d_stats;
+    p.items = e->d_items; p.items_big = e->d_items_big; p.counters = e->d_counters; p.stats = e->d_stats;
     ramp_plan_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
     e->launches++;
     if (!e->templates.empty()) {
         if (e->ev_pending >= MAX_EVENT_PAIRS) { CUDA_TRY(cudaStreamSynchronize(st)); int rc = resolve_events(e); if (rc) return rc; }
-        LookaheadArgs a = make_lookahead_args(e, e->d_items, e->d_counters, e->res, true, e->d_stats);
-        // the number of memo misses decides the kernel shape: a 4-byte read-back (~10 us) against a multi-ms kernel
-        CUDA_TRY(cudaMemcpyAsync(e->h_n_work, &e->d_counters->n_work, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        // the number of memo misses of each size class decides the kernel shapes: a 16-byte read-back (~10 us) against
+        // multi-ms kernels
+        CUDA_TRY(cudaMemcpyAsync(e->h_n_work, &e->d_counters->n_work, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        const int n_items = *e->h_n_work;
-        if (n_items > 0) {
+        const int n_small = e->h_n_work[0], n_big = e->h_n_work[2];
+        if (n_small + n_big > 0) {
+            LookaheadArgs a = make_lookahead_args(e, e->d_items, e->d_counters, e->res, true, e->d_stats);
+            LookaheadArgs ab = a;
+            ab.items = e->d_items_big; ab.n_work = &e->d_counters->n_work_big; ab.cursor = &e->d_counters->work_cursor_big;
             CUDA_TRY(cudaEventRecord(e->ev_a[e->ev_pending], st));
-            launch_lookahead(e, a, n_items, st);
+            const int wpb = e->nt / 32;
+            const int warp_slots = e->grid * wpb;
+            // Latency regime (fewer lookaheads than warp slots): the big ones get one 128-thread CTA each on a second stream
+            // and overlap the small ones (one warp each).  Throughput regime: everything through the warp kernel, the big
+            // list first (longest-processing-time-first keeps the tail short).
+            const bool split = e->mode != 1 && n_big > 0 && n_big <= e->cta_grid && (n_small + n_big) <= warp_slots;
+            if (e->debug) fprintf(stderr, "[ramp] step lookaheads: small=%d big=%d warp_slots=%d cta_grid=%d -> %s\n", n_small, n_big,
+                                  warp_slots, e->cta_grid, split ? "split (CTA128 || warp)" : "single warp kernel, big first");
+            if (split) {
+                const int grid = n_big;
+                CUDA_TRY(cudaEventRecord(e->ev_fork, st));
+                CUDA_TRY(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+                lookahead_cta_kernel_for(128)<<<grid, 128, e->cta_smem_bytes, e->stream2>>>(ab);
+                CUDA_TRY(cudaEventRecord(e->ev_join, e->stream2));
+                e->launches++;
+                if (n_small > 0) {
+                    LookaheadArgs as = a;
+                    as.scratch = a.scratch + (uint64_t)e->cta_grid * a.scratch_stride;     // slabs past the CTA kernel's
+                    const int g2 = std::max(1, std::min(e->grid, (n_small + wpb - 1) / wpb));
+                    lookahead_kernel_for(e->nt)<<<g2, e->nt, e->smem_bytes, st>>>(as);
+                    e->launches++;
+                }
+                CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
+            } else if (e->mode == 2) {
+                if (n_big > 0) { launch_lookahead(e, ab, n_big, st); e->launches++; }
+                if (n_small > 0) { launch_lookahead(e, a, n_small, st); e->launches++; }
+            } else {
+                LookaheadArgs all = ab;                      // list A = big, list B = small, one cursor
+                all.items_b = e->d_items; all.n_work_b = &e->d_counters->n_work;
+                const int n_all = n_small + n_big;
+                const int g = std::max(1, std::min(e->grid, (n_all + wpb - 1) / wpb));
+                lookahead_kernel_for(e->nt)<<<g, e->nt, e->smem_bytes, st>>>(all);
+                e->launches++;
+            }
             CUDA_TRY(cudaEventRecord(e->ev_b[e->ev_pending], st));
             e->ev_pending++;
-            e->launches++;
         }
     }
     StepArgs s{};

@@ -33,7 +33,9 @@ struct TemplateDev {
     int32_t n_ops, n_deps, n_workers, n_channels;
     int32_t num_training_steps, model_id, degree, n_src;
     int32_t canon_id;           // id of the first registered byte-identical template (exact memo key)
-    int32_t trace_need;         // min(N + E + 1, trace_cap): upper bound on ticks (>= 1 op or dep completes per tick)
+    int32_t size_class;         // 0: small (one warp per lookahead is fastest), 1: big (one CTA per lookahead is fastest)
+    int32_t par_in_smem;        // parent counters fit the shared-memory byte counters (max in-degree <= 255, N <= par_cap)
+    int32_t _pad0;
     const int4*     op_rec;       // [N] by op index: {cost.lo, cost.hi, key, worker}
     const int2*     op_row;       // [N] by op index: {first out-edge, out-degree} (CSR row)
     const uint16_t* op_n_parents; // [N] by op index (JOB:508-523)
@@ -69,9 +71,11 @@ struct TracePool {
     uint64_t len;
 };
 
-struct Counters {               // zeroed at the start of every step
-    int32_t n_work;
+struct Counters {               // the first four words are zeroed at the start of every step
+    int32_t n_work;             // work list 0: small lookaheads (or all of them for standalone runs)
     int32_t work_cursor;
+    int32_t n_work_big;         // work list 1: big lookaheads
+    int32_t work_cursor_big;
     int32_t err_episode;        // first episode that recorded an error (+1), 0 if none
     int32_t err_status;
 };
@@ -108,15 +112,18 @@ struct MemoTable {
 
 struct LookaheadArgs {
     const TemplateDev* templates;
-    const WorkItem* items;
-    const int32_t* n_work;      // device-side count
-    int32_t* cursor;            // device-side work cursor (persistent CTAs pull items)
+    const WorkItem* items;      // work list A, consumed first (the big lookaheads: longest-processing-time-first)
+    const int32_t* n_work;      // device-side count of list A
+    const WorkItem* items_b;    // work list B, consumed after A (may be null)
+    const int32_t* n_work_b;    // device-side count of list B (may be null)
+    int32_t* cursor;            // device-side work cursor over A then B (persistent warps / CTAs pull items)
     unsigned char* scratch;     // [gridDim.x][scratch_stride]
     uint64_t scratch_stride;
     ResultSlots res;
     TracePool pool;
     int32_t trace_cap;          // per-CTA temp trace capacity
     int32_t w_cap, c_cap;       // shared-memory key array capacities
+    int32_t par_cap;            // bytes of shared-memory parent counters per lookahead (0 = none)
     MemoStats* stats;
 };
 
@@ -197,13 +204,14 @@ __device__ __forceinline__ void warp_push(int32_t* list, int* counter, bool pred
     if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = val;
 }
 
+// min over the warp of NON-NEGATIVE doubles (remaining times; +inf = "none"): their u64 bit patterns order like the
+// values, so two 32-bit REDUX.MIN (high word, then low word among the lanes holding the minimal high word) replace a
+// ten-shuffle butterfly
 __device__ __forceinline__ double warp_min_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double other = __shfl_xor_sync(0xffffffffu, v, o);
-        v = (other < v) ? other : v;
-    }
-    return v;
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
 }
 
 __device__ __forceinline__ int warp_sum_i32(int v) {
@@ -236,7 +244,7 @@ __device__ __forceinline__ int warp_sum_i32(int v) {
 //   I,J lane 0 accumulates t / comm / comp and the trace in tick order                              (RCE:442-445, 777-791)
 #define RAMP_U 4            // batch depth: independent loads in flight per lane per phase
 #define RAMP_OPS_CAP 48     // op-frontier records kept in shared memory per buffer (overflow goes to HBM)
-#define RAMP_F_CAP 512      // dep-frontier records kept in shared memory (overflow goes to HBM)
+#define RAMP_F_CAP 384      // dep-frontier records kept in shared memory (overflow goes to HBM); sized so that 12 lookahead warps fit an SM
 
 struct OpsView { int4* a_sm; int2* b_sm; int4* a_ovf; int2* b_ovf; };
 __device__ __forceinline__ void ops_get(const OpsView& v, int k, int4& ra, int2& rb) {
@@ -259,7 +267,18 @@ __device__ __forceinline__ void f_get_km_rem(const FrontView& v, int k, unsigned
 }
 
 // bytes of shared memory one lookahead warp needs
-__host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap) {
+// parent counter of op `child` += 1, returns the new value (JOB:530).  Small jobs keep one BYTE per op in shared memory
+// (four per word, atomicAdd of 1 << 8*(child&3): a byte never carries because it never exceeds the in-degree <= 255)
+__device__ __forceinline__ uint32_t par_inc(bool in_smem, uint32_t* par_sm, uint32_t* par_gl, int child) {
+    if (in_smem) {
+        const uint32_t sh = ((uint32_t)child & 3u) * 8u;
+        const uint32_t old = atomicAdd(&par_sm[child >> 2], 1u << sh);
+        return ((old >> sh) & 0xFFu) + 1u;
+    }
+    return atomicAdd(&par_gl[child], 1u) + 1u;
+}
+
+__host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap, int par_cap) {
     size_t b = 0;
     b += (size_t)RAMP_F_CAP * 8 * 2;             // km, rem
     b += (size_t)c_cap * 8;                      // crem
@@ -267,6 +286,7 @@ __host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap) 
     b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
     b += (size_t)RAMP_F_CAP * 4;                 // dst
     b += (size_t)(w_cap + c_cap) * 4;            // wkey, ckey
+    b += (size_t)par_cap;                        // parent counters (bytes)
     return (b + 15) & ~(size_t)15;
 }
 
@@ -277,7 +297,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned char* my_smem = smem_raw + (size_t)warp * lookahead_smem_per_warp(a.w_cap, a.c_cap);
+    unsigned char* my_smem = smem_raw + (size_t)warp * lookahead_smem_per_warp(a.w_cap, a.c_cap, a.par_cap);
     // layout by decreasing alignment: int4 | 8-byte arrays | 4-byte arrays (c_cap may be odd)
     int4* ops_a_sm0 = reinterpret_cast<int4*>(my_smem);                                  // [2][RAMP_OPS_CAP]
     FrontView fr;
@@ -288,6 +308,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
     fr.dst_sm = reinterpret_cast<int32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);                // [RAMP_F_CAP]
     uint32_t* wkey = reinterpret_cast<uint32_t*>(fr.dst_sm + RAMP_F_CAP);                // [w_cap] best key among the ready ops on the worker
     uint32_t* ckey = wkey + a.w_cap;                                                     // [c_cap] best key among the ready flows on the channel
+    uint32_t* par_sm = ckey + a.c_cap;                                                   // [par_cap / 4] byte parent counters
 
     unsigned char* slab = a.scratch + (uint64_t)(blockIdx.x * WPB + warp) * a.scratch_stride;
     const uint64_t trace_region = a.scratch_stride - align_up((uint64_t)a.trace_cap * 12, 16);
@@ -297,8 +318,10 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
         int wi = 0;
         if (lane == 0) wi = atomicAdd(a.cursor, 1);
         wi = __shfl_sync(FULL, wi, 0);
-        if (wi >= *a.n_work) break;
-        const WorkItem item = a.items[wi];
+        const int n_a = *a.n_work;
+        const int n_b = a.n_work_b ? *a.n_work_b : 0;
+        if (wi >= n_a + n_b) break;
+        const WorkItem item = (wi < n_a) ? a.items[wi] : a.items_b[wi - n_a];
         const TemplateDev& T = a.templates[item.template_id];
         const int N = T.n_ops, E = T.n_deps, W = T.n_workers, C = T.n_channels;
         const ScratchView sv = carve(slab, N, E, trace_region, a.trace_cap);
@@ -311,9 +334,11 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
         const double* __restrict__ t_dep_rt = T.dep_rt;
         const int32_t* __restrict__ t_dep_dst = T.dep_dst;
         uint32_t* par_done = sv.par_done;
+        const bool psm = T.par_in_smem != 0;
 
         // ---- init (JOB:432-484) ----
-        for (int i = lane; i < N; i += 32) par_done[i] = 0u;
+        if (psm) { for (int i = lane; i < (N + 3) / 4; i += 32) par_sm[i] = 0u; }
+        else { for (int i = lane; i < N; i += 32) par_done[i] = 0u; }
         for (int i = lane; i < W; i += 32) wkey[i] = 0u;
         for (int i = lane; i < C; i += 32) ckey[i] = 0u;
         OpsView ops, ops_n;
@@ -425,7 +450,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                             rem[u] = r2;
                             if (r2 == 0.0) {                                                     // JOB:562, 525-536
                                 done[u] = true;
-                                cnt[u] = atomicAdd(&par_done[child[u]], 1u) + 1u;               // JOB:530
+                                cnt[u] = par_inc(psm, par_sm, par_done, child[u]);              // JOB:530
                                 np[u] = (uint32_t)__ldg(&t_n_parents[child[u]]);
                                 reca[u] = __ldg(&t_op_rec[child[u]]);
                                 recb[u] = __ldg(&t_op_row[child[u]]);
@@ -435,6 +460,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                 }
 #pragma unroll
                 for (int u = 0; u < RAMP_U; ++u) {
+                    if (kb + u * 32 >= nF) break;                  // (warp-uniform) nothing in this sub-batch
                     bool readied = false;
                     const bool keep = (km[u] != 0ull) && !done[u];
                     if (km[u] != 0ull && (km[u] >> 48) != 0ull) {
@@ -629,7 +655,8 @@ struct PlanArgs {
     int32_t n_templates;
     EpisodeState ep;
     MemoTable memo;
-    WorkItem* items;                // [B]
+    WorkItem* items;                // [B] small lookaheads
+    WorkItem* items_big;            // [B] big lookaheads
     Counters* counters;
     MemoStats* stats;
 };
@@ -677,9 +704,9 @@ __global__ void ramp_plan_kernel(const PlanArgs p) {
     ei[EI_PLAN_SLOT * B + b] = slot;
     ei[EI_PLAN_RAN * B + b] = ran ? 1 : 0;
     if (ran) {
-        const int w = atomicAdd(&p.counters->n_work, 1);
         WorkItem it; it.template_id = act.template_id; it.slot = slot; it.episode = b; it._pad = 0;
-        p.items[w] = it;
+        if (T.size_class) p.items_big[atomicAdd(&p.counters->n_work_big, 1)] = it;
+        else p.items[atomicAdd(&p.counters->n_work, 1)] = it;
     }
 }
 

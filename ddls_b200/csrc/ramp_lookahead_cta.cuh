@@ -27,7 +27,7 @@ struct CtaCells {              // written during tick with parity p, read after 
     unsigned long long min_op, min_dep;
 };
 
-__host__ __device__ inline size_t lookahead_cta_smem(int w_cap, int c_cap) {
+__host__ __device__ inline size_t lookahead_cta_smem(int w_cap, int c_cap, int par_cap) {
     size_t b = 0;
     b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
     b += (size_t)2 * RAMP_CTA_F_CAP * 8 * 2;     // km, rem (two buffers)
@@ -36,6 +36,7 @@ __host__ __device__ inline size_t lookahead_cta_smem(int w_cap, int c_cap) {
     b += (size_t)w_cap * 8;                      // done queue: {row start, degree}
     b += (size_t)2 * RAMP_CTA_F_CAP * 4;         // dst (two buffers)
     b += (size_t)(w_cap + c_cap) * 4;            // wkey, ckey
+    b += (size_t)par_cap;                        // parent counters (bytes)
     return (b + 15) & ~(size_t)15;
 }
 
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
     int32_t* dst_sm0 = reinterpret_cast<int32_t*>(doneq + a.w_cap);                       // [2][F_CAP]
     uint32_t* wkey = reinterpret_cast<uint32_t*>(dst_sm0 + 2 * RAMP_CTA_F_CAP);           // [w_cap]
     uint32_t* ckey = wkey + a.w_cap;                                                      // [c_cap]
+    uint32_t* par_sm = ckey + a.c_cap;                                                    // [par_cap / 4] byte parent counters
 
     __shared__ CtaCells cells[2];
     __shared__ int s_n_ops[2];
@@ -85,8 +87,10 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         if (tid == 0) s_work = atomicAdd(a.cursor, 1);
         __syncthreads();
         const int wi = s_work;
-        if (wi >= *a.n_work) break;
-        const WorkItem item = a.items[wi];
+        const int n_a = *a.n_work;
+        const int n_b = a.n_work_b ? *a.n_work_b : 0;
+        if (wi >= n_a + n_b) break;
+        const WorkItem item = (wi < n_a) ? a.items[wi] : a.items_b[wi - n_a];
         const TemplateDev& T = a.templates[item.template_id];
         const int N = T.n_ops, E = T.n_deps, W = T.n_workers, C = T.n_channels;
         const ScratchView sv = carve(slab, N, E, trace_region, a.trace_cap);
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         const double* __restrict__ t_dep_rt = T.dep_rt;
         const int32_t* __restrict__ t_dep_dst = T.dep_dst;
         uint32_t* par_done = sv.par_done;
+        const bool psm = T.par_in_smem != 0;
 
         FrontBuf F, Falt;
         F.km_sm = km_sm0; F.rem_sm = rem_sm0; F.dst_sm = dst_sm0;
@@ -109,7 +114,8 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         ops_n.a_sm = ops_a_sm0 + RAMP_OPS_CAP; ops_n.b_sm = ops_b_sm0 + RAMP_OPS_CAP; ops_n.a_ovf = sv.ops_a_ovf[1]; ops_n.b_ovf = sv.ops_b_ovf[1];
 
         // ---- init (JOB:432-484) ----
-        for (int i = tid; i < N; i += NT) par_done[i] = 0u;
+        if (psm) { for (int i = tid; i < (N + 3) / 4; i += NT) par_sm[i] = 0u; }
+        else { for (int i = tid; i < N; i += NT) par_done[i] = 0u; }
         for (int i = tid; i < W; i += NT) wkey[i] = 0u;
         for (int i = tid; i < C; i += NT) ckey[i] = 0u;
         for (int k = tid; k < T.n_src; k += NT) {
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                                 if (winner) rescan = true;           // the channel's winner completed: recompute the slots
                                 if (!is_flow) ++nf_done;
                                 ++ddone;
-                                cnt[u] = atomicAdd(&par_done[child[u]], 1u) + 1u;                   // JOB:530
+                                cnt[u] = par_inc(psm, par_sm, par_done, child[u]);                  // JOB:530
                                 np[u] = (uint32_t)__ldg(&t_n_parents[child[u]]);
                                 reca[u] = __ldg(&t_op_rec[child[u]]);
                                 recb[u] = __ldg(&t_op_row[child[u]]);
@@ -251,6 +257,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                     }
 #pragma unroll
                     for (int u = 0; u < RAMP_U; ++u) {
+                        if (kb + u * 32 >= nF) break;              // (warp-uniform) nothing in this sub-batch
                         const bool readied = done[u] && (cnt[u] == np[u]);                           // JOB:531 (fires once)
                         const unsigned m = __ballot_sync(FULL, readied);
                         if (m) {
