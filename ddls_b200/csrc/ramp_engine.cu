@@ -142,11 +142,14 @@ int alloc_result_slots(ResultSlots& r, int32_t n) {
     CUDA_TRY(cudaMalloc(&r.n_ticks, sizeof(int32_t) * n));
     CUDA_TRY(cudaMalloc(&r.status, sizeof(int32_t) * n));
     CUDA_TRY(cudaMalloc(&r.trace_off, sizeof(int64_t) * n));
+    CUDA_TRY(cudaMalloc(&r.util, sizeof(double) * n));
+    CUDA_TRY(cudaMalloc(&r.util_nmw, sizeof(int32_t) * n));
     return RAMP_OK;
 }
 
 void free_result_slots(ResultSlots& r) {
     cudaFree(r.jct); cudaFree(r.comm); cudaFree(r.comp); cudaFree(r.n_ticks); cudaFree(r.status); cudaFree(r.trace_off);
+    cudaFree(r.util); cudaFree(r.util_nmw);
     r = ResultSlots{};
 }
 
@@ -728,7 +731,7 @@ int ramp_run_lookaheads(ramp_engine_t* e, const int32_t* template_ids, int32_t n
     }
     if (!e->sa_counters) CUDA_TRY(cudaMalloc(&e->sa_counters, sizeof(Counters)));
     std::vector<WorkItem> items(n);
-    for (int32_t k = 0; k < n; ++k) { items[k].template_id = template_ids[k]; items[k].slot = k; items[k].episode = -1; items[k]._pad = 0; }
+    for (int32_t k = 0; k < n; ++k) { items[k].template_id = template_ids[k]; items[k].slot = k; items[k].episode = -1; items[k].n_mounted_workers = 0; }
     Counters c{}; c.n_work = n;
     CUDA_TRY(cudaMemcpyAsync(e->sa_items, items.data(), sizeof(WorkItem) * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(e->sa_counters, &c, sizeof(Counters), cudaMemcpyHostToDevice, st));

@@ -51,7 +51,7 @@ struct WorkItem {
     int32_t template_id;
     int32_t slot;               // result slot
     int32_t episode;            // -1 for standalone runs
-    int32_t _pad;
+    int32_t n_mounted_workers;  // len(job.details['mounted_workers']) of the mounting job (RCE:832); 0 = the template's
 };
 
 // lookahead result slots (SoA); slot == memo hash-table position (+ B extra slots for RAMP_MEMO_OFF)
@@ -62,6 +62,8 @@ struct ResultSlots {
     int32_t*  n_ticks;
     int32_t*  status;
     int64_t*  trace_off;        // offset into the trace pool, -1 if none
+    double*   util;             // mean_mounted_worker_utilisation_frac (RCE:830-832) for util_nmw mounted workers
+    int32_t*  util_nmw;
 };
 
 struct TracePool {
@@ -219,6 +221,20 @@ __device__ __forceinline__ int warp_sum_i32(int v) {
 }
 
 #define RAMP_INF_BITS 0x7FF0000000000000ull
+
+// RCE:830-832: util = sum over ticks, in tick order, of (n_active / n_mounted_workers) * (tick / jct).  The divisions
+// and the product of every term are independent, so `n_threads` threads compute them (into term[]), then ONE thread
+// adds them serially in tick order -- the same f64 additions in the same order as the reference.
+__device__ __forceinline__ void util_terms(const int32_t* tr_n, const double* tr_tick, double* term, int n_rec, double nmw,
+                                            double jct, int tid, int n_threads) {
+    for (int k = tid; k < n_rec; k += n_threads)
+        term[k] = __dmul_rn(__ddiv_rn((double)tr_n[k], nmw), __ddiv_rn(tr_tick[k], jct));
+}
+__device__ __forceinline__ double util_sum(const double* term, int n_rec) {
+    double u = 0.0;
+    for (int k = 0; k < n_rec; ++k) u = __dadd_rn(u, term[k]);
+    return u;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // _run_lookahead (RCE:379-467): ONE WARP per lookahead; WPB independent warps per CTA; persistent warps pull
@@ -612,12 +628,22 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
         // ---- results (RCE:450-452): copy the trace to an exactly-sized pool allocation ----
         const int n_rec = tick_no < a.trace_cap ? tick_no : a.trace_cap;
         long long off = -1;
+        __syncwarp();
+        const double steps = (double)T.num_training_steps;
+        const double jct = __dmul_rn(__shfl_sync(FULL, t, 0), steps);
+        const int nmw = item.n_mounted_workers > 0 ? item.n_mounted_workers : W;
+        // utilisation terms go to the (now free) head of the dep-frontier overflow area
+        double* term = sv.f_rem_ovf2;
+        const bool can_util = (status == RAMP_ST_OK) && (tick_no <= a.trace_cap) && (n_rec <= E);
+        if (can_util) util_terms(sv.tr_n, sv.tr_tick, term, n_rec, (double)nmw, jct, lane, 32);
+        __syncwarp();
         if (lane == 0) {
-            const double steps = (double)T.num_training_steps;
-            a.res.jct[item.slot] = __dmul_rn(t, steps);
+            a.res.jct[item.slot] = jct;
             a.res.comm[item.slot] = __dmul_rn(comm, steps);
             a.res.comp[item.slot] = __dmul_rn(comp, steps);
             a.res.n_ticks[item.slot] = tick_no;
+            a.res.util[item.slot] = can_util ? util_sum(term, n_rec) : 0.0;
+            a.res.util_nmw[item.slot] = can_util ? nmw : -1;
             if (a.pool.top != nullptr) {
                 const unsigned long long o = atomicAdd(a.pool.top, (unsigned long long)n_rec);
                 if (o + (unsigned long long)n_rec <= a.pool.len) off = (long long)o;
@@ -704,7 +730,7 @@ __global__ void ramp_plan_kernel(const PlanArgs p) {
     ei[EI_PLAN_SLOT * B + b] = slot;
     ei[EI_PLAN_RAN * B + b] = ran ? 1 : 0;
     if (ran) {
-        WorkItem it; it.template_id = act.template_id; it.slot = slot; it.episode = b; it._pad = 0;
+        WorkItem it; it.template_id = act.template_id; it.slot = slot; it.episode = b; it.n_mounted_workers = act.n_mounted_workers;
         if (T.size_class) p.items_big[atomicAdd(&p.counters->n_work_big, 1)] = it;
         else p.items[atomicAdd(&p.counters->n_work, 1)] = it;
     }
@@ -829,15 +855,20 @@ __global__ void ramp_step_kernel(const StepArgs s) {
                         EI(EI_STATUS) = RAMP_ST_TABLE_FULL; atomicCAS(&s.counters->err_episode, 0, b + 1);
                         step_register_blocked(ep, b, handled, st);
                     } else {
-                        // RCE:830-832 serial sum in tick order
+                        // RCE:830-832: computed by the lookahead kernel for its own mounted-worker count; a memo hit from a job
+                        // mounted on a different number of workers recomputes it here (serial sum in tick order)
                         double util = 0.0;
-                        const long long off = s.res.trace_off[slot];
-                        const int T = s.res.n_ticks[slot];
-                        const double nmw = (double)act.n_mounted_workers;
-                        if (off >= 0) {
-                            for (int k = 0; k < T; ++k)
-                                util = __dadd_rn(util, __dmul_rn(__ddiv_rn((double)s.pool.n_active[off + k], nmw),
-                                                                 __ddiv_rn(s.pool.tick[off + k], jct)));
+                        if (s.res.util_nmw[slot] == act.n_mounted_workers) {
+                            util = s.res.util[slot];
+                        } else {
+                            const long long off = s.res.trace_off[slot];
+                            const int T = s.res.n_ticks[slot];
+                            const double nmw = (double)act.n_mounted_workers;
+                            if (off >= 0) {
+                                for (int k = 0; k < T; ++k)
+                                    util = __dadd_rn(util, __dmul_rn(__ddiv_rn((double)s.pool.n_active[off + k], nmw),
+                                                                     __ddiv_rn(s.pool.tick[off + k], jct)));
+                            }
                         }
                         const int row = EI(EI_N_RUNNING)++;
                         const ramp_arrival_t arr = ep.arr[(size_t)b * ep.max_jobs + handled];

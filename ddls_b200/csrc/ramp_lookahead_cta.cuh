@@ -454,12 +454,25 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
 
         // ---- results (RCE:450-452) ----
         const int n_rec = tick_no < a.trace_cap ? tick_no : a.trace_cap;
+        __shared__ double s_jct;
+        __shared__ int s_can_util;
+        const double steps = (double)T.num_training_steps;
+        const int nmw = item.n_mounted_workers > 0 ? item.n_mounted_workers : W;
+        double* term = sv.f_rem_ovf2;                 // the (now free) head of the dep-frontier overflow area
         if (tid == 0) {
-            const double steps = (double)T.num_training_steps;
-            a.res.jct[item.slot] = __dmul_rn(t, steps);
+            s_jct = __dmul_rn(t, steps);
+            s_can_util = (status == RAMP_ST_OK) && (tick_no <= a.trace_cap) && (n_rec <= E);
+        }
+        __syncthreads();
+        if (s_can_util) util_terms(sv.tr_n, sv.tr_tick, term, n_rec, (double)nmw, s_jct, tid, NT);
+        __syncthreads();
+        if (tid == 0) {
+            a.res.jct[item.slot] = s_jct;
             a.res.comm[item.slot] = __dmul_rn(comm, steps);
             a.res.comp[item.slot] = __dmul_rn(comp, steps);
             a.res.n_ticks[item.slot] = tick_no;
+            a.res.util[item.slot] = s_can_util ? util_sum(term, n_rec) : 0.0;
+            a.res.util_nmw[item.slot] = s_can_util ? nmw : -1;
             long long off = -1;
             if (a.pool.top != nullptr) {
                 const unsigned long long o = atomicAdd(a.pool.top, (unsigned long long)n_rec);
