@@ -435,9 +435,13 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
         op_row[(size_t)i * 2 + 1] = j->row_ptr[i + 1] - j->row_ptr[i];
     }
     std::vector<unsigned long long> dep_km(E);
+    int32_t max_in_deg = 0;
+    for (int32_t i = 0; i < N; ++i) max_in_deg = std::max(max_in_deg, in_deg[i]);
+    const bool par_in_smem = (max_in_deg <= 255 && N <= 8192);       // byte parent counters in shared memory
     for (int32_t k = 0; k < E; ++k)
         dep_km[k] = (unsigned long long)dep_key[k] | ((unsigned long long)j->dep_channel[k] << 32)
-                    | ((unsigned long long)(j->dep_is_flow[k] ? 1 : 0) << 48);
+                    | ((unsigned long long)(j->dep_is_flow[k] ? 1 : 0) << 48)
+                    | (par_in_smem ? ((unsigned long long)j->op_n_parents[j->dep_dst[k]] << 49) : 0ull);
 
     // ---- pack one blob ----
     struct Seg { const void* p; size_t bytes; size_t off; };
@@ -467,12 +471,8 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     d.num_training_steps = j->num_training_steps; d.model_id = j->model_id; d.degree = j->degree;
     d.n_src = (int32_t)src.size(); d.canon_id = canon;
     d.size_class = ((int64_t)N + (int64_t)E >= e->big_threshold) ? 1 : 0;
-    {
-        int32_t max_in = 0;
-        for (int32_t i = 0; i < N; ++i) max_in = std::max(max_in, in_deg[i]);
-        d.par_in_smem = (max_in <= 255 && N <= 8192) ? 1 : 0;       // byte counters in shared memory
-        d._pad0 = 0;
-    }
+    d.par_in_smem = par_in_smem ? 1 : 0;
+    d._pad0 = 0;
     d.op_rec = (const int4*)(base + segs[0].off); d.op_n_parents = (const uint16_t*)(base + segs[1].off);
     d.op_row = (const int2*)(base + segs[2].off); d.dep_km = (const unsigned long long*)(base + segs[3].off);
     d.dep_rt = (const double*)(base + segs[4].off); d.dep_dst = (const int32_t*)(base + segs[5].off);

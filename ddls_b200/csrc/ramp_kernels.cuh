@@ -39,7 +39,8 @@ struct TemplateDev {
     const int4*     op_rec;       // [N] by op index: {cost.lo, cost.hi, key, worker}
     const int2*     op_row;       // [N] by op index: {first out-edge, out-degree} (CSR row)
     const uint16_t* op_n_parents; // [N] by op index (JOB:508-523)
-    const unsigned long long* dep_km;  // [E] by dep index (CSR order): key | channel << 32 | is_flow << 48
+    const unsigned long long* dep_km;  // [E] by dep index (CSR order): key | channel << 32 | is_flow << 48 | n_parents(child) << 49
+                                       //     (the n_parents byte only when par_in_smem, i.e. every in-degree <= 255)
     const double*   dep_rt;       // [E] by dep index: init_run_time (RCE:542-560)
     const int32_t*  dep_dst;      // [E] by dep index: child op index
     const int32_t*  src_ops;      // [n_src] ops with in-degree 0: the initial ops_ready (JOB:474-481)
@@ -435,67 +436,55 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             }
             ++tick_no;
 
-            // ---- H: the deps of the pre-tick snapshot [0, nF); survivors slide down to [0, p) ----
+            // ---- H: the deps of the pre-tick snapshot [0, nF); survivors slide down to [0, p).  32 entries per iteration; the
+            //      common case (nobody in the group completes) only rewrites the remaining times ----
             int nO_next = 0;
             int p = 0;
             int ddone = 0, nf_done = 0;
             bool rescan = false;
-            for (int kb = 0; kb < nF; kb += 32 * RAMP_U) {
-                unsigned long long km[RAMP_U];
-                int child[RAMP_U];
-                double rem[RAMP_U];
-#pragma unroll
-                for (int u = 0; u < RAMP_U; ++u) {
-                    const int k = kb + u * 32 + lane;
-                    km[u] = 0ull; child[u] = 0; rem[u] = 1.0;
-                    if (k < nF) f_get(fr, k, km[u], rem[u], child[u]);
-                }
-                __syncwarp();          // every lane has read this batch before any survivor is written over it
-                uint32_t cnt[RAMP_U];
-                uint32_t np[RAMP_U];
-                int4 reca[RAMP_U];
-                int2 recb[RAMP_U];
-                bool done[RAMP_U];
-#pragma unroll
-                for (int u = 0; u < RAMP_U; ++u) {
-                    done[u] = false; cnt[u] = 0u; np[u] = 1u; reca[u] = make_int4(0, 0, 0, 0); recb[u] = make_int2(0, 0);
-                    if (km[u] != 0ull) {
-                        const bool is_flow = (km[u] >> 48) != 0ull;
-                        if (!(any_nf && is_flow)) {                                              // RCE:434-439
-                            const double r2 = tick_down(rem[u], tick);                           // JOB:561
-                            rem[u] = r2;
-                            if (r2 == 0.0) {                                                     // JOB:562, 525-536
-                                done[u] = true;
-                                cnt[u] = par_inc(psm, par_sm, par_done, child[u]);              // JOB:530
-                                np[u] = (uint32_t)__ldg(&t_n_parents[child[u]]);
-                                reca[u] = __ldg(&t_op_rec[child[u]]);
-                                recb[u] = __ldg(&t_op_row[child[u]]);
-                            }
-                        }
+            for (int kb = 0; kb < nF; kb += 32) {
+                const int k = kb + lane;
+                const bool valid = k < nF;
+                unsigned long long km = 0ull;
+                double rem = 1.0;
+                int child = 0;
+                if (valid) f_get(fr, k, km, rem, child);
+                const bool is_flow = ((km >> 48) & 1ull) != 0ull;
+                const bool ticked = valid && !(any_nf && is_flow);                               // RCE:434-439
+                const double r2 = ticked ? tick_down(rem, tick) : rem;                          // JOB:561
+                const bool done = ticked && (r2 == 0.0);                                        // JOB:562
+                const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
+                const bool winner = valid && is_flow && c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km;
+                const unsigned dmask = __ballot_sync(FULL, done);
+                if (dmask == 0u) {
+                    if (winner && ticked) crem[c] = r2;            // keep the winner's remaining time current
+                    if (p == kb) {                                 // nothing before it died either: update in place
+                        if (ticked) { if (k < RAMP_F_CAP) fr.rem_sm[k] = r2; else fr.rem_ovf[k - RAMP_F_CAP] = r2; }
+                    } else {
+                        __syncwarp();                              // all lanes have read before anything is written over
+                        if (valid) f_put(fr, p + lane, km, r2, child);
                     }
-                }
-#pragma unroll
-                for (int u = 0; u < RAMP_U; ++u) {
-                    if (kb + u * 32 >= nF) break;                  // (warp-uniform) nothing in this sub-batch
-                    bool readied = false;
-                    const bool keep = (km[u] != 0ull) && !done[u];
-                    if (km[u] != 0ull && (km[u] >> 48) != 0ull) {
-                        const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
-                        if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km[u]) {
-                            if (done[u]) rescan = true;            // the channel's winner completed: recompute the slots
-                            else crem[c] = rem[u];                 // keep the winner's remaining time current
-                        }
-                    }
-                    if (done[u]) {
+                    p += (nF - kb < 32) ? (nF - kb) : 32;          // warp-uniform: every valid entry of the group survives
+                } else {
+                    // JOB:525-536 for the completing lanes
+                    uint32_t cnt = 0u, np = 1u;
+                    if (done) {
+                        cnt = par_inc(psm, par_sm, par_done, child);                            // JOB:530
+                        np = psm ? (uint32_t)(km >> 49) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
                         ++ddone;
-                        if ((km[u] >> 48) == 0ull) ++nf_done;
-                        readied = (cnt[u] == np[u]);                                             // JOB:531 (fires once)
+                        if (!is_flow) ++nf_done;
+                        if (winner) rescan = true;                 // the channel's winner completed: recompute the slots
+                    } else if (winner && ticked) {
+                        crem[c] = r2;
                     }
+                    const bool keep = valid && !done;
                     const unsigned mk = __ballot_sync(FULL, keep);
-                    if (keep) f_put(fr, p + __popc(mk & lt_mask), km[u], rem[u], child[u]);
+                    __syncwarp();
+                    if (keep) f_put(fr, p + __popc(mk & lt_mask), km, r2, child);
                     p += __popc(mk);
+                    const bool readied = done && (cnt == np);                                    // JOB:531 (fires once)
                     const unsigned m = __ballot_sync(FULL, readied);
-                    if (readied) ops_put(ops_n, nO_next + __popc(m & lt_mask), reca[u], recb[u]);
+                    if (readied) ops_put(ops_n, nO_next + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
                     nO_next += __popc(m);
                 }
             }
@@ -573,7 +562,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                                 const int jf = jb + u * 32 + lane;
                                 if (jf < total) {
                                     f_put(fr, tail + jf, km[u], rt[u], dst[u]);
-                                    if ((km[u] >> 48) == 0ull) ++arr_nonflow;
+                                    if (((km[u] >> 48) & 1ull) == 0ull) ++arr_nonflow;
                                     else if (!rescan) {
                                         const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
                                         if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km[u]);
@@ -598,7 +587,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                 for (int k = lane; k < tail; k += 32) {
                     unsigned long long w; double r;
                     f_get_km_rem(fr, k, w, r);
-                    if ((w >> 48) != 0ull) {
+                    if (((w >> 48) & 1ull) != 0ull) {
                         const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
                         if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)w);
                     }
@@ -609,7 +598,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             for (int k = (rescan ? 0 : p) + lane; k < tail; k += 32) {
                 unsigned long long w; double r;
                 f_get_km_rem(fr, k, w, r);
-                if ((w >> 48) != 0ull) {
+                if (((w >> 48) & 1ull) != 0ull) {
                     const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
                     if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)w) crem[c] = r;
                 }

@@ -206,66 +206,45 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             }
             ++tick_no;
 
-            // ---- H: deps of the pre-tick snapshot [0, nF), batches dealt round-robin to the warps (last warps first) ----
+            // ---- H: deps of the pre-tick snapshot [0, nF): groups of 32 entries dealt round-robin to the warps (last warps
+            //      first; warp 0 also runs G).  In place: completed entries are marked dead, the rest only get a new rem ----
             {
                 int ddone = 0, nf_done = 0;
                 bool rescan = false;
-                const int n_batches = (nF + 32 * RAMP_U - 1) / (32 * RAMP_U);
-                for (int bi = NW - 1 - warp; bi < n_batches; bi += NW) {
-                    const int kb = bi * 32 * RAMP_U;
-                    unsigned long long km[RAMP_U];
-                    double rem[RAMP_U];
-                    int child[RAMP_U];
-#pragma unroll
-                    for (int u = 0; u < RAMP_U; ++u) {
-                        const int k = kb + u * 32 + lane;
-                        km[u] = 0ull; rem[u] = 1.0; child[u] = 0;
-                        if (k < nF) {
-                            km[u] = fb_km(F, k);
-                            if (km[u] != 0ull && any_nf && (km[u] >> 48) != 0ull) km[u] = 0ull;    // flows are frozen (RCE:434-439)
-                            if (km[u] != 0ull) { rem[u] = fb_rem(F, k); child[u] = fb_dst(F, k); }
+                const int n_groups = (nF + 31) / 32;
+                for (int gi = NW - 1 - warp; gi < n_groups; gi += NW) {
+                    const int k = gi * 32 + lane;
+                    unsigned long long km = 0ull;
+                    if (k < nF) km = fb_km(F, k);
+                    const bool is_flow = ((km >> 48) & 1ull) != 0ull;
+                    const bool ticked = (km != 0ull) && !(any_nf && is_flow);                        // RCE:434-439
+                    double r2 = 1.0;
+                    if (ticked) r2 = tick_down(fb_rem(F, k), tick);                                  // JOB:561
+                    const bool done = ticked && (r2 == 0.0);                                         // JOB:562
+                    const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
+                    const bool winner = ticked && is_flow && c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km;
+                    if (ticked && !done) { fb_set_rem(F, k, r2); if (winner) crem[c] = r2; }
+                    const unsigned dmask = __ballot_sync(FULL, done);
+                    if (dmask != 0u) {                                                               // JOB:525-536
+                        uint32_t cnt = 0u, np = 1u;
+                        int child = 0;
+                        if (done) {
+                            child = fb_dst(F, k);
+                            fb_set_km(F, k, 0ull);
+                            cnt = par_inc(psm, par_sm, par_done, child);                             // JOB:530
+                            np = psm ? (uint32_t)(km >> 49) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
+                            ++ddone;
+                            if (!is_flow) ++nf_done;
+                            if (winner) rescan = true;           // the channel's winner completed: recompute the slots
                         }
-                    }
-                    uint32_t cnt[RAMP_U], np[RAMP_U];
-                    int4 reca[RAMP_U];
-                    int2 recb[RAMP_U];
-                    bool done[RAMP_U];
-#pragma unroll
-                    for (int u = 0; u < RAMP_U; ++u) {
-                        done[u] = false; cnt[u] = 0u; np[u] = 1u; reca[u] = make_int4(0, 0, 0, 0); recb[u] = make_int2(0, 0);
-                        if (km[u] != 0ull) {
-                            const int k = kb + u * 32 + lane;
-                            const double r2 = tick_down(rem[u], tick);                               // JOB:561
-                            const bool is_flow = (km[u] >> 48) != 0ull;
-                            const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
-                            const bool winner = is_flow && c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km[u];
-                            if (r2 == 0.0) {                                                         // JOB:562, 525-536
-                                done[u] = true;
-                                fb_set_km(F, k, 0ull);
-                                if (winner) rescan = true;           // the channel's winner completed: recompute the slots
-                                if (!is_flow) ++nf_done;
-                                ++ddone;
-                                cnt[u] = par_inc(psm, par_sm, par_done, child[u]);                  // JOB:530
-                                np[u] = (uint32_t)__ldg(&t_n_parents[child[u]]);
-                                reca[u] = __ldg(&t_op_rec[child[u]]);
-                                recb[u] = __ldg(&t_op_row[child[u]]);
-                            } else {
-                                fb_set_rem(F, k, r2);
-                                if (winner) crem[c] = r2;            // keep the winner's remaining time current
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < RAMP_U; ++u) {
-                        if (kb + u * 32 >= nF) break;              // (warp-uniform) nothing in this sub-batch
-                        const bool readied = done[u] && (cnt[u] == np[u]);                           // JOB:531 (fires once)
+                        const bool readied = done && (cnt == np);                                     // JOB:531 (fires once)
                         const unsigned m = __ballot_sync(FULL, readied);
                         if (m) {
                             const int leader = __ffs(m) - 1;
                             int base = 0;
                             if (lane == leader) base = atomicAdd(&cc.n_ops_next, __popc(m));
                             base = __shfl_sync(FULL, base, leader);
-                            if (readied) ops_put(ops_n, base + __popc(m & lt_mask), reca[u], recb[u]);
+                            if (readied) ops_put(ops_n, base + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
                         }
                     }
                 }
@@ -371,7 +350,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                             const int jf = jb + u * 32 + lane;
                             if (jf < total) {
                                 fb_put(F, base + jf, km[u], rt[u], dst[u]);
-                                if ((km[u] >> 48) == 0ull) ++arr_nf;
+                                if (((km[u] >> 48) & 1ull) == 0ull) ++arr_nf;
                                 else {
                                     const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
                                     if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km[u]);
@@ -405,7 +384,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                 __syncthreads();
                 for (int k = tid; k < nF2; k += NT) {
                     const unsigned long long w = fb_km(F, k);
-                    if (w != 0ull && (w >> 48) != 0ull) {
+                    if (w != 0ull && ((w >> 48) & 1ull) != 0ull) {
                         const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
                         if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)w);
                     }
@@ -414,7 +393,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             }
             for (int k = (rescan ? 0 : nF) + tid; k < nF2; k += NT) {
                 const unsigned long long w = fb_km(F, k);
-                if (w != 0ull && (w >> 48) != 0ull) {
+                if (w != 0ull && ((w >> 48) & 1ull) != 0ull) {
                     const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
                     if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)w) crem[c] = fb_rem(F, k);
                 }
