@@ -250,9 +250,18 @@ def run_b200_arm(args, rank, world, local_rank):
             torch.cuda.current_stream().wait_event(ev)
             dist.all_gather_into_tensor(gathered, ep_dev)
 
+    memo_acc = {'lookups': 0, 'hits': 0, 'lookaheads': 0}
+
+    def fold_memo():
+        m = eng.memo_stats()           # since the last reset
+        for k in memo_acc:
+            memo_acc[k] += m[k]
+
     def device_step(s):
         p = s % L
         if p == 0:
+            if s > 0:
+                fold_memo()
             eng.reset(arrivals)
         eng.step_device(on_dev[p].data_ptr(), True, stats_dev.data_ptr(), ncs_dev.data_ptr())
         gather_metrics()
@@ -274,6 +283,9 @@ def run_b200_arm(args, rank, world, local_rank):
         device_step(s)
     barrier()
     eng.lookahead_kernel_time(reset=True)
+    fold_memo()
+    for k in memo_acc:
+        memo_acc[k] = 0
     launches0 = eng.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -290,7 +302,8 @@ def run_b200_arm(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
     launches = eng.launch_count - launches0
     kt = eng.lookahead_kernel_time(reset=True)
-    memo = eng.memo_stats()
+    fold_memo()
+    memo = dict(memo_acc)
     eng.check_status()
     # the episode resets inside the loop synchronise the stream, so wall time ~ device time; use the larger
     elapsed_ms = max(dev_ms, 0.0)

@@ -131,6 +131,7 @@ struct ramp_engine {
     double la_ms_total = 0.0;
     int64_t la_launches = 0;
     unsigned long long la_items_base = 0, la_bytes_base = 0;
+    MemoStats memo_base{};       // device counters at the last ramp_reset (memo statistics are reported since the reset)
 };
 
 namespace {
@@ -506,9 +507,8 @@ int ramp_reset(ramp_engine_t* e, const ramp_arrival_t* arrivals, int32_t n_jobs)
     // memo is per env instance per episode: cleared on reset (RCE:269-275)
     CUDA_TRY(cudaMemsetAsync(e->d_memo_keys, 0, sizeof(unsigned long long) * e->memo_cap, e->stream));
     CUDA_TRY(cudaMemsetAsync(e->pool.top, 0, sizeof(unsigned long long), e->stream));
-    CUDA_TRY(cudaMemsetAsync(e->d_stats, 0, sizeof(MemoStats), e->stream));
+    CUDA_TRY(cudaMemcpyAsync(&e->memo_base, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost, e->stream));   // counters stay cumulative
     CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), e->stream));
-    e->la_items_base = 0; e->la_bytes_base = 0;
     ramp_reset_kernel<<<(B + 127) / 128, 128, 0, e->stream>>>(e->ep);
     e->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -683,9 +683,9 @@ int ramp_get_memo_stats(ramp_engine_t* e, int64_t* lookups, int64_t* hits, int64
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     MemoStats s{};
     CUDA_TRY(cudaMemcpy(&s, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost));
-    if (lookups) *lookups = (int64_t)s.lookups;
-    if (hits) *hits = (int64_t)s.hits;
-    if (lookaheads) *lookaheads = (int64_t)s.lookaheads;
+    if (lookups) *lookups = (int64_t)(s.lookups - e->memo_base.lookups);
+    if (hits) *hits = (int64_t)(s.hits - e->memo_base.hits);
+    if (lookaheads) *lookaheads = (int64_t)(s.lookaheads - e->memo_base.lookaheads);
     return RAMP_OK;
 }
 
