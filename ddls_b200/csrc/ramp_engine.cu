@@ -84,6 +84,9 @@ struct ramp_engine {
     // memo + results
     uint32_t memo_cap = 0;
     unsigned long long* d_memo_keys = nullptr;
+    int32_t* d_memo_vals = nullptr;
+    unsigned long long* d_memo_keys2 = nullptr;
+    uint32_t memo_cap2 = 0;
     ResultSlots res{};
     int32_t n_slots = 0;
     TracePool pool{};
@@ -320,7 +323,12 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     e->memo_cap = 1u << cfg.memo_capacity_log2;
     CUDA_TRY(cudaMalloc(&e->d_memo_keys, sizeof(unsigned long long) * e->memo_cap));
     CUDA_TRY(cudaMemset(e->d_memo_keys, 0, sizeof(unsigned long long) * e->memo_cap));
-    e->n_slots = (int32_t)e->memo_cap + B;
+    CUDA_TRY(cudaMalloc(&e->d_memo_vals, sizeof(int32_t) * e->memo_cap));
+    e->memo_cap2 = 1;
+    while (e->memo_cap2 < (uint32_t)cfg.max_templates * 2u) e->memo_cap2 <<= 1;
+    CUDA_TRY(cudaMalloc(&e->d_memo_keys2, sizeof(unsigned long long) * e->memo_cap2));
+    CUDA_TRY(cudaMemset(e->d_memo_keys2, 0, sizeof(unsigned long long) * e->memo_cap2));
+    e->n_slots = (int32_t)e->memo_cap + B + (int32_t)e->memo_cap2;
     if (alloc_result_slots(e->res, e->n_slots) != RAMP_OK) return RAMP_ERR_CUDA;
     CUDA_TRY(cudaMemset(e->res.status, 0, sizeof(int32_t) * e->n_slots));
 
@@ -374,7 +382,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     for (auto& t : e->templates) cudaFree(t.blob);
-    cudaFree(e->d_templates); cudaFree(e->d_memo_keys);
+    cudaFree(e->d_templates); cudaFree(e->d_memo_keys); cudaFree(e->d_memo_vals); cudaFree(e->d_memo_keys2);
     free_result_slots(e->res); free_result_slots(e->sa_res);
     cudaFree(e->pool.n_active); cudaFree(e->pool.tick); cudaFree(e->pool.top);
     cudaFree(e->d_items); cudaFree(e->d_items_big); cudaStreamDestroy(e->stream2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaFree(e->d_counters); cudaFree(e->d_stats); cudaFree(e->d_actions);
@@ -506,7 +514,9 @@ int ramp_reset(ramp_engine_t* e, const ramp_arrival_t* arrivals, int32_t n_jobs)
     e->ep.n_jobs = n_jobs;
     // memo is per env instance per episode: cleared on reset (RCE:269-275)
     CUDA_TRY(cudaMemsetAsync(e->d_memo_keys, 0, sizeof(unsigned long long) * e->memo_cap, e->stream));
-    CUDA_TRY(cudaMemsetAsync(e->pool.top, 0, sizeof(unsigned long long), e->stream));
+    // the batch-wide cache of RAMP_MEMO_SHARED (level-2 keys, its result slots and traces) is a pure function of the
+    // lowered job and survives the reset; every other mode starts from an empty trace pool
+    if (e->cfg.memo_mode != RAMP_MEMO_SHARED) CUDA_TRY(cudaMemsetAsync(e->pool.top, 0, sizeof(unsigned long long), e->stream));
     CUDA_TRY(cudaMemcpyAsync(&e->memo_base, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost, e->stream));   // counters stay cumulative
     CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), e->stream));
     ramp_reset_kernel<<<(B + 127) / 128, 128, 0, e->stream>>>(e->ep);
@@ -541,6 +551,8 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
     PlanArgs p{};
     p.actions = d_actions; p.templates = e->d_templates; p.n_templates = (int32_t)e->templates.size();
     p.ep = e->ep; p.memo.keys = e->d_memo_keys; p.memo.mask = e->memo_cap - 1; p.memo.mode = e->cfg.memo_mode;
+    p.memo.vals = e->d_memo_vals; p.memo.keys2 = e->d_memo_keys2; p.memo.mask2 = e->memo_cap2 - 1;
+    p.memo.slot2_base = (int32_t)e->memo_cap + e->cfg.n_episodes;
     p.items = e->d_items; p.items_big = e->d_items_big; p.counters = e->d_counters; p.stats = e->d_stats;
     ramp_plan_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
     e->launches++;
@@ -686,6 +698,18 @@ int ramp_get_memo_stats(ramp_engine_t* e, int64_t* lookups, int64_t* hits, int64
     if (lookups) *lookups = (int64_t)(s.lookups - e->memo_base.lookups);
     if (hits) *hits = (int64_t)(s.hits - e->memo_base.hits);
     if (lookaheads) *lookaheads = (int64_t)(s.lookaheads - e->memo_base.lookaheads);
+    return RAMP_OK;
+}
+
+int ramp_get_memo_stats_ex(ramp_engine_t* e, int64_t out[4]) {
+    if (!e || !out) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    MemoStats s{};
+    CUDA_TRY(cudaMemcpy(&s, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost));
+    out[0] = (int64_t)(s.lookups - e->memo_base.lookups);
+    out[1] = (int64_t)(s.hits - e->memo_base.hits);
+    out[2] = (int64_t)(s.shared_hits - e->memo_base.shared_hits);
+    out[3] = (int64_t)(s.lookaheads - e->memo_base.lookaheads);
     return RAMP_OK;
 }
 

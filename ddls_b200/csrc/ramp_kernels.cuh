@@ -83,7 +83,7 @@ struct Counters {               // the first four words are zeroed at the start 
     int32_t err_status;
 };
 
-struct MemoStats { unsigned long long lookups, hits, lookaheads, alg_bytes; };
+struct MemoStats { unsigned long long lookups, hits, lookaheads, alg_bytes, shared_hits; };
 
 // running-job table fields (SoA: [field][row][episode])
 enum { RF_JCT = 0, RF_STARTED, RF_COMM, RF_COMP, RF_UTIL, RF_PART_OP_MEM, RF_PART_DEP, RF_FLOW, RF_ORIG_OP_MEM,
@@ -111,6 +111,11 @@ struct MemoTable {
     unsigned long long* keys;   // [cap] 0 = empty
     uint32_t mask;              // cap - 1
     int32_t mode;
+    // RAMP_MEMO_SHARED: level 1 = keys[] above (per episode) with vals[] -> result slot; level 2 = batch-wide cache
+    int32_t* vals;              // [cap]
+    unsigned long long* keys2;  // [cap2] keyed by the canonical (byte-identical) template id
+    uint32_t mask2;
+    int32_t slot2_base;         // result slot of level-2 position 0
 };
 
 struct LookaheadArgs {
@@ -694,6 +699,32 @@ __global__ void ramp_plan_kernel(const PlanArgs p) {
     if (p.memo.mode == RAMP_MEMO_OFF) {
         slot = (int)(cap_mask + 1u) + b;
         ran = true;
+    } else if (p.memo.mode == RAMP_MEMO_SHARED) {
+        // level 1: the reference's per-episode memo (decides WHICH lookahead this job uses: first seen (model, degree) wins)
+        const unsigned long long key = ((unsigned long long)(b + 1) << 32) | ((unsigned long long)(T.model_id & 0xFFFF) << 16)
+                                       | (unsigned long long)(T.degree & 0xFFFF);
+        uint32_t pos = (uint32_t)splitmix64(key) & cap_mask;
+        int pos1 = -1;
+        for (uint32_t probe = 0; probe <= cap_mask; ++probe) {
+            const unsigned long long old = atomicCAS(&p.memo.keys[pos], 0ull, key);
+            if (old == 0ull) { pos1 = (int)pos; break; }
+            if (old == key) { slot = p.memo.vals[pos]; break; }          // hit RCE:495-498
+            pos = (pos + 1u) & cap_mask;
+        }
+        atomicAdd(&p.stats->lookups, 1ull);
+        if (slot >= 0) atomicAdd(&p.stats->hits, 1ull);
+        else if (pos1 >= 0) {
+            // level 2: has any episode of the batch already run (or claimed) the lookahead of this exact lowered job?
+            const unsigned long long key2 = 0x8000000000000000ull | (unsigned long long)(T.canon_id + 1);
+            uint32_t q = (uint32_t)splitmix64(key2) & p.memo.mask2;
+            for (uint32_t probe = 0; probe <= p.memo.mask2; ++probe) {
+                const unsigned long long old = atomicCAS(&p.memo.keys2[q], 0ull, key2);
+                if (old == 0ull) { slot = p.memo.slot2_base + (int)q; ran = true; break; }
+                if (old == key2) { slot = p.memo.slot2_base + (int)q; atomicAdd(&p.stats->shared_hits, 1ull); break; }
+                q = (q + 1u) & p.memo.mask2;
+            }
+            if (slot >= 0) p.memo.vals[pos1] = slot;
+        }
     } else {
         unsigned long long key;
         if (p.memo.mode == RAMP_MEMO_REFERENCE)                           // [model][max_num_partitions] per env instance RCE:491-492

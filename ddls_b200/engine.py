@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libramp_b200.so')
 
 RAMP_OK = 0
-MEMO_REFERENCE, MEMO_EXACT, MEMO_OFF = 0, 1, 2
+MEMO_REFERENCE, MEMO_EXACT, MEMO_OFF, MEMO_SHARED = 0, 1, 2, 3
 ACT_SKIP = 1
 
 STEP_STATS = [
@@ -96,6 +96,7 @@ def load_library():
     L.ramp_episode_state_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.ramp_export_episode_state_to.argtypes = [C.c_void_p, C.c_void_p]
     L.ramp_get_memo_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.ramp_get_memo_stats_ex.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.ramp_get_last_lookahead.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     L.ramp_run_lookaheads.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int32, C.POINTER(C.c_float)]
@@ -106,7 +107,7 @@ def load_library():
     for name in ('ramp_engine_create', 'ramp_engine_destroy', 'ramp_register_template', 'ramp_template_count',
                  'ramp_reset', 'ramp_set_arrivals', 'ramp_step_host', 'ramp_step_device', 'ramp_sync', 'ramp_check_status',
                  'ramp_get_job_records', 'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_export_episode_state_to',
-                 'ramp_get_memo_stats', 'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_get_lookahead_kernel_time'):
+                 'ramp_get_memo_stats', 'ramp_get_memo_stats_ex', 'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_get_lookahead_kernel_time'):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -116,7 +117,7 @@ EXPORTED_SYMBOLS = ['ramp_last_error', 'ramp_engine_create', 'ramp_engine_destro
                     'ramp_register_template', 'ramp_template_count', 'ramp_reset', 'ramp_set_arrivals', 'ramp_step_host',
                     'ramp_step_device', 'ramp_sync', 'ramp_check_status', 'ramp_get_job_records',
                     'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_export_episode_state_to',
-                    'ramp_get_memo_stats',
+                    'ramp_get_memo_stats', 'ramp_get_memo_stats_ex',
                     'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_launch_count',
                     'ramp_get_lookahead_kernel_time']
 
@@ -242,6 +243,11 @@ class RampEngine:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _check(self._L.ramp_get_memo_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(lookups=a.value, hits=b.value, lookaheads=c.value)
+
+    def memo_stats_ex(self):
+        out = (C.c_int64 * 4)()
+        _check(self._L.ramp_get_memo_stats_ex(self._h, out))
+        return dict(lookups=out[0], hits=out[1], shared_hits=out[2], lookaheads=out[3])
 
     def last_lookahead(self, episode):
         res = np.zeros(1, dtype=LOOKAHEAD_RESULT_DTYPE)

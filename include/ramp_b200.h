@@ -51,6 +51,9 @@ extern "C" {
 #define RAMP_MEMO_REFERENCE 0        /* key = (episode, model, max partition degree): first seen wins, per episode */
 #define RAMP_MEMO_EXACT 1            /* key = 64-bit fingerprint of the lowered job: shared across episodes        */
 #define RAMP_MEMO_OFF 2              /* every mount runs its lookahead                                              */
+#define RAMP_MEMO_SHARED 3           /* reference semantics (per-episode first-seen-wins on (model, degree)) on top of a batch-wide
+                                        result cache keyed by the byte-identical lowered job: the lookahead an episode would run is
+                                        executed once per batch and survives ramp_reset -- same results, far fewer lookaheads */
 
 typedef struct ramp_engine ramp_engine_t;
 
@@ -197,6 +200,8 @@ int ramp_episode_state_device(ramp_engine_t* eng, double** d_out);
 int ramp_export_episode_state_to(ramp_engine_t* eng, double* d_dst);
 /* memo statistics since the last reset: lookups, hits, lookaheads executed */
 int ramp_get_memo_stats(ramp_engine_t* eng, int64_t* lookups, int64_t* hits, int64_t* lookaheads);
+/* {lookups, per-episode hits, batch-wide (shared) hits, lookaheads executed} since the last reset */
+int ramp_get_memo_stats_ex(ramp_engine_t* eng, int64_t out[4]);
 /* the lookahead (memoised or fresh) used by episode `episode`'s most recent mount: result + trace
  * (tick_counter_to_active_workers_tick_size RCE:467); trace buffers are HOST, capacity trace_cap. */
 int ramp_get_last_lookahead(ramp_engine_t* eng, int32_t episode, ramp_lookahead_result_t* res,

@@ -77,7 +77,7 @@ def test_lookahead_vs_oracle_all_templates(fname, mode, eng_mod, oracle_lib):
 
 
 @pytest.mark.parametrize('fname', FILES)
-@pytest.mark.parametrize('memo_mode', [0, 1, 2])
+@pytest.mark.parametrize('memo_mode', [0, 1, 2, 3])
 def test_episode_replay_vs_reference_golden(fname, memo_mode, eng_mod):
     """RampClusterEnvironment.step RCE:894-1179 replayed for a batch of 5 identical episodes: step_stats,
     job records and counters against the reference's own run."""
@@ -106,17 +106,23 @@ def test_episode_replay_vs_reference_golden(fname, memo_mode, eng_mod):
                 action_row(actions, b, tids[int(g.d['step_tid'][s])], job.mount)
         stats = eng.step(actions)
         eng.check_status()
-        if memo_mode == 0:
+        if memo_mode in (0, 3):          # 3 = reference semantics + batch-wide result cache: same results, fewer lookaheads
             for b in range(B):
-                for k in exact + ['lookahead_ran']:
+                for k in exact + (['lookahead_ran'] if memo_mode == 0 else []):
                     assert stats[b, SS[k]] == ref[s, SS[k]], (fname, s, b, k)
                 for k in STEP_STATS:
+                    if memo_mode == 3 and k == 'lookahead_ran':
+                        continue
                     a, c = stats[b, SS[k]], ref[s, SS[k]]
                     assert a == pytest.approx(c, rel=1e-6, abs=0), (fname, s, b, k, a, c)
         else:
             cols = [i for k, i in SS.items() if k != 'lookahead_ran']   # in exact mode one episode per key runs it
             assert (stats[:, cols] == stats[0, cols]).all()
-    if memo_mode != 0:
+    if memo_mode == 3:
+        m = eng.memo_stats_ex()
+        assert m['lookaheads'] <= g.n_lookaheads            # 5 episodes share what one reference env ran
+        assert m['shared_hits'] >= (B - 1) * m['lookaheads']
+    if memo_mode not in (0, 3):
         eng.close()
         return
     rec = eng.job_records()
@@ -299,3 +305,37 @@ def test_many_mixed_items_per_launch(mode, cta_threads, eng_mod, oracle_lib):
             assert (res['jct'][sel] == want[d]['jct']).all() and (res['comm'][sel] == want[d]['comm']).all()
             assert (res['comp'][sel] == want[d]['comp']).all() and (res['n_ticks'][sel] == want[d]['n_ticks']).all()
     eng.close()
+
+
+def test_shared_memo_survives_reset_and_matches_reference_mode(eng_mod):
+    """RAMP_MEMO_SHARED: second episode after ramp_reset re-uses the batch-wide cache (no lookahead runs) and every
+    step-stats entry still equals the per-episode reference mode."""
+    from ddls_b200.engine import action_row, SS
+    g = Golden('mixed16')
+    arr = g.arrivals()
+    B = 4
+    runs = {}
+    for mode in (0, 3):
+        eng = eng_mod.RampEngine(n_episodes=B, n_cluster_workers=g.n_cluster_workers, max_jobs=len(arr), memo_mode=mode,
+                                 max_simulation_run_time=g.max_sim_time, trace_cap=1 << 16)
+        tids = [eng.register_template(t) for t in g.templates]
+        out = []
+        for episode in range(2):
+            eng.reset(np.stack([arr] * B))
+            for s in range(g.n_steps):
+                a = eng.make_actions()
+                job = g.step_job(s)
+                if job is not None:
+                    for b in range(B):
+                        action_row(a, b, tids[int(g.d['step_tid'][s])], job.mount)
+                st = eng.step(a)
+                out.append(np.delete(st, SS['lookahead_ran'], axis=1))
+            out.append(eng.job_records()['jct'].copy())
+            if mode == 3:
+                m = eng.memo_stats_ex()
+                if episode == 1:
+                    assert m['lookaheads'] == 0 and m['lookups'] > 0
+        runs[mode] = out
+        eng.close()
+    for a, b in zip(runs[0], runs[3]):
+        np.testing.assert_array_equal(a, b)
