@@ -12,7 +12,6 @@ GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
-    config.addinivalue_line('markers', 'reference: needs the read-only reference checkout at /root/reference')
 
 
 def golden_files():
