@@ -42,6 +42,11 @@ struct TemplateDev {
     const unsigned long long* dep_km;  // [E] by dep index (CSR order): key | channel << 32 | is_flow << 48 | n_parents(child) << 49
                                        //     (the n_parents byte only when par_in_smem, i.e. every in-degree <= 255)
     const double*   dep_rt;       // [E] by dep index: init_run_time (RCE:542-560)
+    const unsigned long long* dep_kd;  // [E] by dep index: the whole dep in one word (warp kernel):
+                                       //     key | channel << kd_cshift | is_flow << kd_fshift | n_parents(child) << (kd_fshift+1)
+                                       //     | child op << kd_dshift; channel == kd_cmask means "none" (non-flows)
+    uint32_t kd_kmask, kd_cmask;  // (1 << key bits) - 1, (1 << channel bits) - 1
+    int32_t  kd_cshift, kd_fshift, kd_dshift, _pad1;
     const int32_t*  dep_dst;      // [E] by dep index: child op index
     const int32_t*  src_ops;      // [n_src] ops with in-degree 0: the initial ops_ready (JOB:474-481)
     uint64_t scratch_bytes;       // HBM-side dynamic state one running lookahead of this template may need
@@ -265,8 +270,12 @@ __device__ __forceinline__ double util_sum(const double* term, int n_rec) {
 //      frontier as one flattened, coalesced copy (first ticked next tick == the RCE:429 snapshot). (RCE:691-716)
 //   I,J lane 0 accumulates t / comm / comp and the trace in tick order                              (RCE:442-445, 777-791)
 #define RAMP_U 4            // batch depth: independent loads in flight per lane per phase
+#ifndef RAMP_OPS_CAP
 #define RAMP_OPS_CAP 48     // op-frontier records kept in shared memory per buffer (overflow goes to HBM)
+#endif
+#ifndef RAMP_F_CAP
 #define RAMP_F_CAP 384      // dep-frontier records kept in shared memory (overflow goes to HBM); sized so that 12 lookahead warps fit an SM
+#endif
 
 struct OpsView { int4* a_sm; int2* b_sm; int4* a_ovf; int2* b_ovf; };
 __device__ __forceinline__ void ops_get(const OpsView& v, int k, int4& ra, int2& rb) {
@@ -275,20 +284,15 @@ __device__ __forceinline__ void ops_get(const OpsView& v, int k, int4& ra, int2&
 __device__ __forceinline__ void ops_put(const OpsView& v, int k, const int4 ra, const int2 rb) {
     if (k < RAMP_OPS_CAP) { v.a_sm[k] = ra; v.b_sm[k] = rb; } else { v.a_ovf[k - RAMP_OPS_CAP] = ra; v.b_ovf[k - RAMP_OPS_CAP] = rb; }
 }
-struct FrontView { unsigned long long* km_sm; double* rem_sm; int32_t* dst_sm; unsigned long long* km_ovf; double* rem_ovf; int32_t* dst_ovf; };
-__device__ __forceinline__ void f_get(const FrontView& v, int k, unsigned long long& km, double& rem, int& dst) {
-    if (k < RAMP_F_CAP) { km = v.km_sm[k]; rem = v.rem_sm[k]; dst = v.dst_sm[k]; }
-    else { km = v.km_ovf[k - RAMP_F_CAP]; rem = v.rem_ovf[k - RAMP_F_CAP]; dst = v.dst_ovf[k - RAMP_F_CAP]; }
+// dep frontier entry = the packed dep word (TemplateDev::dep_kd) + the remaining time: 16 B
+struct FrontView { unsigned long long* kd_sm; double* rem_sm; unsigned long long* kd_ovf; double* rem_ovf; };
+__device__ __forceinline__ void f_get(const FrontView& v, int k, unsigned long long& kd, double& rem) {
+    if (k < RAMP_F_CAP) { kd = v.kd_sm[k]; rem = v.rem_sm[k]; } else { kd = v.kd_ovf[k - RAMP_F_CAP]; rem = v.rem_ovf[k - RAMP_F_CAP]; }
 }
-__device__ __forceinline__ void f_put(const FrontView& v, int k, unsigned long long km, double rem, int dst) {
-    if (k < RAMP_F_CAP) { v.km_sm[k] = km; v.rem_sm[k] = rem; v.dst_sm[k] = dst; }
-    else { v.km_ovf[k - RAMP_F_CAP] = km; v.rem_ovf[k - RAMP_F_CAP] = rem; v.dst_ovf[k - RAMP_F_CAP] = dst; }
-}
-__device__ __forceinline__ void f_get_km_rem(const FrontView& v, int k, unsigned long long& km, double& rem) {
-    if (k < RAMP_F_CAP) { km = v.km_sm[k]; rem = v.rem_sm[k]; } else { km = v.km_ovf[k - RAMP_F_CAP]; rem = v.rem_ovf[k - RAMP_F_CAP]; }
+__device__ __forceinline__ void f_put(const FrontView& v, int k, unsigned long long kd, double rem) {
+    if (k < RAMP_F_CAP) { v.kd_sm[k] = kd; v.rem_sm[k] = rem; } else { v.kd_ovf[k - RAMP_F_CAP] = kd; v.rem_ovf[k - RAMP_F_CAP] = rem; }
 }
 
-// bytes of shared memory one lookahead warp needs
 // parent counter of op `child` += 1, returns the new value (JOB:530).  Small jobs keep one BYTE per op in shared memory
 // (four per word, atomicAdd of 1 << 8*(child&3): a byte never carries because it never exceeds the in-degree <= 255)
 __device__ __forceinline__ uint32_t par_inc(bool in_smem, uint32_t* par_sm, uint32_t* par_gl, int child) {
@@ -300,14 +304,13 @@ __device__ __forceinline__ uint32_t par_inc(bool in_smem, uint32_t* par_sm, uint
     return atomicAdd(&par_gl[child], 1u) + 1u;
 }
 
+// bytes of shared memory one lookahead warp needs
 __host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap, int par_cap) {
     size_t b = 0;
-    b += (size_t)RAMP_F_CAP * 8 * 2;             // km, rem
-    b += (size_t)c_cap * 8;                      // crem
     b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
+    b += (size_t)RAMP_F_CAP * 8 * 2;             // kd, rem
     b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
-    b += (size_t)RAMP_F_CAP * 4;                 // dst
-    b += (size_t)(w_cap + c_cap) * 4;            // wkey, ckey
+    b += (size_t)(w_cap + 2 * c_cap) * 4;        // wkey, ckey (this tick / next tick)
     b += (size_t)par_cap;                        // parent counters (bytes)
     return (b + 15) & ~(size_t)15;
 }
@@ -320,17 +323,15 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned char* my_smem = smem_raw + (size_t)warp * lookahead_smem_per_warp(a.w_cap, a.c_cap, a.par_cap);
-    // layout by decreasing alignment: int4 | 8-byte arrays | 4-byte arrays (c_cap may be odd)
+    // layout by decreasing alignment: int4 | 8-byte arrays | 4-byte arrays
     int4* ops_a_sm0 = reinterpret_cast<int4*>(my_smem);                                  // [2][RAMP_OPS_CAP]
     FrontView fr;
-    fr.km_sm = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);      // [RAMP_F_CAP]
-    fr.rem_sm = reinterpret_cast<double*>(fr.km_sm + RAMP_F_CAP);                        // [RAMP_F_CAP]
-    double* crem = fr.rem_sm + RAMP_F_CAP;                                               // [c_cap] remaining time of the channel's winner
-    int2* ops_b_sm0 = reinterpret_cast<int2*>(crem + a.c_cap);                           // [2][RAMP_OPS_CAP]
-    fr.dst_sm = reinterpret_cast<int32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);                // [RAMP_F_CAP]
-    uint32_t* wkey = reinterpret_cast<uint32_t*>(fr.dst_sm + RAMP_F_CAP);                // [w_cap] best key among the ready ops on the worker
-    uint32_t* ckey = wkey + a.w_cap;                                                     // [c_cap] best key among the ready flows on the channel
-    uint32_t* par_sm = ckey + a.c_cap;                                                   // [par_cap / 4] byte parent counters
+    fr.kd_sm = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);      // [RAMP_F_CAP]
+    fr.rem_sm = reinterpret_cast<double*>(fr.kd_sm + RAMP_F_CAP);                        // [RAMP_F_CAP]
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(fr.rem_sm + RAMP_F_CAP);                   // [2][RAMP_OPS_CAP]
+    uint32_t* wkey = reinterpret_cast<uint32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);          // [w_cap] best key among the ready ops on the worker
+    uint32_t* ckey0 = wkey + a.w_cap;                                                    // [2][c_cap] best key among the ready flows on the channel
+    uint32_t* par_sm = ckey0 + 2 * a.c_cap;                                              // [par_cap / 4] byte parent counters
 
     unsigned char* slab = a.scratch + (uint64_t)(blockIdx.x * WPB + warp) * a.scratch_stride;
     const uint64_t trace_region = a.scratch_stride - align_up((uint64_t)a.trace_cap * 12, 16);
@@ -347,22 +348,25 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
         const TemplateDev& T = a.templates[item.template_id];
         const int N = T.n_ops, E = T.n_deps, W = T.n_workers, C = T.n_channels;
         const ScratchView sv = carve(slab, N, E, trace_region, a.trace_cap);
-        fr.km_ovf = sv.f_km_ovf; fr.rem_ovf = sv.f_rem_ovf; fr.dst_ovf = sv.f_dst_ovf;
+        fr.kd_ovf = sv.f_km_ovf; fr.rem_ovf = sv.f_rem_ovf;
 
         const int4* __restrict__ t_op_rec = T.op_rec;
         const int2* __restrict__ t_op_row = T.op_row;
         const uint16_t* __restrict__ t_n_parents = T.op_n_parents;
-        const unsigned long long* __restrict__ t_dep_km = T.dep_km;
+        const unsigned long long* __restrict__ t_dep_kd = T.dep_kd;
         const double* __restrict__ t_dep_rt = T.dep_rt;
-        const int32_t* __restrict__ t_dep_dst = T.dep_dst;
         uint32_t* par_done = sv.par_done;
         const bool psm = T.par_in_smem != 0;
+        const uint32_t kmask = T.kd_kmask, cmask = T.kd_cmask;
+        const int csh = T.kd_cshift, fsh = T.kd_fshift, dsh = T.kd_dshift;
 
         // ---- init (JOB:432-484) ----
         if (psm) { for (int i = lane; i < (N + 3) / 4; i += 32) par_sm[i] = 0u; }
         else { for (int i = lane; i < N; i += 32) par_done[i] = 0u; }
         for (int i = lane; i < W; i += 32) wkey[i] = 0u;
-        for (int i = lane; i < C; i += 32) ckey[i] = 0u;
+        for (int i = lane; i < 2 * a.c_cap; i += 32) ckey0[i] = 0u;
+        uint32_t* ck_cur = ckey0;             // winners among the deps of this tick's snapshot
+        uint32_t* ck_nxt = ckey0 + a.c_cap;   // being built for the next tick (all zero at the start of a tick)
         OpsView ops, ops_n;
         ops.a_sm = ops_a_sm0; ops.b_sm = ops_b_sm0; ops.a_ovf = sv.ops_a_ovf[0]; ops.b_ovf = sv.ops_b_ovf[0];
         ops_n.a_sm = ops_a_sm0 + RAMP_OPS_CAP; ops_n.b_sm = ops_b_sm0 + RAMP_OPS_CAP; ops_n.a_ovf = sv.ops_a_ovf[1]; ops_n.b_ovf = sv.ops_b_ovf[1];
@@ -412,19 +416,22 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             const double t_op = warp_min_f64(mo);
             const int n_active = warp_sum_i32(na);
 
-            // ---- C, D ----
+            // ---- C, D: ck_cur[c] holds the arg-max key over the ready flows on channel c (built while the previous tick
+            //      compacted its survivors and appended its arrivals), so the winners are the entries that match it ----
             const bool any_nf = n_nonflow > 0;
             double t_comm = 0.0;
             if (!any_nf) {
                 double md = INF;
-                for (int c = lane; c < C; c += 32) {
-                    if (ckey[c] != 0u) {
-                        const double rem = crem[c];
-                        md = (rem < md) ? rem : md;
-                    }
+                for (int k = lane; k < nF; k += 32) {
+                    unsigned long long kd; double rem;
+                    f_get(fr, k, kd, rem);
+                    const uint32_t c = (uint32_t)(kd >> csh) & cmask;
+                    if (c != cmask && ck_cur[c] == ((uint32_t)kd & kmask)) md = (rem < md) ? rem : md;
                 }
                 t_comm = warp_min_f64(md);
             }
+            __syncwarp();
+            for (int c = lane; c < C; c += 32) ck_cur[c] = 0u;        // this table is the next tick's "next"
             // ---- E ----
             const double tick = (t_comm < t_op) ? t_comm : t_op;
 
@@ -441,51 +448,49 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             }
             ++tick_no;
 
-            // ---- H: the deps of the pre-tick snapshot [0, nF); survivors slide down to [0, p).  32 entries per iteration; the
-            //      common case (nobody in the group completes) only rewrites the remaining times ----
+            // ---- H: the deps of the pre-tick snapshot [0, nF); survivors slide down to [0, p) and vote for the next tick's
+            //      channel winners.  32 entries per iteration ----
             int nO_next = 0;
             int p = 0;
             int ddone = 0, nf_done = 0;
-            bool rescan = false;
             for (int kb = 0; kb < nF; kb += 32) {
                 const int k = kb + lane;
-                const bool valid = k < nF;
-                unsigned long long km = 0ull;
+                const int n_here = (nF - kb < 32) ? (nF - kb) : 32;
+                const bool valid = lane < n_here;
+                unsigned long long kd = 0ull;
                 double rem = 1.0;
-                int child = 0;
-                if (valid) f_get(fr, k, km, rem, child);
-                const bool is_flow = ((km >> 48) & 1ull) != 0ull;
+                if (valid) f_get(fr, k, kd, rem);
+                const bool is_flow = ((kd >> fsh) & 1ull) != 0ull;
                 const bool ticked = valid && !(any_nf && is_flow);                               // RCE:434-439
                 const double r2 = ticked ? tick_down(rem, tick) : rem;                          // JOB:561
                 const bool done = ticked && (r2 == 0.0);                                        // JOB:562
-                const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
-                const bool winner = valid && is_flow && c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km;
+                const bool keep = valid && !done;
+                const uint32_t c = (uint32_t)(kd >> csh) & cmask;
+                if (keep && c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd & kmask);            // RCE:665-689 for the next tick
                 const unsigned dmask = __ballot_sync(FULL, done);
                 if (dmask == 0u) {
-                    if (winner && ticked) crem[c] = r2;            // keep the winner's remaining time current
                     if (p == kb) {                                 // nothing before it died either: update in place
                         if (ticked) { if (k < RAMP_F_CAP) fr.rem_sm[k] = r2; else fr.rem_ovf[k - RAMP_F_CAP] = r2; }
                     } else {
                         __syncwarp();                              // all lanes have read before anything is written over
-                        if (valid) f_put(fr, p + lane, km, r2, child);
+                        if (valid) f_put(fr, p + lane, kd, r2);
                     }
-                    p += (nF - kb < 32) ? (nF - kb) : 32;          // warp-uniform: every valid entry of the group survives
+                    p += n_here;                                   // warp-uniform: every valid entry of the group survives
                 } else {
                     // JOB:525-536 for the completing lanes
                     uint32_t cnt = 0u, np = 1u;
+                    int child = 0;
                     if (done) {
+                        child = (int)(kd >> dsh);
                         cnt = par_inc(psm, par_sm, par_done, child);                            // JOB:530
-                        np = psm ? (uint32_t)(km >> 49) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
+                        np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
                         ++ddone;
                         if (!is_flow) ++nf_done;
-                        if (winner) rescan = true;                 // the channel's winner completed: recompute the slots
-                    } else if (winner && ticked) {
-                        crem[c] = r2;
                     }
-                    const bool keep = valid && !done;
-                    const unsigned mk = __ballot_sync(FULL, keep);
+                    const unsigned vm = (n_here == 32) ? FULL : ((1u << n_here) - 1u);
+                    const unsigned mk = vm & ~dmask;
                     __syncwarp();
-                    if (keep) f_put(fr, p + __popc(mk & lt_mask), km, r2, child);
+                    if (keep) f_put(fr, p + __popc(mk & lt_mask), kd, r2);
                     p += __popc(mk);
                     const bool readied = done && (cnt == np);                                    // JOB:531 (fires once)
                     const unsigned m = __ballot_sync(FULL, readied);
@@ -495,7 +500,6 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             }
             ddone = warp_sum_i32(ddone);
             nf_done = warp_sum_i32(nf_done);
-            rescan = __any_sync(FULL, rescan);
             deps_completed += ddone;
 
             // ---- G: tick the op winners; rows of the completed ops are appended at [p, tail) ----
@@ -539,9 +543,8 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                         const int total = __shfl_sync(FULL, inc, 31);
                         const int exc = inc - deg;
                         for (int jb = 0; jb < total; jb += 32 * RAMP_U) {
-                            unsigned long long km[RAMP_U];
+                            unsigned long long kd[RAMP_U];
                             double rt[RAMP_U];
-                            int dst[RAMP_U];
 #pragma unroll
                             for (int u = 0; u < RAMP_U; ++u) {
                                 const int jf = jb + u * 32 + lane;
@@ -555,23 +558,20 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                                 const int o_start = __shfl_sync(FULL, rb.x, lo);
                                 const int o_exc = __shfl_sync(FULL, exc, lo);
                                 const int e = o_start + (jc - o_exc);
-                                km[u] = 0ull; rt[u] = 0.0; dst[u] = 0;
+                                kd[u] = 0ull; rt[u] = 0.0;
                                 if (jf < total) {
-                                    km[u] = __ldg(&t_dep_km[e]);
+                                    kd[u] = __ldg(&t_dep_kd[e]);
                                     rt[u] = __ldg(&t_dep_rt[e]);                                // RCE:542-560
-                                    dst[u] = __ldg(&t_dep_dst[e]);
                                 }
                             }
 #pragma unroll
                             for (int u = 0; u < RAMP_U; ++u) {
                                 const int jf = jb + u * 32 + lane;
                                 if (jf < total) {
-                                    f_put(fr, tail + jf, km[u], rt[u], dst[u]);
-                                    if (((km[u] >> 48) & 1ull) == 0ull) ++arr_nonflow;
-                                    else if (!rescan) {
-                                        const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
-                                        if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km[u]);
-                                    }
+                                    f_put(fr, tail + jf, kd[u], rt[u]);
+                                    if (((kd[u] >> fsh) & 1ull) == 0ull) ++arr_nonflow;
+                                    const uint32_t c = (uint32_t)(kd[u] >> csh) & cmask;
+                                    if (c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd[u] & kmask);
                                 }
                             }
                         }
@@ -584,32 +584,6 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             n_nonflow += arr_nonflow - nf_done;
             __syncwarp();
 
-            // ---- channel winner slots ----
-            if (rescan) {
-                // a completed flow held its channel's slot: recompute the per-channel arg-max from the ready deps (RCE:665-689)
-                for (int c = lane; c < C; c += 32) ckey[c] = 0u;
-                __syncwarp();
-                for (int k = lane; k < tail; k += 32) {
-                    unsigned long long w; double r;
-                    f_get_km_rem(fr, k, w, r);
-                    if (((w >> 48) & 1ull) != 0ull) {
-                        const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
-                        if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)w);
-                    }
-                }
-                __syncwarp();
-            }
-            // remaining time of (possibly new) winners: all ready deps after a rescan, else only this tick's arrivals
-            for (int k = (rescan ? 0 : p) + lane; k < tail; k += 32) {
-                unsigned long long w; double r;
-                f_get_km_rem(fr, k, w, r);
-                if (((w >> 48) & 1ull) != 0ull) {
-                    const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
-                    if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)w) crem[c] = r;
-                }
-            }
-            __syncwarp();
-
             // ---- K, L ----
             const bool finished = (ops_completed == N) && (deps_completed == E);     // JOB:549-551
             if (!finished && isinf(tick)) status = RAMP_ST_INFINITE_TICK;             // RCE:462
@@ -617,6 +591,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             nF = tail;
             nO = nO_next;
             { const OpsView tmp = ops; ops = ops_n; ops_n = tmp; }
+            { uint32_t* tmp = ck_cur; ck_cur = ck_nxt; ck_nxt = tmp; }
         }
 
         // ---- results (RCE:450-452): copy the trace to an exactly-sized pool allocation ----

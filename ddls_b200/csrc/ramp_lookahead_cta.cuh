@@ -20,37 +20,45 @@ namespace ramp {
 #define RAMP_CTA_MIN_WARPS 16  // resident warps per SM the register allocation must allow
 #endif
 
-struct CtaCells {              // written during tick with parity p, read after that tick's barrier, reset one tick later
-    int n_ops_next;            // op frontier being built for the next tick
-    int tail;                  // dep frontier append cursor
-    int ddone, nf_done, arr_nf, ops_done, rescan, dq_n, n_active;
-    unsigned long long min_op, min_dep;
+struct CtaCells {              // written during the tick with parity p, read after that tick's barriers, reset one tick later
+    int n_ops_next;            // op frontier being built for the next tick                 (phase 2)
+    int ddone, nf_done, ops_done, dq_n;                                                  // (phase 2)
+    int n_active;                                                                        // (phase 1)
+    int arr, arr_nf, ctail;    // arrival cursor, arriving non-flows, compaction cursor     (phase 3)
+    unsigned long long min_op, min_dep;                                                  // (phase 1)
 };
 
 __host__ __device__ inline size_t lookahead_cta_smem(int w_cap, int c_cap, int par_cap) {
     size_t b = 0;
     b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
-    b += (size_t)2 * RAMP_CTA_F_CAP * 8 * 2;     // km, rem (two buffers)
-    b += (size_t)c_cap * 8;                      // crem
+    b += (size_t)2 * RAMP_CTA_F_CAP * 8 * 2;     // kd, rem (two buffers)
     b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
     b += (size_t)w_cap * 8;                      // done queue: {row start, degree}
-    b += (size_t)2 * RAMP_CTA_F_CAP * 4;         // dst (two buffers)
-    b += (size_t)(w_cap + c_cap) * 4;            // wkey, ckey
+    b += (size_t)(w_cap + 2 * c_cap) * 4;        // wkey, ckey (this tick / next tick)
     b += (size_t)par_cap;                        // parent counters (bytes)
     return (b + 15) & ~(size_t)15;
 }
 
-struct FrontBuf { unsigned long long* km_sm; double* rem_sm; int32_t* dst_sm; unsigned long long* km_ovf; double* rem_ovf; int32_t* dst_ovf; };
-__device__ __forceinline__ unsigned long long fb_km(const FrontBuf& v, int k) { return (k < RAMP_CTA_F_CAP) ? v.km_sm[k] : v.km_ovf[k - RAMP_CTA_F_CAP]; }
+// dep frontier entry = packed dep word (TemplateDev::dep_kd; 0 = dead entry) + remaining time
+struct FrontBuf { unsigned long long* kd_sm; double* rem_sm; unsigned long long* kd_ovf; double* rem_ovf; };
+__device__ __forceinline__ unsigned long long fb_kd(const FrontBuf& v, int k) { return (k < RAMP_CTA_F_CAP) ? v.kd_sm[k] : v.kd_ovf[k - RAMP_CTA_F_CAP]; }
 __device__ __forceinline__ double fb_rem(const FrontBuf& v, int k) { return (k < RAMP_CTA_F_CAP) ? v.rem_sm[k] : v.rem_ovf[k - RAMP_CTA_F_CAP]; }
-__device__ __forceinline__ int fb_dst(const FrontBuf& v, int k) { return (k < RAMP_CTA_F_CAP) ? v.dst_sm[k] : v.dst_ovf[k - RAMP_CTA_F_CAP]; }
-__device__ __forceinline__ void fb_set_km(const FrontBuf& v, int k, unsigned long long x) { if (k < RAMP_CTA_F_CAP) v.km_sm[k] = x; else v.km_ovf[k - RAMP_CTA_F_CAP] = x; }
+__device__ __forceinline__ void fb_set_kd(const FrontBuf& v, int k, unsigned long long x) { if (k < RAMP_CTA_F_CAP) v.kd_sm[k] = x; else v.kd_ovf[k - RAMP_CTA_F_CAP] = x; }
 __device__ __forceinline__ void fb_set_rem(const FrontBuf& v, int k, double x) { if (k < RAMP_CTA_F_CAP) v.rem_sm[k] = x; else v.rem_ovf[k - RAMP_CTA_F_CAP] = x; }
-__device__ __forceinline__ void fb_put(const FrontBuf& v, int k, unsigned long long km, double rem, int dst) {
-    if (k < RAMP_CTA_F_CAP) { v.km_sm[k] = km; v.rem_sm[k] = rem; v.dst_sm[k] = dst; }
-    else { v.km_ovf[k - RAMP_CTA_F_CAP] = km; v.rem_ovf[k - RAMP_CTA_F_CAP] = rem; v.dst_ovf[k - RAMP_CTA_F_CAP] = dst; }
+__device__ __forceinline__ void fb_put(const FrontBuf& v, int k, unsigned long long kd, double rem) {
+    if (k < RAMP_CTA_F_CAP) { v.kd_sm[k] = kd; v.rem_sm[k] = rem; }
+    else { v.kd_ovf[k - RAMP_CTA_F_CAP] = kd; v.rem_ovf[k - RAMP_CTA_F_CAP] = rem; }
 }
 
+// Three block barriers per tick:
+//   phase 1  op winners' min / count (B) and the min over the channel winners (D: an entry is its channel's winner iff its
+//            key equals ck_cur[channel], the arg-max built during the previous tick)            -> shared cells | barrier
+//   phase 2  thread 0: clock, overheads, trace (I, J).  All: H in place (survivors vote into ck_nxt, completions mark the
+//            entry dead, bump the child's parent counter and append readied ops), G part 1 (op winners tick; survivors go
+//            to the next op frontier, rows of completed ops to the done queue)                                  | barrier
+//   phase 3  G part 2: rows of the done queue are copied to the frontier tail (arrivals vote into ck_nxt), the frontier is
+//            compacted into the other buffer when more than half of it is dead, and phase A of the NEXT tick (per-worker
+//            arg-max over the next op frontier) runs here too                                                   | barrier
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahead_cta_kernel(const LookaheadArgs a) {
     constexpr int NT = NW * 32;
@@ -63,19 +71,15 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
 
     // layout by decreasing alignment
     int4* ops_a_sm0 = reinterpret_cast<int4*>(smem_raw);                                  // [2][RAMP_OPS_CAP]
-    unsigned long long* km_sm0 = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);   // [2][F_CAP]
-    double* rem_sm0 = reinterpret_cast<double*>(km_sm0 + 2 * RAMP_CTA_F_CAP);            // [2][F_CAP]
-    double* crem = rem_sm0 + 2 * RAMP_CTA_F_CAP;                                          // [c_cap]
-    int2* ops_b_sm0 = reinterpret_cast<int2*>(crem + a.c_cap);                            // [2][RAMP_OPS_CAP]
+    unsigned long long* kd_sm0 = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);   // [2][F_CAP]
+    double* rem_sm0 = reinterpret_cast<double*>(kd_sm0 + 2 * RAMP_CTA_F_CAP);            // [2][F_CAP]
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(rem_sm0 + 2 * RAMP_CTA_F_CAP);              // [2][RAMP_OPS_CAP]
     int2* doneq = ops_b_sm0 + 2 * RAMP_OPS_CAP;                                           // [w_cap] rows of ops completed this tick
-    int32_t* dst_sm0 = reinterpret_cast<int32_t*>(doneq + a.w_cap);                       // [2][F_CAP]
-    uint32_t* wkey = reinterpret_cast<uint32_t*>(dst_sm0 + 2 * RAMP_CTA_F_CAP);           // [w_cap]
-    uint32_t* ckey = wkey + a.w_cap;                                                      // [c_cap]
-    uint32_t* par_sm = ckey + a.c_cap;                                                    // [par_cap / 4] byte parent counters
+    uint32_t* wkey = reinterpret_cast<uint32_t*>(doneq + a.w_cap);                        // [w_cap]
+    uint32_t* ckey0 = wkey + a.w_cap;                                                     // [2][c_cap]
+    uint32_t* par_sm = ckey0 + 2 * a.c_cap;                                               // [par_cap / 4] byte parent counters
 
     __shared__ CtaCells cells[2];
-    __shared__ int s_n_ops[2];
-    __shared__ int s_ctail;
     __shared__ int s_work;
     __shared__ long long s_trace_off;
 
@@ -98,43 +102,44 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         const int4* __restrict__ t_op_rec = T.op_rec;
         const int2* __restrict__ t_op_row = T.op_row;
         const uint16_t* __restrict__ t_n_parents = T.op_n_parents;
-        const unsigned long long* __restrict__ t_dep_km = T.dep_km;
+        const unsigned long long* __restrict__ t_dep_kd = T.dep_kd;
         const double* __restrict__ t_dep_rt = T.dep_rt;
-        const int32_t* __restrict__ t_dep_dst = T.dep_dst;
         uint32_t* par_done = sv.par_done;
         const bool psm = T.par_in_smem != 0;
+        const uint32_t kmask = T.kd_kmask, cmask = T.kd_cmask;
+        const int csh = T.kd_cshift, fsh = T.kd_fshift, dsh = T.kd_dshift;
 
         FrontBuf F, Falt;
-        F.km_sm = km_sm0; F.rem_sm = rem_sm0; F.dst_sm = dst_sm0;
-        F.km_ovf = sv.f_km_ovf; F.rem_ovf = sv.f_rem_ovf; F.dst_ovf = sv.f_dst_ovf;
-        Falt.km_sm = km_sm0 + RAMP_CTA_F_CAP; Falt.rem_sm = rem_sm0 + RAMP_CTA_F_CAP; Falt.dst_sm = dst_sm0 + RAMP_CTA_F_CAP;
-        Falt.km_ovf = sv.f_km_ovf2; Falt.rem_ovf = sv.f_rem_ovf2; Falt.dst_ovf = sv.f_dst_ovf2;
+        F.kd_sm = kd_sm0; F.rem_sm = rem_sm0; F.kd_ovf = sv.f_km_ovf; F.rem_ovf = sv.f_rem_ovf;
+        Falt.kd_sm = kd_sm0 + RAMP_CTA_F_CAP; Falt.rem_sm = rem_sm0 + RAMP_CTA_F_CAP; Falt.kd_ovf = sv.f_km_ovf2; Falt.rem_ovf = sv.f_rem_ovf2;
         OpsView ops, ops_n;
         ops.a_sm = ops_a_sm0; ops.b_sm = ops_b_sm0; ops.a_ovf = sv.ops_a_ovf[0]; ops.b_ovf = sv.ops_b_ovf[0];
         ops_n.a_sm = ops_a_sm0 + RAMP_OPS_CAP; ops_n.b_sm = ops_b_sm0 + RAMP_OPS_CAP; ops_n.a_ovf = sv.ops_a_ovf[1]; ops_n.b_ovf = sv.ops_b_ovf[1];
+        uint32_t* ck_cur = ckey0;
+        uint32_t* ck_nxt = ckey0 + a.c_cap;
 
         // ---- init (JOB:432-484) ----
         if (psm) { for (int i = tid; i < (N + 3) / 4; i += NT) par_sm[i] = 0u; }
         else { for (int i = tid; i < N; i += NT) par_done[i] = 0u; }
         for (int i = tid; i < W; i += NT) wkey[i] = 0u;
-        for (int i = tid; i < C; i += NT) ckey[i] = 0u;
+        for (int i = tid; i < 2 * a.c_cap; i += NT) ckey0[i] = 0u;
         for (int k = tid; k < T.n_src; k += NT) {
             const int op = __ldg(&T.src_ops[k]);
             ops_put(ops, k, __ldg(&t_op_rec[op]), __ldg(&t_op_row[op]));          // RCE:1334
         }
         if (tid == 0) {
             for (int q = 0; q < 2; ++q) {
-                cells[q].n_ops_next = 0; cells[q].tail = 0; cells[q].ddone = 0; cells[q].nf_done = 0; cells[q].arr_nf = 0;
-                cells[q].ops_done = 0; cells[q].rescan = 0; cells[q].dq_n = 0; cells[q].n_active = 0;
+                cells[q].n_ops_next = 0; cells[q].ddone = 0; cells[q].nf_done = 0; cells[q].ops_done = 0; cells[q].dq_n = 0;
+                cells[q].n_active = 0; cells[q].arr = 0; cells[q].arr_nf = 0; cells[q].ctail = 0;
                 cells[q].min_op = RAMP_INF_BITS; cells[q].min_dep = RAMP_INF_BITS;
             }
-            s_ctail = 0;
         }
         __syncthreads();
 
         // CTA-uniform state (every thread holds the same values)
         int nO = T.n_src, nF = 0, live = 0, n_nonflow = 0, ops_completed = 0, deps_completed = 0;
         int tick_no = 0, status = RAMP_ST_OK, par = 0;
+        bool a_done = false;                         // phase A of this tick already ran during the previous tick's phase 3
         double t = 0.0, comm = 0.0, comp = 0.0;      // thread 0
 
         for (;;) {
@@ -142,14 +147,16 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             const bool big_ops = nO > 32 * NT;
 
             // ---- A ----
-            for (int k = tid; k < nO; k += NT) {
-                int4 ra; int2 rb;
-                ops_get(ops, k, ra, rb);
-                atomicMax(&wkey[ra.w], (uint32_t)ra.z);
+            if (!a_done) {
+                for (int k = tid; k < nO; k += NT) {
+                    int4 ra; int2 rb;
+                    ops_get(ops, k, ra, rb);
+                    atomicMax(&wkey[ra.w], (uint32_t)ra.z);
+                }
+                __syncthreads();
             }
-            __syncthreads();
 
-            // ---- B, C, D ----
+            // ---- phase 1: B, C, D ----
             const bool any_nf = n_nonflow > 0;
             uint32_t win_mask = 0u;
             {
@@ -166,8 +173,13 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                     }
                 }
                 if (!any_nf) {
-                    for (int c = tid; c < C; c += NT) {
-                        if (ckey[c] != 0u) { const double rem = crem[c]; md = (rem < md) ? rem : md; }
+                    for (int k = tid; k < nF; k += NT) {
+                        const unsigned long long kd = fb_kd(F, k);
+                        const uint32_t c = (uint32_t)(kd >> csh) & cmask;
+                        if (kd != 0ull && c != cmask && ck_cur[c] == ((uint32_t)kd & kmask)) {
+                            const double rem = fb_rem(F, k);
+                            md = (rem < md) ? rem : md;
+                        }
                     }
                 }
                 mo = warp_min_f64(mo);
@@ -189,7 +201,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             const double tick = (t_comm < t_op) ? t_comm : t_op;
             const int n_active = cc.n_active;
 
-            // ---- I, J (thread 0) + reset of the other parity's cells (last read one barrier ago) ----
+            // ---- phase 2.  I, J (thread 0) + reset of the other parity's cells (last read before this tick's first barrier) ----
             if (tid == 0) {
                 const bool ticked_ops = n_active > 0;
                 const bool ticked_flows = (!any_nf) && (live > 0);
@@ -200,42 +212,42 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                 if (tick_no < a.trace_cap) { sv.tr_n[tick_no] = n_active; sv.tr_tick[tick_no] = tick; }
                 else status = RAMP_ST_TRACE_OVERFLOW;
                 CtaCells& o = cells[par ^ 1];
-                o.ddone = 0; o.nf_done = 0; o.arr_nf = 0; o.ops_done = 0; o.rescan = 0; o.dq_n = 0; o.n_active = 0;
+                o.n_ops_next = 0; o.ddone = 0; o.nf_done = 0; o.ops_done = 0; o.dq_n = 0; o.n_active = 0;
+                o.arr = 0; o.arr_nf = 0; o.ctail = 0;
                 o.min_op = RAMP_INF_BITS; o.min_dep = RAMP_INF_BITS;
-                s_ctail = 0;
             }
             ++tick_no;
+            for (int c = tid; c < C; c += NT) ck_cur[c] = 0u;          // this table is the next tick's "next"
 
             // ---- H: deps of the pre-tick snapshot [0, nF): groups of 32 entries dealt round-robin to the warps (last warps
-            //      first; warp 0 also runs G).  In place: completed entries are marked dead, the rest only get a new rem ----
+            //      first; warp 0 also holds thread 0).  In place: completed entries are marked dead ----
             {
                 int ddone = 0, nf_done = 0;
-                bool rescan = false;
                 const int n_groups = (nF + 31) / 32;
                 for (int gi = NW - 1 - warp; gi < n_groups; gi += NW) {
                     const int k = gi * 32 + lane;
-                    unsigned long long km = 0ull;
-                    if (k < nF) km = fb_km(F, k);
-                    const bool is_flow = ((km >> 48) & 1ull) != 0ull;
-                    const bool ticked = (km != 0ull) && !(any_nf && is_flow);                        // RCE:434-439
+                    unsigned long long kd = 0ull;
+                    if (k < nF) kd = fb_kd(F, k);
+                    const bool is_flow = ((kd >> fsh) & 1ull) != 0ull;
+                    const bool alive = kd != 0ull;
+                    const bool ticked = alive && !(any_nf && is_flow);                               // RCE:434-439
                     double r2 = 1.0;
                     if (ticked) r2 = tick_down(fb_rem(F, k), tick);                                  // JOB:561
                     const bool done = ticked && (r2 == 0.0);                                         // JOB:562
-                    const uint32_t c = (uint32_t)(km >> 32) & 0xFFFFu;
-                    const bool winner = ticked && is_flow && c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)km;
-                    if (ticked && !done) { fb_set_rem(F, k, r2); if (winner) crem[c] = r2; }
+                    const uint32_t c = (uint32_t)(kd >> csh) & cmask;
+                    if (ticked && !done) fb_set_rem(F, k, r2);
+                    if (alive && !done && c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd & kmask);  // RCE:665-689 for the next tick
                     const unsigned dmask = __ballot_sync(FULL, done);
                     if (dmask != 0u) {                                                               // JOB:525-536
                         uint32_t cnt = 0u, np = 1u;
                         int child = 0;
                         if (done) {
-                            child = fb_dst(F, k);
-                            fb_set_km(F, k, 0ull);
+                            child = (int)(kd >> dsh);
+                            fb_set_kd(F, k, 0ull);
                             cnt = par_inc(psm, par_sm, par_done, child);                             // JOB:530
-                            np = psm ? (uint32_t)(km >> 49) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
+                            np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
                             ++ddone;
                             if (!is_flow) ++nf_done;
-                            if (winner) rescan = true;           // the channel's winner completed: recompute the slots
                         }
                         const bool readied = done && (cnt == np);                                     // JOB:531 (fires once)
                         const unsigned m = __ballot_sync(FULL, readied);
@@ -250,14 +262,12 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                 }
                 ddone = warp_sum_i32(ddone);
                 nf_done = warp_sum_i32(nf_done);
-                rescan = __any_sync(FULL, rescan);
                 if (lane == 0) {
                     if (ddone) atomicAdd(&cc.ddone, ddone);
                     if (nf_done) atomicAdd(&cc.nf_done, nf_done);
-                    if (rescan) cc.rescan = 1;
                 }
             }
-            // ---- G: tick the op winners (RCE:691-716); rows of completed ops are queued for the cooperative copy below ----
+            // ---- G part 1: tick the op winners (RCE:691-716); rows of completed ops are queued for the cooperative copy below ----
             {
                 int j = 0, done_local = 0;
                 for (int kb = 0; kb < nO; kb += NT, ++j) {
@@ -270,7 +280,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                         ops_get(ops, k, ra, rb);
                         bool win;
                         if (big_ops) win = wkey[ra.w] == (uint32_t)ra.z;
-                        else { win = ((win_mask >> j) & 1u) != 0u; wkey[ra.w] = 0u; }
+                        else { win = ((win_mask >> j) & 1u) != 0u; if (win) wkey[ra.w] = 0u; }   // release the winner slot
                         if (win) {
                             const double rem = tick_down(__hiloint2double(ra.y, ra.x), tick);   // JOB:555
                             if (rem == 0.0) done = true;                                        // JOB:556
@@ -300,11 +310,19 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             }
             __syncthreads();
 
-            // ---- G (cont.): JOB:496-506 out-edges of the completed ops become ready: each warp takes every NW-th queued row
-            //      and copies its rows as one flattened range (all template loads of a batch in flight together) ----
+            // ---- phase 3 ----
             const int nq = cc.dq_n;
+            const int ddone_all = cc.ddone;
+            const int nO_next = cc.n_ops_next;
+            const int live_after = live - ddone_all;
+            // compaction when more than half of the frontier is dead (order is irrelevant: arg-max is by key)
+            const bool compact = nF > 2 * live_after + NT;
+            const FrontBuf& Fdst = compact ? Falt : F;
+            const int base_off = compact ? live_after : nF;          // arrivals go behind the survivors
+
+            // G part 2: JOB:496-506 out-edges of the completed ops become ready: each warp takes every NW-th queued row and
+            // copies its rows as one flattened range (all template loads of a batch in flight together)
             if (nq > 0) {
-                if (big_ops) for (int i = tid; i < W; i += NT) wkey[i] = 0u;
                 int arr_nf = 0;
                 for (int qb = 0; qb < nq; qb += 32 * NW) {
                     const int q = qb + lane * NW + warp;
@@ -319,12 +337,11 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                     const int total = __shfl_sync(FULL, inc, 31);
                     const int exc = inc - row.y;
                     int base = 0;
-                    if (lane == 0 && total > 0) base = atomicAdd(&cc.tail, total);
-                    base = __shfl_sync(FULL, base, 0);
+                    if (lane == 0 && total > 0) base = atomicAdd(&cc.arr, total);
+                    base = base_off + __shfl_sync(FULL, base, 0);
                     for (int jb = 0; jb < total; jb += 32 * RAMP_U) {
-                        unsigned long long km[RAMP_U];
+                        unsigned long long kd[RAMP_U];
                         double rt[RAMP_U];
-                        int dst[RAMP_U];
 #pragma unroll
                         for (int u = 0; u < RAMP_U; ++u) {
                             const int jf = jb + u * 32 + lane;
@@ -338,98 +355,74 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                             const int o_start = __shfl_sync(FULL, row.x, lo);
                             const int o_exc = __shfl_sync(FULL, exc, lo);
                             const int e = o_start + (jc - o_exc);
-                            km[u] = 0ull; rt[u] = 0.0; dst[u] = 0;
+                            kd[u] = 0ull; rt[u] = 0.0;
                             if (jf < total) {
-                                km[u] = __ldg(&t_dep_km[e]);
+                                kd[u] = __ldg(&t_dep_kd[e]);
                                 rt[u] = __ldg(&t_dep_rt[e]);                                    // RCE:542-560
-                                dst[u] = __ldg(&t_dep_dst[e]);
                             }
                         }
 #pragma unroll
                         for (int u = 0; u < RAMP_U; ++u) {
                             const int jf = jb + u * 32 + lane;
                             if (jf < total) {
-                                fb_put(F, base + jf, km[u], rt[u], dst[u]);
-                                if (((km[u] >> 48) & 1ull) == 0ull) ++arr_nf;
-                                else {
-                                    const uint32_t c = (uint32_t)(km[u] >> 32) & 0xFFFFu;
-                                    if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)km[u]);
-                                }
+                                fb_put(Fdst, base + jf, kd[u], rt[u]);
+                                if (((kd[u] >> fsh) & 1ull) == 0ull) ++arr_nf;
+                                const uint32_t c = (uint32_t)(kd[u] >> csh) & cmask;
+                                if (c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd[u] & kmask);
                             }
                         }
                     }
                 }
                 arr_nf = warp_sum_i32(arr_nf);
                 if (lane == 0 && arr_nf) atomicAdd(&cc.arr_nf, arr_nf);
-                __syncthreads();
-            } else if (big_ops) {
-                for (int i = tid; i < W; i += NT) wkey[i] = 0u;
             }
-
-            // ---- K, L + frontier bookkeeping: every thread derives the same values from the shared cells ----
-            const int nF2 = cc.tail;                              // snapshot + this tick's arrivals
-            deps_completed += cc.ddone;
-            ops_completed += cc.ops_done;
-            live += (nF2 - nF) - cc.ddone;
-            n_nonflow += cc.arr_nf - cc.nf_done;
-            const bool rescan = cc.rescan != 0;
-            const int nO_next = cc.n_ops_next;
-            const bool finished = (ops_completed == N) && (deps_completed == E);     // JOB:549-551
-            if (!finished && isinf(tick) && tid == 0) status = RAMP_ST_INFINITE_TICK; // RCE:462
-            if (finished || isinf(tick)) break;
-
-            // channel winner slots
-            if (rescan) {
-                for (int c = tid; c < C; c += NT) ckey[c] = 0u;
-                __syncthreads();
-                for (int k = tid; k < nF2; k += NT) {
-                    const unsigned long long w = fb_km(F, k);
-                    if (w != 0ull && ((w >> 48) & 1ull) != 0ull) {
-                        const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
-                        if (c != RAMP_NO_CHANNEL) atomicMax(&ckey[c], (uint32_t)w);
-                    }
-                }
-                __syncthreads();
-            }
-            for (int k = (rescan ? 0 : nF) + tid; k < nF2; k += NT) {
-                const unsigned long long w = fb_km(F, k);
-                if (w != 0ull && ((w >> 48) & 1ull) != 0ull) {
-                    const uint32_t c = (uint32_t)(w >> 32) & 0xFFFFu;
-                    if (c != RAMP_NO_CHANNEL && ckey[c] == (uint32_t)w) crem[c] = fb_rem(F, k);
-                }
-            }
-            // compaction when more than half of the frontier is dead (order is irrelevant: arg-max is by key)
-            const bool compact = nF2 > 2 * live + NT;
             if (compact) {
-                for (int kb = 0; kb < nF2; kb += NT) {
+                for (int kb = 0; kb < nF; kb += NT) {
                     const int k = kb + tid;
                     unsigned long long w = 0ull;
-                    if (k < nF2) w = fb_km(F, k);
+                    if (k < nF) w = fb_kd(F, k);
                     const bool keep = w != 0ull;
                     const unsigned m = __ballot_sync(FULL, keep);
                     if (m) {
                         const int leader = __ffs(m) - 1;
                         int base = 0;
-                        if (lane == leader) base = atomicAdd(&s_ctail, __popc(m));
+                        if (lane == leader) base = atomicAdd(&cc.ctail, __popc(m));
                         base = __shfl_sync(FULL, base, leader);
-                        if (keep) fb_put(Falt, base + __popc(m & lt_mask), w, fb_rem(F, k), fb_dst(F, k));
+                        if (keep) fb_put(Falt, base + __popc(m & lt_mask), w, fb_rem(F, k));
                     }
                 }
-                { const FrontBuf tmp = F; F = Falt; Falt = tmp; }
-                nF = live;
-            } else {
-                nF = nF2;
             }
-            if (tid == 0) {
-                // only the OTHER parity's cells may be written here: slower threads may still be reading cc.* above
-                cells[par ^ 1].tail = nF;            // next tick's append cursor
-                cells[par ^ 1].n_ops_next = 0;
+            // phase A of the next tick: every winner slot was released in G part 1 (all of wkey is zero again)
+            const bool a_next = !big_ops && (nO_next <= 32 * NT);
+            if (a_next) {
+                for (int k = tid; k < nO_next; k += NT) {
+                    int4 ra; int2 rb;
+                    ops_get(ops_n, k, ra, rb);
+                    atomicMax(&wkey[ra.w], (uint32_t)ra.z);
+                }
+            } else if (big_ops) {
+                for (int i = tid; i < W; i += NT) wkey[i] = 0u;
             }
-            nO = nO_next;
-            { const OpsView tmp = ops; ops = ops_n; ops_n = tmp; }
-            par ^= 1;
             __syncthreads();
+
+            // ---- K, L + frontier bookkeeping: every thread derives the same values from the shared cells ----
+            const int arrived = cc.arr;
+            deps_completed += ddone_all;
+            ops_completed += cc.ops_done;
+            live = live_after + arrived;
+            n_nonflow += cc.arr_nf - cc.nf_done;
+            const bool finished = (ops_completed == N) && (deps_completed == E);     // JOB:549-551
+            if (!finished && isinf(tick) && tid == 0) status = RAMP_ST_INFINITE_TICK; // RCE:462
+            if (finished || isinf(tick)) break;
+            if (compact) { const FrontBuf tmp = F; F = Falt; Falt = tmp; }
+            nF = base_off + arrived;
+            nO = nO_next;
+            a_done = a_next;
+            { const OpsView tmp = ops; ops = ops_n; ops_n = tmp; }
+            { uint32_t* tmp = ck_cur; ck_cur = ck_nxt; ck_nxt = tmp; }
+            par ^= 1;
         }
+        __syncthreads();
 
         // ---- results (RCE:450-452) ----
         const int n_rec = tick_no < a.trace_cap ? tick_no : a.trace_cap;
