@@ -114,6 +114,9 @@ struct ramp_engine {
     int cta_grid = 0;            // resident CTAs of the 128-thread variant
     int cta64_grid = 0;          // resident CTAs of the 64-thread variant
     size_t cta_smem_bytes = 0;
+    int split_warp_nt = 32;      // threads per CTA of the warp kernel when it runs beside a CTA kernel
+    size_t smem2_bytes = 0;      // dynamic shared memory of the 2-warp CTAs used beside a CTA kernel
+    double split_alpha = 1.3;    // 64-thread-CTA split while 2 n_big + n_small <= split_alpha x resident warp slots
     int debug = 0;               // RAMP_DEBUG=1 prints the per-step launch decisions to stderr
     int mode = 0;                // 0 auto, 1 warp-per-lookahead, 2 CTA-per-lookahead (RAMP_LOOKAHEAD_MODE)
     int32_t* h_n_work = nullptr; // pinned [4]
@@ -187,6 +190,13 @@ int ensure_scratch(ramp_engine* e) {
         if (e->max_ctas_per_sm > 0 && occ > e->max_ctas_per_sm) occ = e->max_ctas_per_sm;
         e->grid = e->sm_count * occ;     // persistent CTAs: a whole number of waves (148 SMs x resident CTAs per SM)
         e->smem_bytes = smem;
+        // beside a CTA kernel the small lookaheads run in 2-warp CTAs: they fill the registers and shared memory the CTA
+        // kernel leaves on every SM at a finer grain (the block scheduler spreads both kernels over all SMs)
+        const size_t smem2 = lookahead_smem_per_warp(e->max_w, e->max_c, e->par_cap) * (size_t)(e->split_warp_nt / 32);
+        LookaheadKernel kern2 = lookahead_kernel_for(e->split_warp_nt);
+        CUDA_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        CUDA_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributePreferredSharedMemoryCarveout, RAMP_SMEM_CARVEOUT));
+        e->smem2_bytes = smem2;
     }
     const size_t cta_smem = lookahead_cta_smem(e->max_w, e->max_c, e->par_cap);
     if (cta_smem > 200 * 1024)
@@ -203,8 +213,8 @@ int ensure_scratch(ramp_engine* e) {
         }
         e->cta_smem_bytes = cta_smem;
     }
-    // one slab per lookahead in flight; the warp kernel and the 128-thread CTA kernel may run side by side
-    const int n_slabs = std::max(e->grid * (e->nt / 32) + e->cta_grid, e->cta64_grid);
+    // one slab per lookahead in flight; the warp kernel and one of the CTA kernels may run side by side
+    const int n_slabs = e->grid * (e->nt / 32) + std::max(e->cta_grid, e->cta64_grid);
     if (stride != e->scratch_stride || n_slabs != e->scratch_grid || e->d_scratch == nullptr) {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (e->d_scratch) cudaFree(e->d_scratch);
@@ -313,6 +323,12 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     if (const char* v = getenv("RAMP_LOOKAHEAD_MODE")) e->mode = !strcmp(v, "warp") ? 1 : !strcmp(v, "cta") ? 2 : 0;
     if (const char* v = getenv("RAMP_BIG_THRESHOLD")) e->big_threshold = atoll(v);
     if (const char* v = getenv("RAMP_DEBUG")) e->debug = atoi(v);
+    if (const char* v = getenv("RAMP_SPLIT_ALPHA")) e->split_alpha = atof(v);
+    if (const char* v = getenv("RAMP_SPLIT_WARP_THREADS")) {
+        const int nt = atoi(v);
+        if (lookahead_kernel_for(nt) == nullptr) { delete e; return set_error(RAMP_ERR_BAD_ARG, "RAMP_SPLIT_WARP_THREADS must be 32, 64, 128 or 256"); }
+        e->split_warp_nt = nt;
+    }
     cudaDeviceProp prop{};
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg.device));
     e->sm_count = prop.multiProcessorCount;
@@ -591,24 +607,34 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
             CUDA_TRY(cudaEventRecord(e->ev_a[e->ev_pending], st));
             const int wpb = e->nt / 32;
             const int warp_slots = e->grid * wpb;
-            // Latency regime (fewer lookaheads than warp slots): the big ones get one 128-thread CTA each on a second stream
-            // and overlap the small ones (one warp each).  Throughput regime: everything through the warp kernel, the big
-            // list first (longest-processing-time-first keeps the tail short).
-            const bool split = e->mode != 1 && n_big > 0 && n_big <= e->cta_grid && (n_small + n_big) <= warp_slots;
-            if (e->debug) fprintf(stderr, "[ramp] step lookaheads: small=%d big=%d warp_slots=%d cta_grid=%d -> %s\n", n_small, n_big,
-                                  warp_slots, e->cta_grid, split ? "split (CTA128 || warp)" : "single warp kernel, big first");
+            // The big lookaheads set the step's latency, the small ones its load.  While everything fits the SMs' warp slots
+            // at once (registers cap every mix at cta_grid x 4 warps) each big lookahead gets a 128-thread CTA; while the big
+            // ones still fit as 64-thread CTAs and the small ones need at most a short second wave they get those; beyond
+            // that everything goes through the warp kernel, the big list first (longest-processing-time-first keeps the
+            // tail short).  The CTA kernel runs on a second stream beside the warp kernel for the small list.
+            const int reg_slots = e->cta_grid * 4;
+            int split_nt = 0;
+            if (e->mode != 1 && n_big > 0) {
+                if (n_big <= e->cta_grid && 4 * n_big + n_small <= reg_slots) split_nt = 128;
+                else if (n_big <= e->cta64_grid && 2 * n_big + n_small <= (int)(e->split_alpha * reg_slots)) split_nt = 64;
+            }
+            const bool split = split_nt != 0;
+            if (e->debug) fprintf(stderr, "[ramp] step lookaheads: small=%d big=%d warp_slots=%d reg_slots=%d -> %s %d\n", n_small, n_big,
+                                  warp_slots, reg_slots, split ? "split (CTA || warp), CTA threads" : "single warp kernel, big first", split_nt);
             if (split) {
-                const int grid = n_big;
-                CUDA_TRY(cudaEventRecord(e->ev_fork, st));
-                CUDA_TRY(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
-                lookahead_cta_kernel_for(128)<<<grid, 128, e->cta_smem_bytes, e->stream2>>>(ab);
+                const int cgrid = split_nt == 128 ? e->cta_grid : e->cta64_grid;
+                const int grid = std::min(n_big, cgrid);
+                // `st` is idle here (synchronised for the read-back above), so the second stream needs no fork event and the
+                // CTA kernel's blocks are always placed before the warp kernel's
+                lookahead_cta_kernel_for(split_nt)<<<grid, split_nt, e->cta_smem_bytes, e->stream2>>>(ab);
                 CUDA_TRY(cudaEventRecord(e->ev_join, e->stream2));
                 e->launches++;
                 if (n_small > 0) {
                     LookaheadArgs as = a;
-                    as.scratch = a.scratch + (uint64_t)e->cta_grid * a.scratch_stride;     // slabs past the CTA kernel's
-                    const int g2 = std::max(1, std::min(e->grid, (n_small + wpb - 1) / wpb));
-                    lookahead_kernel_for(e->nt)<<<g2, e->nt, e->smem_bytes, st>>>(as);
+                    as.scratch = a.scratch + (uint64_t)std::max(e->cta_grid, e->cta64_grid) * a.scratch_stride;   // slabs past the CTA kernel's
+                    const int wpb2 = e->split_warp_nt / 32;
+                    const int g2 = std::max(1, std::min(e->grid * wpb / wpb2, (n_small + wpb2 - 1) / wpb2));   // never more warps than slabs
+                    lookahead_kernel_for(e->split_warp_nt)<<<g2, e->split_warp_nt, e->smem2_bytes, st>>>(as);
                     e->launches++;
                 }
                 CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));

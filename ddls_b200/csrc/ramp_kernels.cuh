@@ -149,12 +149,10 @@ struct ScratchView {
     uint32_t* par_done;              // [N] len(parent_deps_completed) JOB:530
     int4*     ops_a_ovf[2];          // [N] overflow of the shared-memory op frontier (ping-pong)
     int2*     ops_b_ovf[2];          // [N]
-    unsigned long long* f_km_ovf;    // [E] overflow of the shared-memory dep frontier
-    double*   f_rem_ovf;             // [E]
-    int32_t*  f_dst_ovf;             // [E]
+    unsigned long long* f_km_ovf;    // [E] overflow of the shared-memory dep frontier: packed dep words
+    double*   f_rem_ovf;             // [E]                                              remaining times
     unsigned long long* f_km_ovf2;   // [E] second buffer (CTA-per-lookahead kernel compacts by ping-pong)
     double*   f_rem_ovf2;            // [E]
-    int32_t*  f_dst_ovf2;            // [E]
     int32_t*  tr_n;                  // [trace_cap] temp trace
     double*   tr_tick;               // [trace_cap]
 };
@@ -165,7 +163,6 @@ __host__ __device__ inline uint64_t scratch_bytes_for(int32_t N, int32_t E) {
     b += 2 * align_up((uint64_t)N * 16, 16);
     b += 2 * align_up((uint64_t)N * 8, 16);
     b += 4 * align_up((uint64_t)E * 8, 16);
-    b += 2 * align_up((uint64_t)E * 4, 16);
     return b;
 }
 
@@ -179,10 +176,8 @@ __device__ inline ScratchView carve(unsigned char* base, int32_t N, int32_t E, u
     v.ops_b_ovf[1] = (int2*)(base + o);              o += align_up((uint64_t)N * 8, 16);
     v.f_km_ovf = (unsigned long long*)(base + o);    o += align_up((uint64_t)E * 8, 16);
     v.f_rem_ovf = (double*)(base + o);               o += align_up((uint64_t)E * 8, 16);
-    v.f_dst_ovf = (int32_t*)(base + o);              o += align_up((uint64_t)E * 4, 16);
     v.f_km_ovf2 = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
     v.f_rem_ovf2 = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
-    v.f_dst_ovf2 = (int32_t*)(base + o);             o += align_up((uint64_t)E * 4, 16);
     v.tr_tick = (double*)(base + trace_region_off);
     v.tr_n = (int32_t*)(v.tr_tick + trace_cap);
     return v;
