@@ -437,6 +437,10 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
         if (j->dep_channel[k] != RAMP_NO_CHANNEL && j->dep_channel[k] >= C)
             return set_error(RAMP_ERR_BAD_ARG, "dep %d on channel %d >= n_channels %d", k, j->dep_channel[k], C);
         if (!(j->dep_run_time[k] >= 0.0)) return set_error(RAMP_ERR_BAD_ARG, "dep %d has a negative or NaN run time", k);
+        // RCE:542-560 zeroes the run time of every non-flow dep when the job is mounted; with a non-zero one the reference's
+        // zero-length ticks (RCE:412-422) would never complete it and _run_lookahead would spin forever
+        if (!j->dep_is_flow[k] && j->dep_run_time[k] != 0.0)
+            return set_error(RAMP_ERR_BAD_ARG, "non-flow dep %d has a non-zero run time (RCE:542-560 zeroes it)", k);
         in_deg[j->dep_dst[k]]++;
     }
     // ---- derive ----

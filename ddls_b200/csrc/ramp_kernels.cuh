@@ -153,6 +153,7 @@ struct ScratchView {
     double*   f_rem_ovf;             // [E]                                              remaining times
     unsigned long long* f_km_ovf2;   // [E] second buffer (CTA-per-lookahead kernel compacts by ping-pong)
     double*   f_rem_ovf2;            // [E]
+    unsigned long long* nf_ovf;      // [E] overflow of the shared-memory list of ready non-flow deps
     int32_t*  tr_n;                  // [trace_cap] temp trace
     double*   tr_tick;               // [trace_cap]
 };
@@ -162,7 +163,7 @@ __host__ __device__ inline uint64_t scratch_bytes_for(int32_t N, int32_t E) {
     b += align_up((uint64_t)N * 4, 16);
     b += 2 * align_up((uint64_t)N * 16, 16);
     b += 2 * align_up((uint64_t)N * 8, 16);
-    b += 4 * align_up((uint64_t)E * 8, 16);
+    b += 5 * align_up((uint64_t)E * 8, 16);
     return b;
 }
 
@@ -178,6 +179,7 @@ __device__ inline ScratchView carve(unsigned char* base, int32_t N, int32_t E, u
     v.f_rem_ovf = (double*)(base + o);               o += align_up((uint64_t)E * 8, 16);
     v.f_km_ovf2 = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
     v.f_rem_ovf2 = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
+    v.nf_ovf = (unsigned long long*)(base + o);      o += align_up((uint64_t)E * 8, 16);
     v.tr_tick = (double*)(base + trace_region_off);
     v.tr_n = (int32_t*)(v.tr_tick + trace_cap);
     return v;
@@ -272,6 +274,10 @@ __device__ __forceinline__ double util_sum(const double* term, int n_rec) {
 #define RAMP_F_CAP 384      // dep-frontier records kept in shared memory (overflow goes to HBM); sized so that 12 lookahead warps fit an SM
 #endif
 
+#ifndef RAMP_NF_CAP
+#define RAMP_NF_CAP 64      // ready non-flow deps kept in shared memory (they live for exactly one tick)
+#endif
+
 struct OpsView { int4* a_sm; int2* b_sm; int4* a_ovf; int2* b_ovf; };
 __device__ __forceinline__ void ops_get(const OpsView& v, int k, int4& ra, int2& rb) {
     if (k < RAMP_OPS_CAP) { ra = v.a_sm[k]; rb = v.b_sm[k]; } else { ra = v.a_ovf[k - RAMP_OPS_CAP]; rb = v.b_ovf[k - RAMP_OPS_CAP]; }
@@ -304,6 +310,7 @@ __host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap, 
     size_t b = 0;
     b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
     b += (size_t)RAMP_F_CAP * 8 * 2;             // kd, rem
+    b += (size_t)RAMP_NF_CAP * 8;                // ready non-flow deps
     b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
     b += (size_t)(w_cap + 2 * c_cap) * 4;        // wkey, ckey (this tick / next tick)
     b += (size_t)par_cap;                        // parent counters (bytes)
@@ -323,7 +330,8 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
     FrontView fr;
     fr.kd_sm = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);      // [RAMP_F_CAP]
     fr.rem_sm = reinterpret_cast<double*>(fr.kd_sm + RAMP_F_CAP);                        // [RAMP_F_CAP]
-    int2* ops_b_sm0 = reinterpret_cast<int2*>(fr.rem_sm + RAMP_F_CAP);                   // [2][RAMP_OPS_CAP]
+    unsigned long long* nf_sm = reinterpret_cast<unsigned long long*>(fr.rem_sm + RAMP_F_CAP);   // [RAMP_NF_CAP]
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(nf_sm + RAMP_NF_CAP);                      // [2][RAMP_OPS_CAP]
     uint32_t* wkey = reinterpret_cast<uint32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);          // [w_cap] best key among the ready ops on the worker
     uint32_t* ckey0 = wkey + a.w_cap;                                                    // [2][c_cap] best key among the ready flows on the channel
     uint32_t* par_sm = ckey0 + 2 * a.c_cap;                                              // [par_cap / 4] byte parent counters
@@ -344,6 +352,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
         const int N = T.n_ops, E = T.n_deps, W = T.n_workers, C = T.n_channels;
         const ScratchView sv = carve(slab, N, E, trace_region, a.trace_cap);
         fr.kd_ovf = sv.f_km_ovf; fr.rem_ovf = sv.f_rem_ovf;
+        unsigned long long* nf_ovf = sv.nf_ovf;
 
         const int4* __restrict__ t_op_rec = T.op_rec;
         const int2* __restrict__ t_op_row = T.op_row;
@@ -373,8 +382,8 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
 
         // warp-uniform state
         int nO = T.n_src;          // ready ops
-        int nF = 0;                // ready deps (the frontier holds no dead entries)
-        int n_nonflow = 0;         // ready non-flow deps
+        int nF = 0;                // ready flows (the frontier holds no dead entries)
+        int nNF = 0;               // ready non-flow deps: zero run time (RCE:542-560), so each lives for exactly one tick
         int ops_completed = 0, deps_completed = 0;
         int tick_no = 0;
         int status = RAMP_ST_OK;
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
 
             // ---- C, D: ck_cur[c] holds the arg-max key over the ready flows on channel c (built while the previous tick
             //      compacted its survivors and appended its arrivals), so the winners are the entries that match it ----
-            const bool any_nf = n_nonflow > 0;
+            const bool any_nf = nNF > 0;
             double t_comm = 0.0;
             if (!any_nf) {
                 double md = INF;
@@ -426,14 +435,16 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                 t_comm = warp_min_f64(md);
             }
             __syncwarp();
-            for (int c = lane; c < C; c += 32) ck_cur[c] = 0u;        // this table is the next tick's "next"
+            // a tick that freezes the flows (any_nf) leaves the winners table as it is: its arrivals vote into ck_cur
+            if (!any_nf) { for (int c = lane; c < C; c += 32) ck_cur[c] = 0u; }   // else: this table is the next tick's "next"
+            uint32_t* ck_vote = any_nf ? ck_cur : ck_nxt;
             // ---- E ----
             const double tick = (t_comm < t_op) ? t_comm : t_op;
 
             // ---- I, J ----
             if (lane == 0) {
                 const bool ticked_ops = n_active > 0;
-                const bool ticked_flows = (!any_nf) && (nF > 0);
+                const bool ticked_flows = (!any_nf) && (nF > 0);                 // RCE:434-439
                 if (ticked_ops && ticked_flows) { comm = __dadd_rn(comm, tick); comp = __dadd_rn(comp, tick); }
                 else if (ticked_flows) comm = __dadd_rn(comm, tick);
                 else if (ticked_ops) comp = __dadd_rn(comp, tick);
@@ -443,63 +454,81 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             }
             ++tick_no;
 
-            // ---- H: the deps of the pre-tick snapshot [0, nF); survivors slide down to [0, p) and vote for the next tick's
-            //      channel winners.  32 entries per iteration ----
+            // ---- H: the deps of the pre-tick snapshot.  A tick with ready non-flow deps is a zero-length tick that completes
+            //      exactly those (RCE:412-422, 718-731) and leaves the flows untouched; any other tick ticks every flow
+            //      [0, nF): survivors slide down to [0, p) and vote for the next tick's channel winners.  32 per iteration ----
             int nO_next = 0;
             int p = 0;
-            int ddone = 0, nf_done = 0;
-            for (int kb = 0; kb < nF; kb += 32) {
-                const int k = kb + lane;
-                const int n_here = (nF - kb < 32) ? (nF - kb) : 32;
-                const bool valid = lane < n_here;
-                unsigned long long kd = 0ull;
-                double rem = 1.0;
-                if (valid) f_get(fr, k, kd, rem);
-                const bool is_flow = ((kd >> fsh) & 1ull) != 0ull;
-                const bool ticked = valid && !(any_nf && is_flow);                               // RCE:434-439
-                const double r2 = ticked ? tick_down(rem, tick) : rem;                          // JOB:561
-                const bool done = ticked && (r2 == 0.0);                                        // JOB:562
-                const bool keep = valid && !done;
-                const uint32_t c = (uint32_t)(kd >> csh) & cmask;
-                if (keep && c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd & kmask);            // RCE:665-689 for the next tick
-                const unsigned dmask = __ballot_sync(FULL, done);
-                if (dmask == 0u) {
-                    if (p == kb) {                                 // nothing before it died either: update in place
-                        if (ticked) { if (k < RAMP_F_CAP) fr.rem_sm[k] = r2; else fr.rem_ovf[k - RAMP_F_CAP] = r2; }
-                    } else {
-                        __syncwarp();                              // all lanes have read before anything is written over
-                        if (valid) f_put(fr, p + lane, kd, r2);
-                    }
-                    p += n_here;                                   // warp-uniform: every valid entry of the group survives
-                } else {
-                    // JOB:525-536 for the completing lanes
+            if (any_nf) {
+                for (int kb = 0; kb < nNF; kb += 32) {
+                    const int k = kb + lane;
+                    const bool valid = k < nNF;
                     uint32_t cnt = 0u, np = 1u;
                     int child = 0;
-                    if (done) {
+                    if (valid) {                                                                // JOB:525-536
+                        const unsigned long long kd = (k < RAMP_NF_CAP) ? nf_sm[k] : nf_ovf[k - RAMP_NF_CAP];
                         child = (int)(kd >> dsh);
                         cnt = par_inc(psm, par_sm, par_done, child);                            // JOB:530
                         np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
-                        ++ddone;
-                        if (!is_flow) ++nf_done;
                     }
-                    const unsigned vm = (n_here == 32) ? FULL : ((1u << n_here) - 1u);
-                    const unsigned mk = vm & ~dmask;
-                    __syncwarp();
-                    if (keep) f_put(fr, p + __popc(mk & lt_mask), kd, r2);
-                    p += __popc(mk);
-                    const bool readied = done && (cnt == np);                                    // JOB:531 (fires once)
+                    const bool readied = valid && (cnt == np);                                   // JOB:531 (fires once)
                     const unsigned m = __ballot_sync(FULL, readied);
                     if (readied) ops_put(ops_n, nO_next + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
                     nO_next += __popc(m);
                 }
+                deps_completed += nNF;
+                p = nF;
+                __syncwarp();
+            } else {
+                int ddone = 0;
+                for (int kb = 0; kb < nF; kb += 32) {
+                    const int k = kb + lane;
+                    const int n_here = (nF - kb < 32) ? (nF - kb) : 32;
+                    const bool valid = lane < n_here;
+                    unsigned long long kd = 0ull;
+                    double rem = 1.0;
+                    if (valid) f_get(fr, k, kd, rem);
+                    const double r2 = tick_down(rem, tick);                                         // JOB:561
+                    const bool done = valid && (r2 == 0.0);                                         // JOB:562
+                    const bool keep = valid && !done;
+                    const uint32_t c = (uint32_t)(kd >> csh) & cmask;
+                    if (keep && c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd & kmask);            // RCE:665-689 for the next tick
+                    const unsigned dmask = __ballot_sync(FULL, done);
+                    if (dmask == 0u) {
+                        if (p == kb) {                                 // nothing before it died either: update in place
+                            if (valid) { if (k < RAMP_F_CAP) fr.rem_sm[k] = r2; else fr.rem_ovf[k - RAMP_F_CAP] = r2; }
+                        } else {
+                            __syncwarp();                              // all lanes have read before anything is written over
+                            if (valid) f_put(fr, p + lane, kd, r2);
+                        }
+                        p += n_here;                                   // warp-uniform: every valid entry of the group survives
+                    } else {
+                        // JOB:525-536 for the completing lanes
+                        uint32_t cnt = 0u, np = 1u;
+                        int child = 0;
+                        if (done) {
+                            child = (int)(kd >> dsh);
+                            cnt = par_inc(psm, par_sm, par_done, child);                            // JOB:530
+                            np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
+                        }
+                        ddone += __popc(dmask);
+                        const unsigned vm = (n_here == 32) ? FULL : ((1u << n_here) - 1u);
+                        const unsigned mk = vm & ~dmask;
+                        __syncwarp();
+                        if (keep) f_put(fr, p + __popc(mk & lt_mask), kd, r2);
+                        p += __popc(mk);
+                        const bool readied = done && (cnt == np);                                    // JOB:531 (fires once)
+                        const unsigned m = __ballot_sync(FULL, readied);
+                        if (readied) ops_put(ops_n, nO_next + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
+                        nO_next += __popc(m);
+                    }
+                }
+                deps_completed += ddone;
             }
-            ddone = warp_sum_i32(ddone);
-            nf_done = warp_sum_i32(nf_done);
-            deps_completed += ddone;
 
             // ---- G: tick the op winners; rows of the completed ops are appended at [p, tail) ----
             int tail = p;
-            int arr_nonflow = 0;                // lane-local count of arriving non-flow deps
+            int nNF_next = 0;                   // this tick's non-flow arrivals (the previous ones were all consumed above)
             {
                 int j = 0;
                 for (int kb = 0; kb < nO; kb += 32, ++j) {
@@ -542,6 +571,8 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                             double rt[RAMP_U];
 #pragma unroll
                             for (int u = 0; u < RAMP_U; ++u) {
+                                kd[u] = 0ull; rt[u] = 0.0;
+                                if (jb + u * 32 >= total) continue;          // warp-uniform: nothing left for this slice
                                 const int jf = jb + u * 32 + lane;
                                 const int jc = jf < total ? jf : total - 1;
                                 int lo = 0;                 // owner = first lane whose inclusive prefix exceeds jc
@@ -553,7 +584,6 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                                 const int o_start = __shfl_sync(FULL, rb.x, lo);
                                 const int o_exc = __shfl_sync(FULL, exc, lo);
                                 const int e = o_start + (jc - o_exc);
-                                kd[u] = 0ull; rt[u] = 0.0;
                                 if (jf < total) {
                                     kd[u] = __ldg(&t_dep_kd[e]);
                                     rt[u] = __ldg(&t_dep_rt[e]);                                // RCE:542-560
@@ -561,22 +591,29 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                             }
 #pragma unroll
                             for (int u = 0; u < RAMP_U; ++u) {
+                                if (jb + u * 32 >= total) continue;      // warp-uniform
                                 const int jf = jb + u * 32 + lane;
-                                if (jf < total) {
-                                    f_put(fr, tail + jf, kd[u], rt[u]);
-                                    if (((kd[u] >> fsh) & 1ull) == 0ull) ++arr_nonflow;
+                                const bool valid = jf < total;
+                                const bool flow = valid && (((kd[u] >> fsh) & 1ull) != 0ull);
+                                const unsigned fm = __ballot_sync(FULL, flow);
+                                const unsigned nm = __ballot_sync(FULL, valid && !flow);
+                                if (flow) {
+                                    f_put(fr, tail + __popc(fm & lt_mask), kd[u], rt[u]);
                                     const uint32_t c = (uint32_t)(kd[u] >> csh) & cmask;
-                                    if (c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd[u] & kmask);
+                                    if (c != cmask) atomicMax(&ck_vote[c], (uint32_t)kd[u] & kmask);
+                                } else if (valid) {
+                                    const int q = nNF_next + __popc(nm & lt_mask);
+                                    if (q < RAMP_NF_CAP) nf_sm[q] = kd[u]; else nf_ovf[q - RAMP_NF_CAP] = kd[u];
                                 }
+                                tail += __popc(fm);
+                                nNF_next += __popc(nm);
                             }
                         }
-                        tail += total;
                     }
                 }
             }
             if (big_ops) { __syncwarp(); for (int i = lane; i < W; i += 32) wkey[i] = 0u; }
-            arr_nonflow = warp_sum_i32(arr_nonflow);
-            n_nonflow += arr_nonflow - nf_done;
+            nNF = nNF_next;
             __syncwarp();
 
             // ---- K, L ----
@@ -586,7 +623,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             nF = tail;
             nO = nO_next;
             { const OpsView tmp = ops; ops = ops_n; ops_n = tmp; }
-            { uint32_t* tmp = ck_cur; ck_cur = ck_nxt; ck_nxt = tmp; }
+            if (!any_nf) { uint32_t* tmp = ck_cur; ck_cur = ck_nxt; ck_nxt = tmp; }
         }
 
         // ---- results (RCE:450-452): copy the trace to an exactly-sized pool allocation ----

@@ -22,9 +22,9 @@ namespace ramp {
 
 struct CtaCells {              // written during the tick with parity p, read after that tick's barriers, reset one tick later
     int n_ops_next;            // op frontier being built for the next tick                 (phase 2)
-    int ddone, nf_done, ops_done, dq_n;                                                  // (phase 2)
+    int ddone, ops_done, dq_n;                                                           // (phase 2)
     int n_active;                                                                        // (phase 1)
-    int arr, arr_nf, ctail;    // arrival cursor, arriving non-flows, compaction cursor     (phase 3)
+    int arr, arr_nf, ctail;    // flow / non-flow arrival cursors, compaction cursor        (phase 3)
     unsigned long long min_op, min_dep;                                                  // (phase 1)
 };
 
@@ -32,6 +32,7 @@ __host__ __device__ inline size_t lookahead_cta_smem(int w_cap, int c_cap, int p
     size_t b = 0;
     b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
     b += (size_t)2 * RAMP_CTA_F_CAP * 8 * 2;     // kd, rem (two buffers)
+    b += (size_t)RAMP_NF_CAP * 8;                // ready non-flow deps
     b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
     b += (size_t)w_cap * 8;                      // done queue: {row start, degree}
     b += (size_t)(w_cap + 2 * c_cap) * 4;        // wkey, ckey (this tick / next tick)
@@ -73,7 +74,8 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
     int4* ops_a_sm0 = reinterpret_cast<int4*>(smem_raw);                                  // [2][RAMP_OPS_CAP]
     unsigned long long* kd_sm0 = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);   // [2][F_CAP]
     double* rem_sm0 = reinterpret_cast<double*>(kd_sm0 + 2 * RAMP_CTA_F_CAP);            // [2][F_CAP]
-    int2* ops_b_sm0 = reinterpret_cast<int2*>(rem_sm0 + 2 * RAMP_CTA_F_CAP);              // [2][RAMP_OPS_CAP]
+    unsigned long long* nf_sm = reinterpret_cast<unsigned long long*>(rem_sm0 + 2 * RAMP_CTA_F_CAP);   // [RAMP_NF_CAP]
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(nf_sm + RAMP_NF_CAP);                       // [2][RAMP_OPS_CAP]
     int2* doneq = ops_b_sm0 + 2 * RAMP_OPS_CAP;                                           // [w_cap] rows of ops completed this tick
     uint32_t* wkey = reinterpret_cast<uint32_t*>(doneq + a.w_cap);                        // [w_cap]
     uint32_t* ckey0 = wkey + a.w_cap;                                                     // [2][c_cap]
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         const unsigned long long* __restrict__ t_dep_kd = T.dep_kd;
         const double* __restrict__ t_dep_rt = T.dep_rt;
         uint32_t* par_done = sv.par_done;
+        unsigned long long* nf_ovf = sv.nf_ovf;
         const bool psm = T.par_in_smem != 0;
         const uint32_t kmask = T.kd_kmask, cmask = T.kd_cmask;
         const int csh = T.kd_cshift, fsh = T.kd_fshift, dsh = T.kd_dshift;
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         }
         if (tid == 0) {
             for (int q = 0; q < 2; ++q) {
-                cells[q].n_ops_next = 0; cells[q].ddone = 0; cells[q].nf_done = 0; cells[q].ops_done = 0; cells[q].dq_n = 0;
+                cells[q].n_ops_next = 0; cells[q].ddone = 0; cells[q].ops_done = 0; cells[q].dq_n = 0;
                 cells[q].n_active = 0; cells[q].arr = 0; cells[q].arr_nf = 0; cells[q].ctail = 0;
                 cells[q].min_op = RAMP_INF_BITS; cells[q].min_dep = RAMP_INF_BITS;
             }
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         __syncthreads();
 
         // CTA-uniform state (every thread holds the same values)
-        int nO = T.n_src, nF = 0, live = 0, n_nonflow = 0, ops_completed = 0, deps_completed = 0;
+        int nO = T.n_src, nF = 0, live = 0, nNF = 0, ops_completed = 0, deps_completed = 0;   // nNF: ready non-flow deps (one-tick lives)
         int tick_no = 0, status = RAMP_ST_OK, par = 0;
         bool a_done = false;                         // phase A of this tick already ran during the previous tick's phase 3
         double t = 0.0, comm = 0.0, comp = 0.0;      // thread 0
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             }
 
             // ---- phase 1: B, C, D ----
-            const bool any_nf = n_nonflow > 0;
+            const bool any_nf = nNF > 0;
             uint32_t win_mask = 0u;
             {
                 double mo = INF, md = INF;
@@ -212,31 +215,58 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                 if (tick_no < a.trace_cap) { sv.tr_n[tick_no] = n_active; sv.tr_tick[tick_no] = tick; }
                 else status = RAMP_ST_TRACE_OVERFLOW;
                 CtaCells& o = cells[par ^ 1];
-                o.n_ops_next = 0; o.ddone = 0; o.nf_done = 0; o.ops_done = 0; o.dq_n = 0; o.n_active = 0;
+                o.n_ops_next = 0; o.ddone = 0; o.ops_done = 0; o.dq_n = 0; o.n_active = 0;
                 o.arr = 0; o.arr_nf = 0; o.ctail = 0;
                 o.min_op = RAMP_INF_BITS; o.min_dep = RAMP_INF_BITS;
             }
             ++tick_no;
-            for (int c = tid; c < C; c += NT) ck_cur[c] = 0u;          // this table is the next tick's "next"
+            // a tick that freezes the flows (any_nf) leaves the winners table as it is: its arrivals vote into ck_cur
+            if (!any_nf) { for (int c = tid; c < C; c += NT) ck_cur[c] = 0u; }   // else: this table is the next tick's "next"
+            uint32_t* ck_vote = any_nf ? ck_cur : ck_nxt;
 
-            // ---- H: deps of the pre-tick snapshot [0, nF): groups of 32 entries dealt round-robin to the warps (last warps
-            //      first; warp 0 also holds thread 0).  In place: completed entries are marked dead ----
-            {
-                int ddone = 0, nf_done = 0;
+            // ---- H.  A tick with ready non-flow deps is a zero-length tick that completes exactly those (RCE:412-422, 718-731)
+            //      and leaves the flows untouched.  Any other tick ticks every flow of the pre-tick snapshot [0, nF): groups of
+            //      32 entries dealt round-robin to the warps (last warps first; warp 0 also holds thread 0), in place:
+            //      completed entries are marked dead ----
+            if (any_nf) {
+                const int n_groups = (nNF + 31) / 32;
+                for (int gi = NW - 1 - warp; gi < n_groups; gi += NW) {
+                    const int k = gi * 32 + lane;
+                    const bool valid = k < nNF;
+                    uint32_t cnt = 0u, np = 1u;
+                    int child = 0;
+                    if (valid) {                                                                     // JOB:525-536
+                        const unsigned long long kd = (k < RAMP_NF_CAP) ? nf_sm[k] : nf_ovf[k - RAMP_NF_CAP];
+                        child = (int)(kd >> dsh);
+                        cnt = par_inc(psm, par_sm, par_done, child);                                 // JOB:530
+                        np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
+                    }
+                    const bool readied = valid && (cnt == np);                                        // JOB:531 (fires once)
+                    const unsigned m = __ballot_sync(FULL, readied);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(&cc.n_ops_next, __popc(m));
+                        base = __shfl_sync(FULL, base, leader);
+                        if (readied) ops_put(ops_n, base + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
+                    }
+                }
+            } else {
+                int ddone = 0;
                 const int n_groups = (nF + 31) / 32;
                 for (int gi = NW - 1 - warp; gi < n_groups; gi += NW) {
                     const int k = gi * 32 + lane;
                     unsigned long long kd = 0ull;
                     if (k < nF) kd = fb_kd(F, k);
-                    const bool is_flow = ((kd >> fsh) & 1ull) != 0ull;
                     const bool alive = kd != 0ull;
-                    const bool ticked = alive && !(any_nf && is_flow);                               // RCE:434-439
                     double r2 = 1.0;
-                    if (ticked) r2 = tick_down(fb_rem(F, k), tick);                                  // JOB:561
-                    const bool done = ticked && (r2 == 0.0);                                         // JOB:562
+                    if (alive) r2 = tick_down(fb_rem(F, k), tick);                                   // JOB:561
+                    const bool done = alive && (r2 == 0.0);                                          // JOB:562
                     const uint32_t c = (uint32_t)(kd >> csh) & cmask;
-                    if (ticked && !done) fb_set_rem(F, k, r2);
-                    if (alive && !done && c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd & kmask);  // RCE:665-689 for the next tick
+                    if (alive && !done) {
+                        fb_set_rem(F, k, r2);
+                        if (c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd & kmask);                 // RCE:665-689 for the next tick
+                    }
                     const unsigned dmask = __ballot_sync(FULL, done);
                     if (dmask != 0u) {                                                               // JOB:525-536
                         uint32_t cnt = 0u, np = 1u;
@@ -246,9 +276,8 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                             fb_set_kd(F, k, 0ull);
                             cnt = par_inc(psm, par_sm, par_done, child);                             // JOB:530
                             np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
-                            ++ddone;
-                            if (!is_flow) ++nf_done;
                         }
+                        ddone += __popc(dmask);
                         const bool readied = done && (cnt == np);                                     // JOB:531 (fires once)
                         const unsigned m = __ballot_sync(FULL, readied);
                         if (m) {
@@ -260,12 +289,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                         }
                     }
                 }
-                ddone = warp_sum_i32(ddone);
-                nf_done = warp_sum_i32(nf_done);
-                if (lane == 0) {
-                    if (ddone) atomicAdd(&cc.ddone, ddone);
-                    if (nf_done) atomicAdd(&cc.nf_done, nf_done);
-                }
+                if (lane == 0 && ddone) atomicAdd(&cc.ddone, ddone);
             }
             // ---- G part 1: tick the op winners (RCE:691-716); rows of completed ops are queued for the cooperative copy below ----
             {
@@ -312,18 +336,17 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
 
             // ---- phase 3 ----
             const int nq = cc.dq_n;
-            const int ddone_all = cc.ddone;
+            const int ddone_all = cc.ddone;                      // flows completed by this tick (0 in a zero-length tick)
             const int nO_next = cc.n_ops_next;
             const int live_after = live - ddone_all;
             // compaction when more than half of the frontier is dead (order is irrelevant: arg-max is by key)
-            const bool compact = nF > 2 * live_after + NT;
+            const bool compact = !any_nf && nF > 2 * live_after + NT;
             const FrontBuf& Fdst = compact ? Falt : F;
             const int base_off = compact ? live_after : nF;          // arrivals go behind the survivors
 
             // G part 2: JOB:496-506 out-edges of the completed ops become ready: each warp takes every NW-th queued row and
             // copies its rows as one flattened range (all template loads of a batch in flight together)
             if (nq > 0) {
-                int arr_nf = 0;
                 for (int qb = 0; qb < nq; qb += 32 * NW) {
                     const int q = qb + lane * NW + warp;
                     int2 row = make_int2(0, 0);
@@ -336,14 +359,13 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                     }
                     const int total = __shfl_sync(FULL, inc, 31);
                     const int exc = inc - row.y;
-                    int base = 0;
-                    if (lane == 0 && total > 0) base = atomicAdd(&cc.arr, total);
-                    base = base_off + __shfl_sync(FULL, base, 0);
                     for (int jb = 0; jb < total; jb += 32 * RAMP_U) {
                         unsigned long long kd[RAMP_U];
                         double rt[RAMP_U];
 #pragma unroll
                         for (int u = 0; u < RAMP_U; ++u) {
+                            kd[u] = 0ull; rt[u] = 0.0;
+                            if (jb + u * 32 >= total) continue;              // warp-uniform: nothing left for this slice
                             const int jf = jb + u * 32 + lane;
                             const int jc = jf < total ? jf : total - 1;
                             int lo = 0;
@@ -355,7 +377,6 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                             const int o_start = __shfl_sync(FULL, row.x, lo);
                             const int o_exc = __shfl_sync(FULL, exc, lo);
                             const int e = o_start + (jc - o_exc);
-                            kd[u] = 0ull; rt[u] = 0.0;
                             if (jf < total) {
                                 kd[u] = __ldg(&t_dep_kd[e]);
                                 rt[u] = __ldg(&t_dep_rt[e]);                                    // RCE:542-560
@@ -363,18 +384,30 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                         }
 #pragma unroll
                         for (int u = 0; u < RAMP_U; ++u) {
+                            if (jb + u * 32 >= total) continue;              // warp-uniform
                             const int jf = jb + u * 32 + lane;
-                            if (jf < total) {
-                                fb_put(Fdst, base + jf, kd[u], rt[u]);
-                                if (((kd[u] >> fsh) & 1ull) == 0ull) ++arr_nf;
+                            const bool valid = jf < total;
+                            const bool flow = valid && (((kd[u] >> fsh) & 1ull) != 0ull);
+                            const unsigned fm = __ballot_sync(FULL, flow);
+                            const unsigned nm = __ballot_sync(FULL, valid && !flow);
+                            int fbase = 0, nbase = 0;
+                            if (lane == 0) {
+                                if (fm) fbase = atomicAdd(&cc.arr, __popc(fm));
+                                if (nm) nbase = atomicAdd(&cc.arr_nf, __popc(nm));
+                            }
+                            fbase = base_off + __shfl_sync(FULL, fbase, 0);
+                            nbase = __shfl_sync(FULL, nbase, 0);
+                            if (flow) {
+                                fb_put(Fdst, fbase + __popc(fm & lt_mask), kd[u], rt[u]);
                                 const uint32_t c = (uint32_t)(kd[u] >> csh) & cmask;
-                                if (c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd[u] & kmask);
+                                if (c != cmask) atomicMax(&ck_vote[c], (uint32_t)kd[u] & kmask);
+                            } else if (valid) {
+                                const int q = nbase + __popc(nm & lt_mask);
+                                if (q < RAMP_NF_CAP) nf_sm[q] = kd[u]; else nf_ovf[q - RAMP_NF_CAP] = kd[u];
                             }
                         }
                     }
                 }
-                arr_nf = warp_sum_i32(arr_nf);
-                if (lane == 0 && arr_nf) atomicAdd(&cc.arr_nf, arr_nf);
             }
             if (compact) {
                 for (int kb = 0; kb < nF; kb += NT) {
@@ -407,10 +440,10 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
 
             // ---- K, L + frontier bookkeeping: every thread derives the same values from the shared cells ----
             const int arrived = cc.arr;
-            deps_completed += ddone_all;
+            deps_completed += ddone_all + (any_nf ? nNF : 0);
             ops_completed += cc.ops_done;
             live = live_after + arrived;
-            n_nonflow += cc.arr_nf - cc.nf_done;
+            nNF = cc.arr_nf;                                  // the previous non-flow deps were all consumed by this tick
             const bool finished = (ops_completed == N) && (deps_completed == E);     // JOB:549-551
             if (!finished && isinf(tick) && tid == 0) status = RAMP_ST_INFINITE_TICK; // RCE:462
             if (finished || isinf(tick)) break;
@@ -419,7 +452,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             nO = nO_next;
             a_done = a_next;
             { const OpsView tmp = ops; ops = ops_n; ops_n = tmp; }
-            { uint32_t* tmp = ck_cur; ck_cur = ck_nxt; ck_nxt = tmp; }
+            if (!any_nf) { uint32_t* tmp = ck_cur; ck_cur = ck_nxt; ck_nxt = tmp; }
             par ^= 1;
         }
         __syncthreads();

@@ -165,6 +165,13 @@ CASES = {
                     shape=(2, 2, 4), n_jobs=5, max_partitions=8, interarrival=300.0, frac=(0.1, 1.0), actor='random', seed=3),
     'tfm32_acceptable': dict(graphs=[synth.transformer_like_graph(n_layers=2, name='tfm2', seed=9)], shape=(4, 4, 2), n_jobs=6,
                              max_partitions=16, interarrival=600.0, frac=(0.05, 0.6), actor='acceptable_jct', seed=4),
+    # many jobs in flight on a 64-worker cluster, three models sharing one memo, placements that fail when the cluster is full
+    'mixed64_busy': dict(graphs=[synth.chain_graph(4, 'chain4'), synth.resnet_like_graph(n_blocks=1, stem=2, name='res1', seed=11, body_per_block=2),
+                                 synth.transformer_like_graph(n_layers=1, name='tfm1b', seed=6)],
+                         shape=(4, 4, 4), n_jobs=8, max_partitions=8, interarrival=60.0, frac=(0.2, 1.0), actor='random', seed=12),
+    # arrivals far faster than completions: most jobs are blocked (no free workers / JCT above the acceptable one)
+    'res16_flood': dict(graphs=[synth.resnet_like_graph(n_blocks=1, stem=1, name='res1s', seed=3, body_per_block=2)], shape=(2, 2, 4),
+                        n_jobs=30, max_partitions=4, interarrival=20.0, frac=(0.3, 1.0), actor='sipml', seed=8),
     'residual32_deg16': dict(graphs=[synth.residual_small_graph()], shape=(4, 4, 2), n_jobs=3, max_partitions=16,
                              interarrival=1000.0, frac=(0.1, 1.0), actor='sipml', seed=1),
 }
