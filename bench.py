@@ -331,6 +331,16 @@ def run_b200_arm(args, rank, world, local_rank):
     e2e_value = world * B * K / float(e2e_t[0])
     eng.check_status()
 
+    # ---- raw RampClusterEnvironment.step calls per env-step: the scripted segments are deterministic, so one
+    #      untimed replay of a segment counts them exactly (an env-step = 1 cluster.step(action) + k cluster.step(Action())) ----
+    eng.reset(arrivals)
+    n_cluster_steps = 0
+    for p in range(L):
+        eng.step_device(on_dev[p].data_ptr(), True, stats_dev.data_ptr(), ncs_dev.data_ptr())
+        eng.sync()
+        n_cluster_steps += int(ncs_dev.sum().item())
+    cluster_steps_per_env_step = n_cluster_steps / float(B * L)
+
     # ---- secondary: RAMP_MEMO_SHARED (reference semantics + batch-wide result cache), device-resident inputs ----
     shared = None
     try:
@@ -375,7 +385,7 @@ def run_b200_arm(args, rank, world, local_rank):
                        'templates': [[t.n_ops, t.n_deps] for t in wl.templates], 'memo_mode': args.memo_mode,
                        'agent': 'random partition degree + aligned first-fit blocks (stand-in for the PAC-ML GNN policy)',
                        'l2': 'inputs larger than L2: the lookahead kernel streams its per-lookahead HBM slabs (~%.1f GB across the '
-                             'resident warps) plus %d MB of shared templates; no explicit flush' % (_scratch_gb(wl), _template_mb(wl)),
+                             'resident warps and CTAs) plus %d MB of shared templates; no explicit flush' % (_scratch_gb(wl), _template_mb(wl)),
                        'parallelism': f'episodes sharded x{world}, one NCCL all-gather of episode metrics per step' if world > 1
                                       else 'single GPU'},
             'e2e': {'value': e2e_value, 'unit': UNIT,
@@ -389,7 +399,10 @@ def run_b200_arm(args, rank, world, local_rank):
                          'algorithmic_bytes_per_launch': kt['algorithmic_bytes'] / max(kt['launches'], 1)},
             'memo': {'lookups': memo['lookups'], 'hits': memo['hits'],
                      'hit_rate': memo['hits'] / memo['lookups'] if memo['lookups'] else None},
-            'clocks': clocks, 'wall_ms_per_step': wall_ms / K, 'memo_shared': shared,
+            'clocks': clocks, 'wall_ms_per_step': wall_ms / K,
+            'cluster_steps': {'per_env_step': cluster_steps_per_env_step, 'value': value * cluster_steps_per_env_step,
+                              'e2e': e2e_value * cluster_steps_per_env_step, 'unit': 'RampClusterEnvironment.step calls/s'},
+            'memo_shared': shared,
         }
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args, wl)
@@ -401,7 +414,7 @@ def run_b200_arm(args, rank, world, local_rank):
 
 def _scratch_gb(wl):
     t = max(wl.templates, key=lambda t: t.n_deps)
-    return (52 * t.n_ops + 40 * t.n_deps) * 148 * 12 / 1e9
+    return (56 * t.n_ops + 40 * t.n_deps) * 148 * (12 + 8) / 1e9     # one slab per resident warp / CTA (ramp_kernels.cuh scratch_bytes_for)
 
 
 def _template_mb(wl):

@@ -12,6 +12,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "../../include/ramp_b200.h"
 
@@ -154,6 +155,7 @@ struct ScratchView {
     unsigned long long* f_km_ovf2;   // [E] second buffer (CTA-per-lookahead kernel compacts by ping-pong)
     double*   f_rem_ovf2;            // [E]
     unsigned long long* nf_ovf;      // [E] overflow of the shared-memory list of ready non-flow deps
+    int32_t*  rq_ovf;                // [N] overflow of the CTA kernel's queue of ops readied in the current tick
     int32_t*  tr_n;                  // [trace_cap] temp trace
     double*   tr_tick;               // [trace_cap]
 };
@@ -164,6 +166,7 @@ __host__ __device__ inline uint64_t scratch_bytes_for(int32_t N, int32_t E) {
     b += 2 * align_up((uint64_t)N * 16, 16);
     b += 2 * align_up((uint64_t)N * 8, 16);
     b += 5 * align_up((uint64_t)E * 8, 16);
+    b += align_up((uint64_t)N * 4, 16);
     return b;
 }
 
@@ -180,6 +183,7 @@ __device__ inline ScratchView carve(unsigned char* base, int32_t N, int32_t E, u
     v.f_km_ovf2 = (unsigned long long*)(base + o);   o += align_up((uint64_t)E * 8, 16);
     v.f_rem_ovf2 = (double*)(base + o);              o += align_up((uint64_t)E * 8, 16);
     v.nf_ovf = (unsigned long long*)(base + o);      o += align_up((uint64_t)E * 8, 16);
+    v.rq_ovf = (int32_t*)(base + o);                 o += align_up((uint64_t)N * 4, 16);
     v.tr_tick = (double*)(base + trace_region_off);
     v.tr_n = (int32_t*)(v.tr_tick + trace_cap);
     return v;
@@ -286,6 +290,15 @@ __device__ __forceinline__ void ops_put(const OpsView& v, int k, const int4 ra, 
     if (k < RAMP_OPS_CAP) { v.a_sm[k] = ra; v.b_sm[k] = rb; } else { v.a_ovf[k - RAMP_OPS_CAP] = ra; v.b_ovf[k - RAMP_OPS_CAP] = rb; }
 }
 // dep frontier entry = the packed dep word (TemplateDev::dep_kd) + the remaining time: 16 B
+// a readied op is first recorded as its op index only (in the row slot); its 24-byte record is fetched later, all
+// records of a tick in one batch, so that the tick waits for ONE L2 round trip instead of one per 32-dep group
+__device__ __forceinline__ void ops_put_child(const OpsView& v, int k, int child) {
+    if (k < RAMP_OPS_CAP) v.b_sm[k] = make_int2(child, 0); else v.b_ovf[k - RAMP_OPS_CAP] = make_int2(child, 0);
+}
+__device__ __forceinline__ int ops_get_child(const OpsView& v, int k) {
+    return (k < RAMP_OPS_CAP) ? v.b_sm[k].x : v.b_ovf[k - RAMP_OPS_CAP].x;
+}
+
 struct FrontView { unsigned long long* kd_sm; double* rem_sm; unsigned long long* kd_ovf; double* rem_ovf; };
 __device__ __forceinline__ void f_get(const FrontView& v, int k, unsigned long long& kd, double& rem) {
     if (k < RAMP_F_CAP) { kd = v.kd_sm[k]; rem = v.rem_sm[k]; } else { kd = v.kd_ovf[k - RAMP_F_CAP]; rem = v.rem_ovf[k - RAMP_F_CAP]; }
@@ -473,7 +486,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     }
                     const bool readied = valid && (cnt == np);                                   // JOB:531 (fires once)
                     const unsigned m = __ballot_sync(FULL, readied);
-                    if (readied) ops_put(ops_n, nO_next + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
+                    if (readied) ops_put_child(ops_n, nO_next + __popc(m & lt_mask), child);
                     nO_next += __popc(m);
                 }
                 deps_completed += nNF;
@@ -481,13 +494,18 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                 __syncwarp();
             } else {
                 int ddone = 0;
-                for (int kb = 0; kb < nF; kb += 32) {
+                // one group of 32 flows.  FULLG: all 32 lanes hold an entry (every group but the last); INSM: the group lies in
+                // the shared-memory part of the frontier (then so does everything it writes: p <= kb)
+                auto h_group = [&](auto full_tag, auto insm_tag, const int kb) {
+                    constexpr bool FULLG = decltype(full_tag)::value;
+                    constexpr bool INSM = decltype(insm_tag)::value;
                     const int k = kb + lane;
-                    const int n_here = (nF - kb < 32) ? (nF - kb) : 32;
-                    const bool valid = lane < n_here;
+                    const int n_here = FULLG ? 32 : (nF - kb);
+                    const bool valid = FULLG ? true : (lane < n_here);
                     unsigned long long kd = 0ull;
                     double rem = 1.0;
-                    if (valid) f_get(fr, k, kd, rem);
+                    if (INSM) { if (valid) { kd = fr.kd_sm[k]; rem = fr.rem_sm[k]; } }
+                    else { if (valid) f_get(fr, k, kd, rem); }
                     const double r2 = tick_down(rem, tick);                                         // JOB:561
                     const bool done = valid && (r2 == 0.0);                                         // JOB:562
                     const bool keep = valid && !done;
@@ -496,10 +514,10 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     const unsigned dmask = __ballot_sync(FULL, done);
                     if (dmask == 0u) {
                         if (p == kb) {                                 // nothing before it died either: update in place
-                            if (valid) { if (k < RAMP_F_CAP) fr.rem_sm[k] = r2; else fr.rem_ovf[k - RAMP_F_CAP] = r2; }
+                            if (valid) { if (INSM) fr.rem_sm[k] = r2; else if (k < RAMP_F_CAP) fr.rem_sm[k] = r2; else fr.rem_ovf[k - RAMP_F_CAP] = r2; }
                         } else {
                             __syncwarp();                              // all lanes have read before anything is written over
-                            if (valid) f_put(fr, p + lane, kd, r2);
+                            if (valid) { if (INSM) { fr.kd_sm[p + lane] = kd; fr.rem_sm[p + lane] = r2; } else f_put(fr, p + lane, kd, r2); }
                         }
                         p += n_here;                                   // warp-uniform: every valid entry of the group survives
                     } else {
@@ -512,18 +530,41 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                             np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
                         }
                         ddone += __popc(dmask);
-                        const unsigned vm = (n_here == 32) ? FULL : ((1u << n_here) - 1u);
+                        const unsigned vm = FULLG ? FULL : ((1u << n_here) - 1u);
                         const unsigned mk = vm & ~dmask;
                         __syncwarp();
-                        if (keep) f_put(fr, p + __popc(mk & lt_mask), kd, r2);
+                        if (keep) {
+                            const int q = p + __popc(mk & lt_mask);
+                            if (INSM) { fr.kd_sm[q] = kd; fr.rem_sm[q] = r2; } else f_put(fr, q, kd, r2);
+                        }
                         p += __popc(mk);
                         const bool readied = done && (cnt == np);                                    // JOB:531 (fires once)
                         const unsigned m = __ballot_sync(FULL, readied);
-                        if (readied) ops_put(ops_n, nO_next + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
+                        if (readied) ops_put_child(ops_n, nO_next + __popc(m & lt_mask), child);
                         nO_next += __popc(m);
                     }
-                }
+                };
+                const int n_full = nF & ~31;                           // entries covered by full groups
+                const int n_full_sm = (n_full < RAMP_F_CAP) ? n_full : RAMP_F_CAP;   // RAMP_F_CAP is a multiple of 32
+                int kb = 0;
+                for (; kb < n_full_sm; kb += 32) h_group(std::true_type{}, std::true_type{}, kb);
+                for (; kb < nF; kb += 32) h_group(std::false_type{}, std::false_type{}, kb);
                 deps_completed += ddone;
+            }
+            // the records of the ops readied above: the first 32 are loaded here and stored after G (the loads fly while G
+            // runs), any more are fetched in place
+            const int n_ready = nO_next;
+            __syncwarp();
+            int4 rdy_a = make_int4(0, 0, 0, 0);
+            int2 rdy_b = make_int2(0, 0);
+            if (lane < n_ready) {
+                const int child = ops_get_child(ops_n, lane);
+                rdy_a = __ldg(&t_op_rec[child]);
+                rdy_b = __ldg(&t_op_row[child]);
+            }
+            for (int k = 32 + lane; k < n_ready; k += 32) {
+                const int child = ops_get_child(ops_n, k);
+                ops_put(ops_n, k, __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
             }
 
             // ---- G: tick the op winners; rows of the completed ops are appended at [p, tail) ----
@@ -612,6 +653,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     }
                 }
             }
+            if (lane < n_ready) ops_put(ops_n, lane, rdy_a, rdy_b);
             if (big_ops) { __syncwarp(); for (int i = lane; i < W; i += 32) wkey[i] = 0u; }
             nNF = nNF_next;
             __syncwarp();

@@ -16,12 +16,16 @@ namespace ramp {
 #ifndef RAMP_CTA_F_CAP
 #define RAMP_CTA_F_CAP 512     // dep-frontier records per buffer kept in shared memory (x2 buffers)
 #endif
+#ifndef RAMP_RQ_CAP
+#define RAMP_RQ_CAP 64         // ops readied in the current tick kept in shared memory (op indices; overflow goes to HBM)
+#endif
 #ifndef RAMP_CTA_MIN_WARPS
 #define RAMP_CTA_MIN_WARPS 16  // resident warps per SM the register allocation must allow
 #endif
 
 struct CtaCells {              // written during the tick with parity p, read after that tick's barriers, reset one tick later
-    int n_ops_next;            // op frontier being built for the next tick                 (phase 2)
+    int n_ops_next;            // surviving ops copied to the next op frontier              (phase 2)
+    int n_ready;               // ops readied by this tick's completions (queued op indices) (phase 2)
     int ddone, ops_done, dq_n;                                                           // (phase 2)
     int n_active;                                                                        // (phase 1)
     int arr, arr_nf, ctail;    // flow / non-flow arrival cursors, compaction cursor        (phase 3)
@@ -35,6 +39,7 @@ __host__ __device__ inline size_t lookahead_cta_smem(int w_cap, int c_cap, int p
     b += (size_t)RAMP_NF_CAP * 8;                // ready non-flow deps
     b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
     b += (size_t)w_cap * 8;                      // done queue: {row start, degree}
+    b += (size_t)RAMP_RQ_CAP * 4;                // readied-op queue
     b += (size_t)(w_cap + 2 * c_cap) * 4;        // wkey, ckey (this tick / next tick)
     b += (size_t)par_cap;                        // parent counters (bytes)
     return (b + 15) & ~(size_t)15;
@@ -77,7 +82,8 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
     unsigned long long* nf_sm = reinterpret_cast<unsigned long long*>(rem_sm0 + 2 * RAMP_CTA_F_CAP);   // [RAMP_NF_CAP]
     int2* ops_b_sm0 = reinterpret_cast<int2*>(nf_sm + RAMP_NF_CAP);                       // [2][RAMP_OPS_CAP]
     int2* doneq = ops_b_sm0 + 2 * RAMP_OPS_CAP;                                           // [w_cap] rows of ops completed this tick
-    uint32_t* wkey = reinterpret_cast<uint32_t*>(doneq + a.w_cap);                        // [w_cap]
+    int32_t* rq_sm = reinterpret_cast<int32_t*>(doneq + a.w_cap);                         // [RAMP_RQ_CAP]
+    uint32_t* wkey = reinterpret_cast<uint32_t*>(rq_sm + RAMP_RQ_CAP);                    // [w_cap]
     uint32_t* ckey0 = wkey + a.w_cap;                                                     // [2][c_cap]
     uint32_t* par_sm = ckey0 + 2 * a.c_cap;                                               // [par_cap / 4] byte parent counters
 
@@ -108,6 +114,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         const double* __restrict__ t_dep_rt = T.dep_rt;
         uint32_t* par_done = sv.par_done;
         unsigned long long* nf_ovf = sv.nf_ovf;
+        int32_t* rq_ovf = sv.rq_ovf;
         const bool psm = T.par_in_smem != 0;
         const uint32_t kmask = T.kd_kmask, cmask = T.kd_cmask;
         const int csh = T.kd_cshift, fsh = T.kd_fshift, dsh = T.kd_dshift;
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
         }
         if (tid == 0) {
             for (int q = 0; q < 2; ++q) {
-                cells[q].n_ops_next = 0; cells[q].ddone = 0; cells[q].ops_done = 0; cells[q].dq_n = 0;
+                cells[q].n_ops_next = 0; cells[q].n_ready = 0; cells[q].ddone = 0; cells[q].ops_done = 0; cells[q].dq_n = 0;
                 cells[q].n_active = 0; cells[q].arr = 0; cells[q].arr_nf = 0; cells[q].ctail = 0;
                 cells[q].min_op = RAMP_INF_BITS; cells[q].min_dep = RAMP_INF_BITS;
             }
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                 if (tick_no < a.trace_cap) { sv.tr_n[tick_no] = n_active; sv.tr_tick[tick_no] = tick; }
                 else status = RAMP_ST_TRACE_OVERFLOW;
                 CtaCells& o = cells[par ^ 1];
-                o.n_ops_next = 0; o.ddone = 0; o.ops_done = 0; o.dq_n = 0; o.n_active = 0;
+                o.n_ops_next = 0; o.n_ready = 0; o.ddone = 0; o.ops_done = 0; o.dq_n = 0; o.n_active = 0;
                 o.arr = 0; o.arr_nf = 0; o.ctail = 0;
                 o.min_op = RAMP_INF_BITS; o.min_dep = RAMP_INF_BITS;
             }
@@ -243,12 +250,12 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                     }
                     const bool readied = valid && (cnt == np);                                        // JOB:531 (fires once)
                     const unsigned m = __ballot_sync(FULL, readied);
-                    if (m) {
+                    if (m) {                         // queue the op index; its record is fetched in phase 3, all of a tick in one batch
                         const int leader = __ffs(m) - 1;
                         int base = 0;
-                        if (lane == leader) base = atomicAdd(&cc.n_ops_next, __popc(m));
+                        if (lane == leader) base = atomicAdd(&cc.n_ready, __popc(m));
                         base = __shfl_sync(FULL, base, leader);
-                        if (readied) ops_put(ops_n, base + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
+                        if (readied) { const int q = base + __popc(m & lt_mask); if (q < RAMP_RQ_CAP) rq_sm[q] = child; else rq_ovf[q - RAMP_RQ_CAP] = child; }
                     }
                 }
             } else {
@@ -280,12 +287,12 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                         ddone += __popc(dmask);
                         const bool readied = done && (cnt == np);                                     // JOB:531 (fires once)
                         const unsigned m = __ballot_sync(FULL, readied);
-                        if (m) {
+                        if (m) {                     // queue the op index; its record is fetched in phase 3
                             const int leader = __ffs(m) - 1;
                             int base = 0;
-                            if (lane == leader) base = atomicAdd(&cc.n_ops_next, __popc(m));
+                            if (lane == leader) base = atomicAdd(&cc.n_ready, __popc(m));
                             base = __shfl_sync(FULL, base, leader);
-                            if (readied) ops_put(ops_n, base + __popc(m & lt_mask), __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
+                            if (readied) { const int q = base + __popc(m & lt_mask); if (q < RAMP_RQ_CAP) rq_sm[q] = child; else rq_ovf[q - RAMP_RQ_CAP] = child; }
                         }
                     }
                 }
@@ -337,12 +344,23 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             // ---- phase 3 ----
             const int nq = cc.dq_n;
             const int ddone_all = cc.ddone;                      // flows completed by this tick (0 in a zero-length tick)
-            const int nO_next = cc.n_ops_next;
+            const int n_kept = cc.n_ops_next, n_ready = cc.n_ready;
+            const int nO_next = n_kept + n_ready;                // next op frontier = surviving ops, then the readied ones
             const int live_after = live - ddone_all;
             // compaction when more than half of the frontier is dead (order is irrelevant: arg-max is by key)
             const bool compact = !any_nf && nF > 2 * live_after + NT;
             const FrontBuf& Fdst = compact ? Falt : F;
             const int base_off = compact ? live_after : nF;          // arrivals go behind the survivors
+
+            // records of the readied ops: one load per thread issued now, stored at the end of the phase (the loads fly while
+            // the rows are copied)
+            int4 rdy_a = make_int4(0, 0, 0, 0);
+            int2 rdy_b = make_int2(0, 0);
+            if (tid < n_ready) {
+                const int child = (tid < RAMP_RQ_CAP) ? rq_sm[tid] : rq_ovf[tid - RAMP_RQ_CAP];
+                rdy_a = __ldg(&t_op_rec[child]);
+                rdy_b = __ldg(&t_op_row[child]);
+            }
 
             // G part 2: JOB:496-506 out-edges of the completed ops become ready: each warp takes every NW-th queued row and
             // copies its rows as one flattened range (all template loads of a batch in flight together)
@@ -428,13 +446,23 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             // phase A of the next tick: every winner slot was released in G part 1 (all of wkey is zero again)
             const bool a_next = !big_ops && (nO_next <= 32 * NT);
             if (a_next) {
-                for (int k = tid; k < nO_next; k += NT) {
+                for (int k = tid; k < n_kept; k += NT) {
                     int4 ra; int2 rb;
                     ops_get(ops_n, k, ra, rb);
                     atomicMax(&wkey[ra.w], (uint32_t)ra.z);
                 }
             } else if (big_ops) {
                 for (int i = tid; i < W; i += NT) wkey[i] = 0u;
+            }
+            if (tid < n_ready) {
+                ops_put(ops_n, n_kept + tid, rdy_a, rdy_b);
+                if (a_next) atomicMax(&wkey[rdy_a.w], (uint32_t)rdy_a.z);
+            }
+            for (int k = NT + tid; k < n_ready; k += NT) {
+                const int child = (k < RAMP_RQ_CAP) ? rq_sm[k] : rq_ovf[k - RAMP_RQ_CAP];
+                const int4 ra = __ldg(&t_op_rec[child]);
+                ops_put(ops_n, n_kept + k, ra, __ldg(&t_op_row[child]));
+                if (a_next) atomicMax(&wkey[ra.w], (uint32_t)ra.z);
             }
             __syncthreads();
 

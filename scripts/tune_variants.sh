@@ -4,9 +4,7 @@ cp ddls_b200/libramp_b200.so /tmp/lib_orig.so
 for lib in build_variants/lib_*.so; do
   cp $lib ddls_b200/libramp_b200.so
   echo "== $(basename $lib)"
-  RAMP_LOOKAHEAD_MODE=cta RAMP_LOOKAHEAD_CTA_THREADS=128 timeout 100 python scripts/latency_probe2.py 16 1 592
-  RAMP_LOOKAHEAD_MODE=cta RAMP_LOOKAHEAD_CTA_THREADS=64 timeout 100 python scripts/latency_probe2.py 16 1 592
-  timeout 120 python scripts/step_profile.py 2>&1 | cut -c1-75
+  timeout 120 python scripts/step_profile.py 2>&1 | cut -c1-75 | head -3
   timeout 120 python bench.py --steps 16 --warmup 8 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']))"
 done
 cp /tmp/lib_orig.so ddls_b200/libramp_b200.so
