@@ -261,17 +261,19 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
             } else {
                 int ddone = 0;
                 const int n_groups = (nF + 31) / 32;
-                for (int gi = NW - 1 - warp; gi < n_groups; gi += NW) {
+                // one group of 32 entries; INSM: the group lies in the shared-memory part of the frontier
+                auto h_group = [&](auto insm_tag, const int gi) {
+                    constexpr bool INSM = decltype(insm_tag)::value;
                     const int k = gi * 32 + lane;
                     unsigned long long kd = 0ull;
-                    if (k < nF) kd = fb_kd(F, k);
+                    if (k < nF) kd = INSM ? F.kd_sm[k] : fb_kd(F, k);
                     const bool alive = kd != 0ull;
                     double r2 = 1.0;
-                    if (alive) r2 = tick_down(fb_rem(F, k), tick);                                   // JOB:561
+                    if (alive) r2 = tick_down(INSM ? F.rem_sm[k] : fb_rem(F, k), tick);              // JOB:561
                     const bool done = alive && (r2 == 0.0);                                          // JOB:562
                     const uint32_t c = (uint32_t)(kd >> csh) & cmask;
                     if (alive && !done) {
-                        fb_set_rem(F, k, r2);
+                        if (INSM) F.rem_sm[k] = r2; else fb_set_rem(F, k, r2);
                         if (c != cmask) atomicMax(&ck_nxt[c], (uint32_t)kd & kmask);                 // RCE:665-689 for the next tick
                     }
                     const unsigned dmask = __ballot_sync(FULL, done);
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                         int child = 0;
                         if (done) {
                             child = (int)(kd >> dsh);
-                            fb_set_kd(F, k, 0ull);
+                            if (INSM) F.kd_sm[k] = 0ull; else fb_set_kd(F, k, 0ull);
                             cnt = par_inc(psm, par_sm, par_done, child);                             // JOB:530
                             np = psm ? (uint32_t)(kd >> (fsh + 1)) & 0xFFu : (uint32_t)__ldg(&t_n_parents[child]);
                         }
@@ -295,6 +297,10 @@ __global__ void __launch_bounds__(NW * 32, RAMP_CTA_MIN_WARPS / NW) ramp_lookahe
                             if (readied) { const int q = base + __popc(m & lt_mask); if (q < RAMP_RQ_CAP) rq_sm[q] = child; else rq_ovf[q - RAMP_RQ_CAP] = child; }
                         }
                     }
+                };
+                for (int gi = NW - 1 - warp; gi < n_groups; gi += NW) {
+                    if (gi * 32 + 32 <= RAMP_CTA_F_CAP) h_group(std::true_type{}, gi);
+                    else h_group(std::false_type{}, gi);
                 }
                 if (lane == 0 && ddone) atomicAdd(&cc.ddone, ddone);
             }

@@ -339,3 +339,67 @@ def test_shared_memo_survives_reset_and_matches_reference_mode(eng_mod):
         eng.close()
     for a, b in zip(runs[0], runs[3]):
         np.testing.assert_array_equal(a, b)
+
+
+def _fan_template(M, W, seed):
+    """source -> M children -> sink on W workers: every shared-memory list of the kernels overflows into HBM when M is in
+    the thousands (flow frontier, one-tick non-flow list, op frontier, readied-op queue), and the sink's in-degree M > 255
+    forces the global parent counters."""
+    from ddls_b200.lowered import LoweredJob, MountScalars
+    rng = np.random.default_rng(seed)
+    N, E = M + 2, 2 * M
+    worker = np.concatenate([[0], rng.integers(0, W, size=M), [0]]).astype(np.int64)
+    cost = np.concatenate([[1.0], np.round(rng.uniform(0.0, 3.0, size=M), 2), [0.5]])
+    cost[1:M + 1][rng.random(M) < 0.1] = 0.0                                   # zero-cost ops complete in zero-length ticks
+    row_ptr = np.concatenate([[0, M], M + 1 + np.arange(M), [E]]).astype(np.int64)   # op 0: M deps; child i: 1 dep; sink: 0
+    dst = np.concatenate([1 + np.arange(M), np.full(M, M + 1)]).astype(np.int64)
+    src_w = np.concatenate([np.zeros(M, dtype=np.int64), worker[1:M + 1]])
+    dst_w = worker[dst]
+    is_flow = (src_w != dst_w).astype(np.uint8)
+    pair = src_w * W + dst_w
+    chans = {p: i for i, p in enumerate(np.unique(pair[is_flow == 1]))}
+    channel = np.array([chans[p] if f else 0xFFFF for p, f in zip(pair, is_flow)], dtype=np.int64)
+    rt = np.where(is_flow == 1, np.round(rng.uniform(0.01, 2.0, size=E), 3), 0.0)
+    rt[(is_flow == 1) & (rng.random(E) < 0.3)] = 0.25                            # many equal run times: completions in bulk
+    n_par = np.concatenate([[0], np.ones(M), [M]]).astype(np.int64)
+    return LoweredJob(n_ops=N, n_deps=E, n_workers=W, n_channels=len(chans), num_training_steps=3, model_id=0, degree=2,
+                      op_cost=cost, op_prio=rng.integers(0, 50, size=N), op_worker=worker, op_n_parents=n_par, row_ptr=row_ptr,
+                      dep_dst=dst, dep_run_time=rt, dep_prio=rng.integers(0, 20, size=E), dep_channel=channel, dep_is_flow=is_flow,
+                      mount=MountScalars(n_mounted_workers=W)).canonicalise()
+
+
+@pytest.mark.parametrize('mode,cta_threads', [('warp', '0'), ('cta', '64'), ('cta', '128')])
+@pytest.mark.parametrize('M,W', [(200, 4), (3000, 6)])
+def test_wide_fan_overflows_every_shared_memory_list(M, W, mode, cta_threads, eng_mod, oracle_lib):
+    import os
+    t = _fan_template(M, W, seed=M)
+    want = oracle_lib.run_lookahead(t)
+    os.environ['RAMP_LOOKAHEAD_MODE'] = mode
+    if cta_threads != '0':
+        os.environ['RAMP_LOOKAHEAD_CTA_THREADS'] = cta_threads
+    try:
+        eng = eng_mod.RampEngine(n_episodes=1, n_cluster_workers=8, max_jobs=1, trace_cap=1 << 15)
+    finally:
+        os.environ.pop('RAMP_LOOKAHEAD_MODE', None)
+        os.environ.pop('RAMP_LOOKAHEAD_CTA_THREADS', None)
+    tid = eng.register_template(t)
+    res, _, tn, tt = eng.run_lookaheads(np.full(5, tid, dtype=np.int32), want_trace=True)
+    assert (res['status'] == 0).all() and (res['n_ticks'] == want['n_ticks']).all()
+    for i in range(5):
+        T = int(res['n_ticks'][i])
+        np.testing.assert_array_equal(tn[i, :T], want['trace_n_active'])
+        np.testing.assert_array_equal(tt[i, :T], want['trace_tick'])
+    assert (res['jct'] == want['jct']).all() and (res['comm'] == want['comm']).all() and (res['comp'] == want['comp']).all()
+    eng.close()
+
+
+def test_register_rejects_non_flow_dep_with_run_time(eng_mod):
+    """RCE:542-560 zeroes every non-flow run time; with a non-zero one the reference's zero-length ticks never end."""
+    t = _fan_template(20, 3, seed=1)
+    k = int(np.nonzero(np.asarray(t.dep_is_flow) == 0)[0][0])
+    t.dep_run_time = np.array(t.dep_run_time, dtype=np.float64)
+    t.dep_run_time[k] = 0.5
+    eng = eng_mod.RampEngine(n_episodes=1, n_cluster_workers=8, max_jobs=1)
+    with pytest.raises(Exception, match='non-flow dep'):
+        eng.register_template(t)
+    eng.close()

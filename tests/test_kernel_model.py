@@ -41,3 +41,14 @@ def test_model_matches_oracle_on_random_jobs(seed, oracle_lib):
     np.testing.assert_array_equal(out['trace_n_active'], ref['trace_n_active'])
     np.testing.assert_array_equal(out['trace_tick'], ref['trace_tick'])
     assert out['jct'] == ref['jct'] and out['comm'] == ref['comm'] and out['comp'] == ref['comp']
+
+
+def test_model_matches_oracle_on_wide_fan(oracle_lib):
+    """Hundreds of flows sharing a handful of channels, bulk completions, zero-cost ops (the template of the GPU overflow test)."""
+    from test_gpu_parity import _fan_template
+    job = _fan_template(200, 4, seed=200)
+    ref = oracle_lib.run_lookahead(job)
+    out = run_lookahead_model(job)
+    np.testing.assert_array_equal(out['trace_n_active'], ref['trace_n_active'])
+    np.testing.assert_array_equal(out['trace_tick'], ref['trace_tick'])
+    assert out['jct'] == ref['jct'] and out['comm'] == ref['comm'] and out['comp'] == ref['comp']
