@@ -248,16 +248,18 @@ LookaheadArgs make_lookahead_args(ramp_engine* e, const WorkItem* items, Counter
     return a;
 }
 
-// Launches the lookahead kernel for n_items work items: one CTA per lookahead when the items fit in about one wave of
-// CTAs (latency-bound regime), one warp per lookahead otherwise (instruction-efficiency regime).
-void launch_lookahead(ramp_engine* e, const LookaheadArgs& a, int n_items, cudaStream_t st) {
-    // measured on B200 (profiles/r1_tune_cta.txt, ResNet-50-like degree-16 lookahead): 128-thread CTAs 4.3 ms each while
-    // they all fit in one wave, 64-thread CTAs 6.0 ms, one warp 7.7 ms but the most lookaheads per SM
+// Launches ONE lookahead kernel for n_items work items of a standalone run (ramp_run_lookaheads): one CTA per lookahead
+// when there are big lookaheads among them and the items fit in about one wave of CTAs (latency-bound regime), one warp
+// per lookahead otherwise (small lookaheads are fastest on one warp; many lookaheads need the warp kernel's density).
+// Measured on B200 (ResNet-50-like job): degree 16 alone 2.7 ms on a 128-thread CTA, 4.0 ms on a 64-thread CTA, 4.5-5 ms on
+// one warp; degree 2: 1.8 / 1.8 / 1.5 ms.
+void launch_lookahead(ramp_engine* e, const LookaheadArgs& a, int n_items, int n_big, cudaStream_t st) {
     int cta_nt = 0;
-    if (e->mode != 1) {
-        if (e->cta_nt) { if (e->mode == 2 || n_items <= (e->cta_nt == 128 ? e->cta_grid : e->cta64_grid)) cta_nt = e->cta_nt; }
+    if (e->mode == 2) cta_nt = e->cta_nt ? e->cta_nt : (n_items <= e->cta_grid ? 128 : 64);
+    else if (e->mode != 1 && n_big > 0) {
+        if (e->cta_nt) { if (n_items <= (e->cta_nt == 128 ? e->cta_grid : e->cta64_grid)) cta_nt = e->cta_nt; }
         else if (n_items <= e->cta_grid) cta_nt = 128;
-        else if (n_items <= e->cta64_grid || e->mode == 2) cta_nt = 64;
+        else if (n_items <= e->cta64_grid) cta_nt = 64;
     }
     if (cta_nt) {
         const int grid = std::max(1, std::min(cta_nt == 128 ? e->cta_grid : e->cta64_grid, n_items));
@@ -643,8 +645,8 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
                 }
                 CUDA_TRY(cudaStreamWaitEvent(st, e->ev_join, 0));
             } else if (e->mode == 2) {
-                if (n_big > 0) { launch_lookahead(e, ab, n_big, st); e->launches++; }
-                if (n_small > 0) { launch_lookahead(e, a, n_small, st); e->launches++; }
+                if (n_big > 0) { launch_lookahead(e, ab, n_big, n_big, st); e->launches++; }
+                if (n_small > 0) { launch_lookahead(e, a, n_small, 0, st); e->launches++; }
             } else {
                 LookaheadArgs all = ab;                      // list A = big, list B = small, one cursor
                 all.items_b = e->d_items; all.n_work_b = &e->d_counters->n_work;
@@ -827,7 +829,9 @@ int ramp_run_lookaheads(ramp_engine_t* e, const int32_t* template_ids, int32_t n
     cudaEvent_t ea = e->ev_a[MAX_EVENT_PAIRS - 1], eb = e->ev_b[MAX_EVENT_PAIRS - 1];
     if (e->ev_pending >= MAX_EVENT_PAIRS - 1) { CUDA_TRY(cudaStreamSynchronize(st)); rc = resolve_events(e); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(ea, st));
-    launch_lookahead(e, a, n, st);
+    int n_big = 0;
+    for (int32_t k = 0; k < n; ++k) n_big += e->templates[template_ids[k]].dev.size_class;
+    launch_lookahead(e, a, n, n_big, st);
     CUDA_TRY(cudaEventRecord(eb, st));
     e->launches++;
     CUDA_TRY(cudaGetLastError());

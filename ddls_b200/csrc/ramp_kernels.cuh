@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     constexpr bool FULLG = decltype(full_tag)::value;
                     constexpr bool INSM = decltype(insm_tag)::value;
                     const int k = kb + lane;
-                    const int n_here = FULLG ? 32 : (nF - kb);
+                    const int n_here = FULLG ? 32 : ((nF - kb < 32) ? (nF - kb) : 32);
                     const bool valid = FULLG ? true : (lane < n_here);
                     unsigned long long kd = 0ull;
                     double rem = 1.0;
