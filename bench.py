@@ -24,8 +24,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 must print ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO in the image env) off stdout
-if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION', 'INFO') and not os.environ.get('RAMP_KEEP_NCCL_DEBUG'):
+# rank 0 must print ONE JSON line on stdout: NCCL prints its version banner at every level >= VERSION (WARN included), so
+# its log goes to stderr
+if not os.environ.get('NCCL_DEBUG_FILE'):
+    os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
+if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO') and not os.environ.get('RAMP_KEEP_NCCL_DEBUG'):
     os.environ['NCCL_DEBUG'] = 'WARN'
 
 METRIC = 'env_steps_per_sec'
