@@ -54,6 +54,10 @@ LookaheadKernel lookahead_kernel_for(int nt) {   // nt = threads per CTA = 32 x 
     }
 }
 
+// the dense shape of the warp kernel: smaller shared-memory frontiers, 16 instead of 12 lookahead warps per SM
+constexpr int DENSE_F_CAP = 256, DENSE_OPS_CAP = 32, DENSE_NT = 128;
+LookaheadKernel lookahead_dense_kernel() { return ramp_lookahead_kernel<DENSE_NT / 32, DENSE_F_CAP, DENSE_OPS_CAP>; }
+
 LookaheadKernel lookahead_cta_kernel_for(int nt) {   // one CTA of nt threads per lookahead
     switch (nt) {
         case 64: return ramp_lookahead_cta_kernel<2>;
@@ -111,6 +115,9 @@ struct ramp_engine {
     size_t smem_bytes = 0;
     // CTA-per-lookahead variant (lower latency; used when a launch has fewer work items than warp slots)
     int cta_nt = 0;              // 0 = pick 128 or 64 threads per launch; RAMP_LOOKAHEAD_CTA_THREADS forces one
+    int dense_grid = 0;          // resident CTAs of the dense warp-kernel shape
+    size_t dense_smem_bytes = 0;
+    double dense_factor = 2.0;   // the dense shape runs a step's lookaheads when there are more than dense_factor x warp slots
     int cta_grid = 0;            // resident CTAs of the 128-thread variant
     int cta64_grid = 0;          // resident CTAs of the 64-thread variant
     size_t cta_smem_bytes = 0;
@@ -197,6 +204,14 @@ int ensure_scratch(ramp_engine* e) {
         CUDA_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         CUDA_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributePreferredSharedMemoryCarveout, RAMP_SMEM_CARVEOUT));
         e->smem2_bytes = smem2;
+        const size_t smem_d = lookahead_smem_per_warp(e->max_w, e->max_c, e->par_cap, DENSE_F_CAP, DENSE_OPS_CAP) * (size_t)(DENSE_NT / 32);
+        LookaheadKernel kern_d = lookahead_dense_kernel();
+        CUDA_TRY(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+        CUDA_TRY(cudaFuncSetAttribute(kern_d, cudaFuncAttributePreferredSharedMemoryCarveout, RAMP_SMEM_CARVEOUT));
+        int occ_d = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, kern_d, DENSE_NT, smem_d));
+        e->dense_grid = e->sm_count * std::max(occ_d, 1);
+        e->dense_smem_bytes = smem_d;
     }
     const size_t cta_smem = lookahead_cta_smem(e->max_w, e->max_c, e->par_cap);
     if (cta_smem > 200 * 1024)
@@ -214,7 +229,7 @@ int ensure_scratch(ramp_engine* e) {
         e->cta_smem_bytes = cta_smem;
     }
     // one slab per lookahead in flight; the warp kernel and one of the CTA kernels may run side by side
-    const int n_slabs = e->grid * (e->nt / 32) + std::max(e->cta_grid, e->cta64_grid);
+    const int n_slabs = std::max(e->grid * (e->nt / 32) + std::max(e->cta_grid, e->cta64_grid), e->dense_grid * (DENSE_NT / 32));
     if (stride != e->scratch_stride || n_slabs != e->scratch_grid || e->d_scratch == nullptr) {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
         if (e->d_scratch) cudaFree(e->d_scratch);
@@ -326,6 +341,7 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     if (const char* v = getenv("RAMP_BIG_THRESHOLD")) e->big_threshold = atoll(v);
     if (const char* v = getenv("RAMP_DEBUG")) e->debug = atoi(v);
     if (const char* v = getenv("RAMP_SPLIT_ALPHA")) e->split_alpha = atof(v);
+    if (const char* v = getenv("RAMP_DENSE_FACTOR")) e->dense_factor = atof(v);
     if (const char* v = getenv("RAMP_SPLIT_WARP_THREADS")) {
         const int nt = atoi(v);
         if (lookahead_kernel_for(nt) == nullptr) { delete e; return set_error(RAMP_ERR_BAD_ARG, "RAMP_SPLIT_WARP_THREADS must be 32, 64, 128 or 256"); }
@@ -651,8 +667,15 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
                 LookaheadArgs all = ab;                      // list A = big, list B = small, one cursor
                 all.items_b = e->d_items; all.n_work_b = &e->d_counters->n_work;
                 const int n_all = n_small + n_big;
-                const int g = std::max(1, std::min(e->grid, (n_all + wpb - 1) / wpb));
-                lookahead_kernel_for(e->nt)<<<g, e->nt, e->smem_bytes, st>>>(all);
+                if (e->mode == 0 && e->dense_grid * (DENSE_NT / 32) > warp_slots && n_all > (int)(e->dense_factor * warp_slots)) {
+                    // far more lookaheads than slots: throughput matters, not the latency of one -> 16 warps per SM
+                    const int wd = DENSE_NT / 32;
+                    const int g = std::max(1, std::min(e->dense_grid, (n_all + wd - 1) / wd));
+                    lookahead_dense_kernel()<<<g, DENSE_NT, e->dense_smem_bytes, st>>>(all);
+                } else {
+                    const int g = std::max(1, std::min(e->grid, (n_all + wpb - 1) / wpb));
+                    lookahead_kernel_for(e->nt)<<<g, e->nt, e->smem_bytes, st>>>(all);
+                }
                 e->launches++;
             }
             CUDA_TRY(cudaEventRecord(e->ev_b[e->ev_pending], st));

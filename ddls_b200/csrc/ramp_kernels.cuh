@@ -283,28 +283,34 @@ __device__ __forceinline__ double util_sum(const double* term, int n_rec) {
 #endif
 
 struct OpsView { int4* a_sm; int2* b_sm; int4* a_ovf; int2* b_ovf; };
+template <int OC = RAMP_OPS_CAP>
 __device__ __forceinline__ void ops_get(const OpsView& v, int k, int4& ra, int2& rb) {
-    if (k < RAMP_OPS_CAP) { ra = v.a_sm[k]; rb = v.b_sm[k]; } else { ra = v.a_ovf[k - RAMP_OPS_CAP]; rb = v.b_ovf[k - RAMP_OPS_CAP]; }
+    if (k < OC) { ra = v.a_sm[k]; rb = v.b_sm[k]; } else { ra = v.a_ovf[k - OC]; rb = v.b_ovf[k - OC]; }
 }
+template <int OC = RAMP_OPS_CAP>
 __device__ __forceinline__ void ops_put(const OpsView& v, int k, const int4 ra, const int2 rb) {
-    if (k < RAMP_OPS_CAP) { v.a_sm[k] = ra; v.b_sm[k] = rb; } else { v.a_ovf[k - RAMP_OPS_CAP] = ra; v.b_ovf[k - RAMP_OPS_CAP] = rb; }
+    if (k < OC) { v.a_sm[k] = ra; v.b_sm[k] = rb; } else { v.a_ovf[k - OC] = ra; v.b_ovf[k - OC] = rb; }
 }
 // dep frontier entry = the packed dep word (TemplateDev::dep_kd) + the remaining time: 16 B
 // a readied op is first recorded as its op index only (in the row slot); its 24-byte record is fetched later, all
 // records of a tick in one batch, so that the tick waits for ONE L2 round trip instead of one per 32-dep group
+template <int OC = RAMP_OPS_CAP>
 __device__ __forceinline__ void ops_put_child(const OpsView& v, int k, int child) {
-    if (k < RAMP_OPS_CAP) v.b_sm[k] = make_int2(child, 0); else v.b_ovf[k - RAMP_OPS_CAP] = make_int2(child, 0);
+    if (k < OC) v.b_sm[k] = make_int2(child, 0); else v.b_ovf[k - OC] = make_int2(child, 0);
 }
+template <int OC = RAMP_OPS_CAP>
 __device__ __forceinline__ int ops_get_child(const OpsView& v, int k) {
-    return (k < RAMP_OPS_CAP) ? v.b_sm[k].x : v.b_ovf[k - RAMP_OPS_CAP].x;
+    return (k < OC) ? v.b_sm[k].x : v.b_ovf[k - OC].x;
 }
 
 struct FrontView { unsigned long long* kd_sm; double* rem_sm; unsigned long long* kd_ovf; double* rem_ovf; };
+template <int FC = RAMP_F_CAP>
 __device__ __forceinline__ void f_get(const FrontView& v, int k, unsigned long long& kd, double& rem) {
-    if (k < RAMP_F_CAP) { kd = v.kd_sm[k]; rem = v.rem_sm[k]; } else { kd = v.kd_ovf[k - RAMP_F_CAP]; rem = v.rem_ovf[k - RAMP_F_CAP]; }
+    if (k < FC) { kd = v.kd_sm[k]; rem = v.rem_sm[k]; } else { kd = v.kd_ovf[k - FC]; rem = v.rem_ovf[k - FC]; }
 }
+template <int FC = RAMP_F_CAP>
 __device__ __forceinline__ void f_put(const FrontView& v, int k, unsigned long long kd, double rem) {
-    if (k < RAMP_F_CAP) { v.kd_sm[k] = kd; v.rem_sm[k] = rem; } else { v.kd_ovf[k - RAMP_F_CAP] = kd; v.rem_ovf[k - RAMP_F_CAP] = rem; }
+    if (k < FC) { v.kd_sm[k] = kd; v.rem_sm[k] = rem; } else { v.kd_ovf[k - FC] = kd; v.rem_ovf[k - FC] = rem; }
 }
 
 // parent counter of op `child` += 1, returns the new value (JOB:530).  Small jobs keep one BYTE per op in shared memory
@@ -319,33 +325,35 @@ __device__ __forceinline__ uint32_t par_inc(bool in_smem, uint32_t* par_sm, uint
 }
 
 // bytes of shared memory one lookahead warp needs
-__host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap, int par_cap) {
+__host__ __device__ inline size_t lookahead_smem_per_warp(int w_cap, int c_cap, int par_cap, int f_cap = RAMP_F_CAP, int ops_cap = RAMP_OPS_CAP) {
     size_t b = 0;
-    b += (size_t)2 * RAMP_OPS_CAP * 16;          // op records a (ping-pong)
-    b += (size_t)RAMP_F_CAP * 8 * 2;             // kd, rem
+    b += (size_t)2 * ops_cap * 16;               // op records a (ping-pong)
+    b += (size_t)f_cap * 8 * 2;                  // kd, rem
     b += (size_t)RAMP_NF_CAP * 8;                // ready non-flow deps
-    b += (size_t)2 * RAMP_OPS_CAP * 8;           // op records b
+    b += (size_t)2 * ops_cap * 8;                // op records b
     b += (size_t)(w_cap + 2 * c_cap) * 4;        // wkey, ckey (this tick / next tick)
     b += (size_t)par_cap;                        // parent counters (bytes)
     return (b + 15) & ~(size_t)15;
 }
 
-template <int WPB>
+// FC / OC: flow-frontier entries / op-frontier records kept in shared memory per warp.  The engine instantiates a roomy
+// shape (384 / 48: 12 warps per SM) and a dense one (256 / 32: 16 warps per SM) for steps with far more lookaheads than slots
+template <int WPB, int FC = RAMP_F_CAP, int OC = RAMP_OPS_CAP>
 __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const LookaheadArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned char* my_smem = smem_raw + (size_t)warp * lookahead_smem_per_warp(a.w_cap, a.c_cap, a.par_cap);
+    unsigned char* my_smem = smem_raw + (size_t)warp * lookahead_smem_per_warp(a.w_cap, a.c_cap, a.par_cap, FC, OC);
     // layout by decreasing alignment: int4 | 8-byte arrays | 4-byte arrays
-    int4* ops_a_sm0 = reinterpret_cast<int4*>(my_smem);                                  // [2][RAMP_OPS_CAP]
+    int4* ops_a_sm0 = reinterpret_cast<int4*>(my_smem);                                  // [2][OC]
     FrontView fr;
-    fr.kd_sm = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * RAMP_OPS_CAP);      // [RAMP_F_CAP]
-    fr.rem_sm = reinterpret_cast<double*>(fr.kd_sm + RAMP_F_CAP);                        // [RAMP_F_CAP]
-    unsigned long long* nf_sm = reinterpret_cast<unsigned long long*>(fr.rem_sm + RAMP_F_CAP);   // [RAMP_NF_CAP]
-    int2* ops_b_sm0 = reinterpret_cast<int2*>(nf_sm + RAMP_NF_CAP);                      // [2][RAMP_OPS_CAP]
-    uint32_t* wkey = reinterpret_cast<uint32_t*>(ops_b_sm0 + 2 * RAMP_OPS_CAP);          // [w_cap] best key among the ready ops on the worker
+    fr.kd_sm = reinterpret_cast<unsigned long long*>(ops_a_sm0 + 2 * OC);      // [FC]
+    fr.rem_sm = reinterpret_cast<double*>(fr.kd_sm + FC);                        // [FC]
+    unsigned long long* nf_sm = reinterpret_cast<unsigned long long*>(fr.rem_sm + FC);   // [RAMP_NF_CAP]
+    int2* ops_b_sm0 = reinterpret_cast<int2*>(nf_sm + RAMP_NF_CAP);                      // [2][OC]
+    uint32_t* wkey = reinterpret_cast<uint32_t*>(ops_b_sm0 + 2 * OC);          // [w_cap] best key among the ready ops on the worker
     uint32_t* ckey0 = wkey + a.w_cap;                                                    // [2][c_cap] best key among the ready flows on the channel
     uint32_t* par_sm = ckey0 + 2 * a.c_cap;                                              // [par_cap / 4] byte parent counters
 
@@ -386,10 +394,10 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
         uint32_t* ck_nxt = ckey0 + a.c_cap;   // being built for the next tick (all zero at the start of a tick)
         OpsView ops, ops_n;
         ops.a_sm = ops_a_sm0; ops.b_sm = ops_b_sm0; ops.a_ovf = sv.ops_a_ovf[0]; ops.b_ovf = sv.ops_b_ovf[0];
-        ops_n.a_sm = ops_a_sm0 + RAMP_OPS_CAP; ops_n.b_sm = ops_b_sm0 + RAMP_OPS_CAP; ops_n.a_ovf = sv.ops_a_ovf[1]; ops_n.b_ovf = sv.ops_b_ovf[1];
+        ops_n.a_sm = ops_a_sm0 + OC; ops_n.b_sm = ops_b_sm0 + OC; ops_n.a_ovf = sv.ops_a_ovf[1]; ops_n.b_ovf = sv.ops_b_ovf[1];
         for (int k = lane; k < T.n_src; k += 32) {
             const int op = __ldg(&T.src_ops[k]);
-            ops_put(ops, k, __ldg(&t_op_rec[op]), __ldg(&t_op_row[op]));          // RCE:1334
+            ops_put<OC>(ops, k, __ldg(&t_op_rec[op]), __ldg(&t_op_row[op]));          // RCE:1334
         }
         __syncwarp();
 
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             // ---- A ----
             for (int k = lane; k < nO; k += 32) {
                 int4 ra; int2 rb;
-                ops_get(ops, k, ra, rb);
+                ops_get<OC>(ops, k, ra, rb);
                 atomicMax(&wkey[ra.w], (uint32_t)ra.z);
             }
             __syncwarp();
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                 int j = 0;
                 for (int k = lane; k < nO; k += 32, ++j) {
                     int4 ra; int2 rb;
-                    ops_get(ops, k, ra, rb);
+                    ops_get<OC>(ops, k, ra, rb);
                     if (wkey[ra.w] == (uint32_t)ra.z) {
                         if (j < 32) win_mask |= 1u << j;
                         ++na;
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                 double md = INF;
                 for (int k = lane; k < nF; k += 32) {
                     unsigned long long kd; double rem;
-                    f_get(fr, k, kd, rem);
+                    f_get<FC>(fr, k, kd, rem);
                     const uint32_t c = (uint32_t)(kd >> csh) & cmask;
                     if (c != cmask && ck_cur[c] == ((uint32_t)kd & kmask)) md = (rem < md) ? rem : md;
                 }
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     }
                     const bool readied = valid && (cnt == np);                                   // JOB:531 (fires once)
                     const unsigned m = __ballot_sync(FULL, readied);
-                    if (readied) ops_put_child(ops_n, nO_next + __popc(m & lt_mask), child);
+                    if (readied) ops_put_child<OC>(ops_n, nO_next + __popc(m & lt_mask), child);
                     nO_next += __popc(m);
                 }
                 deps_completed += nNF;
@@ -505,7 +513,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     unsigned long long kd = 0ull;
                     double rem = 1.0;
                     if (INSM) { if (valid) { kd = fr.kd_sm[k]; rem = fr.rem_sm[k]; } }
-                    else { if (valid) f_get(fr, k, kd, rem); }
+                    else { if (valid) f_get<FC>(fr, k, kd, rem); }
                     const double r2 = tick_down(rem, tick);                                         // JOB:561
                     const bool done = valid && (r2 == 0.0);                                         // JOB:562
                     const bool keep = valid && !done;
@@ -514,10 +522,10 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     const unsigned dmask = __ballot_sync(FULL, done);
                     if (dmask == 0u) {
                         if (p == kb) {                                 // nothing before it died either: update in place
-                            if (valid) { if (INSM) fr.rem_sm[k] = r2; else if (k < RAMP_F_CAP) fr.rem_sm[k] = r2; else fr.rem_ovf[k - RAMP_F_CAP] = r2; }
+                            if (valid) { if (INSM) fr.rem_sm[k] = r2; else if (k < FC) fr.rem_sm[k] = r2; else fr.rem_ovf[k - FC] = r2; }
                         } else {
                             __syncwarp();                              // all lanes have read before anything is written over
-                            if (valid) { if (INSM) { fr.kd_sm[p + lane] = kd; fr.rem_sm[p + lane] = r2; } else f_put(fr, p + lane, kd, r2); }
+                            if (valid) { if (INSM) { fr.kd_sm[p + lane] = kd; fr.rem_sm[p + lane] = r2; } else f_put<FC>(fr, p + lane, kd, r2); }
                         }
                         p += n_here;                                   // warp-uniform: every valid entry of the group survives
                     } else {
@@ -535,17 +543,17 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                         __syncwarp();
                         if (keep) {
                             const int q = p + __popc(mk & lt_mask);
-                            if (INSM) { fr.kd_sm[q] = kd; fr.rem_sm[q] = r2; } else f_put(fr, q, kd, r2);
+                            if (INSM) { fr.kd_sm[q] = kd; fr.rem_sm[q] = r2; } else f_put<FC>(fr, q, kd, r2);
                         }
                         p += __popc(mk);
                         const bool readied = done && (cnt == np);                                    // JOB:531 (fires once)
                         const unsigned m = __ballot_sync(FULL, readied);
-                        if (readied) ops_put_child(ops_n, nO_next + __popc(m & lt_mask), child);
+                        if (readied) ops_put_child<OC>(ops_n, nO_next + __popc(m & lt_mask), child);
                         nO_next += __popc(m);
                     }
                 };
                 const int n_full = nF & ~31;                           // entries covered by full groups
-                const int n_full_sm = (n_full < RAMP_F_CAP) ? n_full : RAMP_F_CAP;   // RAMP_F_CAP is a multiple of 32
+                const int n_full_sm = (n_full < FC) ? n_full : FC;   // FC is a multiple of 32
                 int kb = 0;
                 for (; kb < n_full_sm; kb += 32) h_group(std::true_type{}, std::true_type{}, kb);
                 for (; kb < nF; kb += 32) h_group(std::false_type{}, std::false_type{}, kb);
@@ -558,13 +566,13 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
             int4 rdy_a = make_int4(0, 0, 0, 0);
             int2 rdy_b = make_int2(0, 0);
             if (lane < n_ready) {
-                const int child = ops_get_child(ops_n, lane);
+                const int child = ops_get_child<OC>(ops_n, lane);
                 rdy_a = __ldg(&t_op_rec[child]);
                 rdy_b = __ldg(&t_op_row[child]);
             }
             for (int k = 32 + lane; k < n_ready; k += 32) {
-                const int child = ops_get_child(ops_n, k);
-                ops_put(ops_n, k, __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
+                const int child = ops_get_child<OC>(ops_n, k);
+                ops_put<OC>(ops_n, k, __ldg(&t_op_rec[child]), __ldg(&t_op_row[child]));
             }
 
             // ---- G: tick the op winners; rows of the completed ops are appended at [p, tail) ----
@@ -579,7 +587,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     int2 rb = make_int2(0, 0);
                     bool done = false;
                     if (valid) {
-                        ops_get(ops, k, ra, rb);
+                        ops_get<OC>(ops, k, ra, rb);
                         bool win;
                         if (big_ops) win = wkey[ra.w] == (uint32_t)ra.z;
                         else { win = ((win_mask >> j) & 1u) != 0u; wkey[ra.w] = 0u; }   // release the winner slot
@@ -591,7 +599,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     }
                     const bool keep = valid && !done;
                     const unsigned km_ = __ballot_sync(FULL, keep);
-                    if (keep) ops_put(ops_n, nO_next + __popc(km_ & lt_mask), ra, rb);
+                    if (keep) ops_put<OC>(ops_n, nO_next + __popc(km_ & lt_mask), ra, rb);
                     nO_next += __popc(km_);
                     const unsigned dm = __ballot_sync(FULL, done);
                     if (dm) {
@@ -639,7 +647,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                                 const unsigned fm = __ballot_sync(FULL, flow);
                                 const unsigned nm = __ballot_sync(FULL, valid && !flow);
                                 if (flow) {
-                                    f_put(fr, tail + __popc(fm & lt_mask), kd[u], rt[u]);
+                                    f_put<FC>(fr, tail + __popc(fm & lt_mask), kd[u], rt[u]);
                                     const uint32_t c = (uint32_t)(kd[u] >> csh) & cmask;
                                     if (c != cmask) atomicMax(&ck_vote[c], (uint32_t)kd[u] & kmask);
                                 } else if (valid) {
@@ -653,7 +661,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
                     }
                 }
             }
-            if (lane < n_ready) ops_put(ops_n, lane, rdy_a, rdy_b);
+            if (lane < n_ready) ops_put<OC>(ops_n, lane, rdy_a, rdy_b);
             if (big_ops) { __syncwarp(); for (int i = lane; i < W; i += 32) wkey[i] = 0u; }
             nNF = nNF_next;
             __syncwarp();

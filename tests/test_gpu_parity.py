@@ -148,16 +148,24 @@ def test_episode_replay_vs_reference_golden(fname, memo_mode, eng_mod):
     eng.close()
 
 
+@pytest.mark.parametrize('shape', ['roomy', 'dense'])
 @pytest.mark.parametrize('fname', FILES)
-def test_episode_replay_vs_oracle_bit_exact(fname, eng_mod, oracle_lib):
-    """Same replay, CUDA vs CPU oracle: every step_stats entry and job record identical (bit-exact f64)."""
+def test_episode_replay_vs_oracle_bit_exact(fname, shape, eng_mod, oracle_lib):
+    """Same replay, CUDA vs CPU oracle: every step_stats entry and job record identical (bit-exact f64).  'dense' forces the
+    warp kernel's 16-warps-per-SM shape (smaller shared-memory frontiers) that steps with far more lookaheads than slots use."""
+    import os
     from ddls_b200.engine import action_row
     g = Golden(fname)
     arr = g.arrivals()
     env = oracle_lib.OracleEnv(g.n_cluster_workers, max_jobs=len(arr), memo_models=max(g.n_models, 1))
     env.reset(arr, max_simulation_run_time=g.max_sim_time)
-    eng = eng_mod.RampEngine(n_episodes=2, n_cluster_workers=g.n_cluster_workers, max_jobs=len(arr),
-                             max_simulation_run_time=g.max_sim_time, trace_cap=1 << 16)
+    if shape == 'dense':
+        os.environ['RAMP_DENSE_FACTOR'] = '0'
+    try:
+        eng = eng_mod.RampEngine(n_episodes=2, n_cluster_workers=g.n_cluster_workers, max_jobs=len(arr),
+                                 max_simulation_run_time=g.max_sim_time, trace_cap=1 << 16)
+    finally:
+        os.environ.pop('RAMP_DENSE_FACTOR', None)
     tids = [eng.register_template(t) for t in g.templates]
     eng.reset(np.stack([arr, arr]))
     for s in range(g.n_steps):
