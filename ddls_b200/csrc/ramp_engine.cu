@@ -61,6 +61,7 @@ LookaheadKernel lookahead_dense_kernel() { return ramp_lookahead_kernel<DENSE_NT
 LookaheadKernel lookahead_cta_kernel_for(int nt) {   // one CTA of nt threads per lookahead
     switch (nt) {
         case 64: return ramp_lookahead_cta_kernel<2>;
+        case 256: return ramp_lookahead_cta_kernel<8>;
         case 128: return ramp_lookahead_cta_kernel<4>;
         default: return nullptr;
     }
@@ -120,9 +121,12 @@ struct ramp_engine {
     double dense_factor = 2.0;   // the dense shape runs a step's lookaheads when there are more than dense_factor x warp slots
     int cta_grid = 0;            // resident CTAs of the 128-thread variant
     int cta64_grid = 0;          // resident CTAs of the 64-thread variant
+    int cta256_grid = 0;         // resident CTAs of the 256-thread variant
+    int cta_grid_for(int nt) const { return nt == 256 ? cta256_grid : nt == 128 ? cta_grid : cta64_grid; }
     size_t cta_smem_bytes = 0;
     int split_warp_nt = 32;      // threads per CTA of the warp kernel when it runs beside a CTA kernel
     size_t smem2_bytes = 0;      // dynamic shared memory of the 2-warp CTAs used beside a CTA kernel
+    int use_cta256 = 1;          // RAMP_USE_CTA256=0 turns off: 256-thread CTAs for the big lookaheads when 8 n_big + n_small fit the warp slots
     double split_alpha = 1.3;    // 64-thread-CTA split while 2 n_big + n_small <= split_alpha x resident warp slots
     int debug = 0;               // RAMP_DEBUG=1 prints the per-step launch decisions to stderr
     int mode = 0;                // 0 auto, 1 warp-per-lookahead, 2 CTA-per-lookahead (RAMP_LOOKAHEAD_MODE)
@@ -217,14 +221,14 @@ int ensure_scratch(ramp_engine* e) {
     if (cta_smem > 200 * 1024)
         return set_error(RAMP_ERR_CAPACITY, "a template needs %zu B of shared memory (max 200 KiB)", cta_smem);
     if (cta_smem != e->cta_smem_bytes || e->cta_grid == 0) {
-        for (int nt : {128, 64}) {
+        for (int nt : {256, 128, 64}) {
             LookaheadKernel kern = lookahead_cta_kernel_for(nt);
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, RAMP_SMEM_CARVEOUT));
             int occ = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, cta_smem));
             if (occ < 1) occ = 1;
-            (nt == 128 ? e->cta_grid : e->cta64_grid) = e->sm_count * occ;
+            (nt == 256 ? e->cta256_grid : nt == 128 ? e->cta_grid : e->cta64_grid) = e->sm_count * occ;
         }
         e->cta_smem_bytes = cta_smem;
     }
@@ -272,12 +276,12 @@ void launch_lookahead(ramp_engine* e, const LookaheadArgs& a, int n_items, int n
     int cta_nt = 0;
     if (e->mode == 2) cta_nt = e->cta_nt ? e->cta_nt : (n_items <= e->cta_grid ? 128 : 64);
     else if (e->mode != 1 && n_big > 0) {
-        if (e->cta_nt) { if (n_items <= (e->cta_nt == 128 ? e->cta_grid : e->cta64_grid)) cta_nt = e->cta_nt; }
+        if (e->cta_nt) { if (n_items <= e->cta_grid_for(e->cta_nt)) cta_nt = e->cta_nt; }
         else if (n_items <= e->cta_grid) cta_nt = 128;
         else if (n_items <= e->cta64_grid) cta_nt = 64;
     }
     if (cta_nt) {
-        const int grid = std::max(1, std::min(cta_nt == 128 ? e->cta_grid : e->cta64_grid, n_items));
+        const int grid = std::max(1, std::min(e->cta_grid_for(cta_nt), n_items));
         lookahead_cta_kernel_for(cta_nt)<<<grid, cta_nt, e->cta_smem_bytes, st>>>(a);
     } else {
         const int wpb = e->nt / 32;
@@ -334,13 +338,14 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     if (const char* v = getenv("RAMP_LOOKAHEAD_CTAS_PER_SM")) e->max_ctas_per_sm = atoi(v);
     if (const char* v = getenv("RAMP_LOOKAHEAD_CTA_THREADS")) {
         const int nt = atoi(v);
-        if (lookahead_cta_kernel_for(nt) == nullptr) { delete e; return set_error(RAMP_ERR_BAD_ARG, "RAMP_LOOKAHEAD_CTA_THREADS must be 64 or 128"); }
+        if (lookahead_cta_kernel_for(nt) == nullptr) { delete e; return set_error(RAMP_ERR_BAD_ARG, "RAMP_LOOKAHEAD_CTA_THREADS must be 64, 128 or 256"); }
         e->cta_nt = nt;
     }
     if (const char* v = getenv("RAMP_LOOKAHEAD_MODE")) e->mode = !strcmp(v, "warp") ? 1 : !strcmp(v, "cta") ? 2 : 0;
     if (const char* v = getenv("RAMP_BIG_THRESHOLD")) e->big_threshold = atoll(v);
     if (const char* v = getenv("RAMP_DEBUG")) e->debug = atoi(v);
     if (const char* v = getenv("RAMP_SPLIT_ALPHA")) e->split_alpha = atof(v);
+    if (const char* v = getenv("RAMP_USE_CTA256")) e->use_cta256 = atoi(v);
     if (const char* v = getenv("RAMP_DENSE_FACTOR")) e->dense_factor = atof(v);
     if (const char* v = getenv("RAMP_SPLIT_WARP_THREADS")) {
         const int nt = atoi(v);
@@ -630,21 +635,23 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
             const int wpb = e->nt / 32;
             const int warp_slots = e->grid * wpb;
             // The big lookaheads set the step's latency, the small ones its load.  While everything fits the SMs' warp slots
-            // at once (registers cap every mix at cta_grid x 4 warps) each big lookahead gets a 128-thread CTA; while the big
+            // at once (registers cap every mix at cta_grid x 4 warps) each big lookahead gets a 256-thread CTA if 8 warps per
+            // big one still fit (2.4 ms instead of 2.9 ms for the bench job), else a 128-thread CTA; while the big
             // ones still fit as 64-thread CTAs and the small ones need at most a short second wave they get those; beyond
             // that everything goes through the warp kernel, the big list first (longest-processing-time-first keeps the
             // tail short).  The CTA kernel runs on a second stream beside the warp kernel for the small list.
             const int reg_slots = e->cta_grid * 4;
             int split_nt = 0;
             if (e->mode != 1 && n_big > 0) {
-                if (n_big <= e->cta_grid && 4 * n_big + n_small <= reg_slots) split_nt = 128;
+                if (e->use_cta256 && n_big <= e->cta256_grid && 8 * n_big + n_small <= reg_slots) split_nt = 256;
+                else if (n_big <= e->cta_grid && 4 * n_big + n_small <= reg_slots) split_nt = 128;
                 else if (n_big <= e->cta64_grid && 2 * n_big + n_small <= (int)(e->split_alpha * reg_slots)) split_nt = 64;
             }
             const bool split = split_nt != 0;
             if (e->debug) fprintf(stderr, "[ramp] step lookaheads: small=%d big=%d warp_slots=%d reg_slots=%d -> %s %d\n", n_small, n_big,
                                   warp_slots, reg_slots, split ? "split (CTA || warp), CTA threads" : "single warp kernel, big first", split_nt);
             if (split) {
-                const int cgrid = split_nt == 128 ? e->cta_grid : e->cta64_grid;
+                const int cgrid = e->cta_grid_for(split_nt);
                 const int grid = std::min(n_big, cgrid);
                 // `st` is idle here (synchronised for the read-back above), so the second stream needs no fork event and the
                 // CTA kernel's blocks are always placed before the warp kernel's
