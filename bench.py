@@ -421,7 +421,7 @@ def _scratch_gb(wl):
 
 
 def _template_mb(wl):
-    return int(sum(26 * t.n_ops + 20 * t.n_deps for t in wl.templates) / 1e6) + 1
+    return int(sum(26 * t.n_ops + 16 * t.n_deps for t in wl.templates) / 1e6) + 1
 
 
 def cpu_baseline(args, wl_gpu):

@@ -486,16 +486,10 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
         op_row[(size_t)i * 2] = j->row_ptr[i];
         op_row[(size_t)i * 2 + 1] = j->row_ptr[i + 1] - j->row_ptr[i];
     }
-    std::vector<unsigned long long> dep_km(E);
     int32_t max_in_deg = 0;
     for (int32_t i = 0; i < N; ++i) max_in_deg = std::max(max_in_deg, in_deg[i]);
     const bool par_in_smem = (max_in_deg <= 255 && N <= 8192);       // byte parent counters in shared memory
-    for (int32_t k = 0; k < E; ++k)
-        dep_km[k] = (unsigned long long)dep_key[k] | ((unsigned long long)j->dep_channel[k] << 32)
-                    | ((unsigned long long)(j->dep_is_flow[k] ? 1 : 0) << 48)
-                    | (par_in_smem ? ((unsigned long long)j->op_n_parents[j->dep_dst[k]] << 49) : 0ull);
-
-    // the whole dep in one word for the warp kernel's 16-byte frontier entries (TemplateDev::dep_kd)
+    // the whole dep in one word for the kernels' 16-byte frontier entries (TemplateDev::dep_kd)
     auto bits_for = [](uint64_t max_value) { int b = 1; while ((max_value >> b) != 0) ++b; return b; };
     const int kbits = bits_for((uint64_t)std::max(E, 1));                 // keys are 1..E, 0 = "none"
     const int cbits = bits_for((uint64_t)C + 1);                          // channels 0..C-1, all ones = "none"
@@ -516,11 +510,10 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
 
     // ---- pack one blob ----
     struct Seg { const void* p; size_t bytes; size_t off; };
-    Seg segs[8] = {
+    Seg segs[6] = {
         {op_rec.data(), sizeof(OpRec) * (size_t)N, 0}, {j->op_n_parents, sizeof(uint16_t) * (size_t)N, 0},
-        {op_row.data(), sizeof(int32_t) * op_row.size(), 0}, {dep_km.data(), sizeof(unsigned long long) * (size_t)E, 0},
-        {dep_rt.data(), sizeof(double) * (size_t)E, 0}, {j->dep_dst, sizeof(int32_t) * (size_t)E, 0},
-        {src.data(), sizeof(int32_t) * src.size(), 0}, {dep_kd.data(), sizeof(unsigned long long) * (size_t)E, 0}};
+        {op_row.data(), sizeof(int32_t) * op_row.size(), 0}, {dep_kd.data(), sizeof(unsigned long long) * (size_t)E, 0},
+        {dep_rt.data(), sizeof(double) * (size_t)E, 0}, {src.data(), sizeof(int32_t) * src.size(), 0}};
     size_t total = 0;
     for (auto& s : segs) { s.off = total; total += align_up(std::max<size_t>(s.bytes, 1), 256); }
     HostTemplate ht;
@@ -545,10 +538,8 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     d.par_in_smem = par_in_smem ? 1 : 0;
     d._pad0 = 0;
     d.op_rec = (const int4*)(base + segs[0].off); d.op_n_parents = (const uint16_t*)(base + segs[1].off);
-    d.op_row = (const int2*)(base + segs[2].off); d.dep_km = (const unsigned long long*)(base + segs[3].off);
-    d.dep_rt = (const double*)(base + segs[4].off); d.dep_dst = (const int32_t*)(base + segs[5].off);
-    d.src_ops = (const int32_t*)(base + segs[6].off);
-    d.dep_kd = (const unsigned long long*)(base + segs[7].off);
+    d.op_row = (const int2*)(base + segs[2].off); d.dep_kd = (const unsigned long long*)(base + segs[3].off);
+    d.dep_rt = (const double*)(base + segs[4].off); d.src_ops = (const int32_t*)(base + segs[5].off);
     d.kd_kmask = kd_kmask; d.kd_cmask = kd_cmask; d.kd_cshift = kd_cshift; d.kd_fshift = kd_fshift; d.kd_dshift = kd_dshift; d._pad1 = 0;
     d.scratch_bytes = scratch_bytes_for(N, E);
     d.algorithmic_bytes_static = 20ull * (uint64_t)N + 19ull * (uint64_t)E + 24ull;

@@ -29,7 +29,7 @@ namespace ramp {
 // the per-worker / per-channel arg-max is one 32-bit shared-memory atomicMax per item.  Everything a ready
 // item needs is packed into a self-contained record, so the tick loop never gathers through an index:
 //   op record  = { f64 remaining, u32 key, u32 worker } + { i32 first out-edge, i32 out-degree }   (24 B)
-//   dep record = { u32 key | u16 channel | u16 is_flow } + { f64 remaining } + { i32 child op }    (20 B)
+//   dep record = { u64 key | channel | is_flow | n_parents(child) | child op } + { f64 remaining }  (16 B)
 struct TemplateDev {
     int32_t n_ops, n_deps, n_workers, n_channels;
     int32_t num_training_steps, model_id, degree, n_src;
@@ -40,15 +40,13 @@ struct TemplateDev {
     const int4*     op_rec;       // [N] by op index: {cost.lo, cost.hi, key, worker}
     const int2*     op_row;       // [N] by op index: {first out-edge, out-degree} (CSR row)
     const uint16_t* op_n_parents; // [N] by op index (JOB:508-523)
-    const unsigned long long* dep_km;  // [E] by dep index (CSR order): key | channel << 32 | is_flow << 48 | n_parents(child) << 49
-                                       //     (the n_parents byte only when par_in_smem, i.e. every in-degree <= 255)
     const double*   dep_rt;       // [E] by dep index: init_run_time (RCE:542-560)
-    const unsigned long long* dep_kd;  // [E] by dep index: the whole dep in one word (warp kernel):
+    const unsigned long long* dep_kd;  // [E] by dep index (CSR order): the whole dep in one word:
                                        //     key | channel << kd_cshift | is_flow << kd_fshift | n_parents(child) << (kd_fshift+1)
-                                       //     | child op << kd_dshift; channel == kd_cmask means "none" (non-flows)
+                                       //     | child op << kd_dshift; channel == kd_cmask means "none" (non-flows); the n_parents byte
+                                       //     only when par_in_smem, i.e. every in-degree <= 255
     uint32_t kd_kmask, kd_cmask;  // (1 << key bits) - 1, (1 << channel bits) - 1
     int32_t  kd_cshift, kd_fshift, kd_dshift, _pad1;
-    const int32_t*  dep_dst;      // [E] by dep index: child op index
     const int32_t*  src_ops;      // [n_src] ops with in-degree 0: the initial ops_ready (JOB:474-481)
     uint64_t scratch_bytes;       // HBM-side dynamic state one running lookahead of this template may need
     uint64_t algorithmic_bytes_static; // 20 N + 19 E + 24, + 12 T added per run
