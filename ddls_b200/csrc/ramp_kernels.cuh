@@ -203,19 +203,6 @@ __device__ __forceinline__ double tick_down(double rem, double tick) {
     return __dsub_rn(rem, m);
 }
 
-// Warp-aggregated append to a frontier list: one shared-memory atomic per warp.  Must be called by all
-// 32 lanes of the warp convergently.
-__device__ __forceinline__ void warp_push(int32_t* list, int* counter, bool pred, int32_t val) {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = val;
-}
-
 // min over the warp of NON-NEGATIVE doubles (remaining times; +inf = "none"): their u64 bit patterns order like the
 // values, so two 32-bit REDUX.MIN (high word, then low word among the lanes holding the minimal high word) replace a
 // ten-shuffle butterfly
@@ -255,25 +242,27 @@ __device__ __forceinline__ double util_sum(const double* term, int n_rec) {
 //
 // Per tick (letters as in SURVEY.md 3.3):
 //   A  per-worker arg-max over ready ops           -> atomicMax of rank keys into smem wkey[]      (RCE:562-590, 44-67)
-//   B  t_op = min remaining over the op winners    -> butterfly shuffles                            (RCE:592-606)
-//   C  any ready non-flow dep?                      -> a counter kept up to date as deps arrive / complete (RCE:520-540)
-//   D  t_comm = min remaining over the per-channel winners.  The per-channel arg-max (RCE:608-629, 665-689) is
-//      maintained INCREMENTALLY: ckey[c] is the best key among the ready flows on channel c and crem[c] that
-//      flow's remaining time.  A flow that becomes ready does one atomicMax; when a completing flow held its
-//      channel's slot the slots are recomputed from the ready deps.  The tick only scans the C slots. (RCE:653-663)
+//   B  t_op = min remaining over the op winners    -> REDUX.MIN on the f64 bit pattern              (RCE:592-606)
+//   C  any ready non-flow dep?  They sit in their own list: run time zero (RCE:542-560), so each lives for exactly one
+//      tick, and a tick that finds the list non-empty is the reference's zero-length tick (RCE:412-422, 718-731): it
+//      completes exactly those and leaves the flows and the channel winners untouched                  (RCE:520-540)
+//   D  t_comm = min remaining over the per-channel winners.  The per-channel arg-max (RCE:608-629, 665-689) is kept in a
+//      DOUBLE-BUFFERED table: while a tick runs, every flow that survives it and every flow that arrives votes (atomicMax
+//      of its key) into the next tick's table, so the table is always complete and never needs a rescan when a winner
+//      completes.  D is one pass over the ready flows: the winners are the entries whose key equals ck_cur[channel]. (RCE:653-663)
 //   E  tick = min(t_op, t_comm)                                                                     (RCE:426)
-//   H  every dep of the pre-tick snapshot (only the non-flows if C): rem -= min(tick, rem); == 0 -> completed:
-//      atomicAdd on the child's parent counter, == n_parents -> child's op record appended to the next op
-//      frontier.  Survivors are slid down in place, so the frontier never holds dead entries.     (RCE:718-775)
-//   G  op winners: same; completed -> the CSR rows of all ops completed in this tick are appended to the dep
-//      frontier as one flattened, coalesced copy (first ticked next tick == the RCE:429 snapshot). (RCE:691-716)
+//   H  every flow of the pre-tick snapshot: rem -= min(tick, rem); == 0 -> completed: atomicAdd on the child's parent
+//      counter, == n_parents -> the child is readied (its op index is queued; the 24-byte records of all ops readied in
+//      the tick are fetched in ONE batch, the loads overlapping G).  Survivors are slid down in place. (RCE:733-775)
+//   G  op winners: same; completed -> the CSR rows of all ops completed in this tick are appended to the flow frontier /
+//      the non-flow list as one flattened, coalesced copy (first ticked next tick == the RCE:429 snapshot). (RCE:691-716)
 //   I,J lane 0 accumulates t / comm / comp and the trace in tick order                              (RCE:442-445, 777-791)
 #define RAMP_U 4            // batch depth: independent loads in flight per lane per phase
 #ifndef RAMP_OPS_CAP
 #define RAMP_OPS_CAP 48     // op-frontier records kept in shared memory per buffer (overflow goes to HBM)
 #endif
 #ifndef RAMP_F_CAP
-#define RAMP_F_CAP 384      // dep-frontier records kept in shared memory (overflow goes to HBM); sized so that 12 lookahead warps fit an SM
+#define RAMP_F_CAP 384      // flow-frontier entries kept in shared memory (overflow goes to HBM); sized so that 12 lookahead warps fit an SM
 #endif
 
 #ifndef RAMP_NF_CAP
