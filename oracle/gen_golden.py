@@ -172,6 +172,10 @@ CASES = {
     # arrivals far faster than completions: most jobs are blocked (no free workers / JCT above the acceptable one)
     'res16_flood': dict(graphs=[synth.resnet_like_graph(n_blocks=1, stem=1, name='res1s', seed=3, body_per_block=2)], shape=(2, 2, 4),
                         n_jobs=30, max_partitions=4, interarrival=20.0, frac=(0.3, 1.0), actor='sipml', seed=8),
+    # BASELINE.json's job at full size: the bench's ResNet-50-like graph at degree 16 on the 64-worker cluster
+    # (N=5,280 ops, E=132,016 deps, T=1,169 ticks) -- one job, one lookahead of the reference itself
+    'resnet64_deg16_full': dict(graphs=[synth.resnet_like_graph()], shape=(4, 4, 4), n_jobs=1, max_partitions=16,
+                                interarrival=1000.0, frac=(1.0, 1.0), actor='sipml', seed=1),
     'residual32_deg16': dict(graphs=[synth.residual_small_graph()], shape=(4, 4, 2), n_jobs=3, max_partitions=16,
                              interarrival=1000.0, frac=(0.1, 1.0), actor='sipml', seed=1),
 }
