@@ -407,12 +407,29 @@ def run_b200_arm(args, rank, world, local_rank):
                               'e2e': e2e_value * cluster_steps_per_env_step, 'unit': 'RampClusterEnvironment.step calls/s'},
             'memo_shared': shared,
         }
+        if args.config == 'cfg3-resnet50-64w':
+            line['python_reference'] = python_reference_note()
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args, wl)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def python_reference_note():
+    """The unmodified Python reference cannot run on the GPU box; its speed on this config's job at degree 16 was measured once
+    in the build container when the full-size golden fixture was generated (oracle/gen_golden.py) and travels in the fixture."""
+    p = os.path.join(ROOT, 'tests', 'golden', 'resnet64_deg16_full.npz')
+    try:
+        d = np.load(p)
+        wall, n = float(d['meta_reference_wall_s']), int(d['meta_n_env_steps'])
+        return {'value': n / wall, 'unit': UNIT, 'cores': 1,
+                'source': 'tests/golden/resnet64_deg16_full.npz: RampJobPartitioningEnvironment.step of the unmodified reference, '
+                          '%d env-step(s) in %.1f s, 64-worker RAMP, ResNet-50-like job at degree 16 (N=5,280, E=132,016), one CPU '
+                          'process in the build container; informational, not the reference arm' % (n, wall)}
+    except Exception:
+        return None
 
 
 def _scratch_gb(wl):
