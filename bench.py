@@ -53,7 +53,8 @@ def parse_args():
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): NVML when importable,
+    else the nvidia-smi query line."""
 
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -63,9 +64,31 @@ class ClockSampler(threading.Thread):
         self.gpu_index, self.period = gpu_index, period
         self.samples, self._stop_evt = [], threading.Event()
 
+    def _nvml(self):
+        """NVML handle for fast sampling (a 100 ms timed region gets ~1 nvidia-smi sample but tens of NVML ones)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        except Exception:
+            return None, None
+
     def run(self):
+        nv, h = self._nvml()
         while not self._stop_evt.is_set():
             try:
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    act = lambda bit: 'Active' if (r & bit) else 'Not Active'
+                    # bits: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+                    self.samples.append([str(sm), str(mx), '', act(0x8), act(0x40), act(0x20), act(0x4)])
+                    self._stop_evt.wait(0.01)
+                    continue
                 out = subprocess.run(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
                                       str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
