@@ -64,3 +64,23 @@ def test_lowering_rejects_unsupported_inputs():
     del action2.actions['op_placement'].action[0][some_op]
     with pytest.raises(Exception, match='no worker'):
         lower_job(cluster, action2, 0)
+
+
+def test_synthetic_builder_matches_reference_pipeline_structure():
+    """The bench's synthetic Action generator (ddls_b200/template_builder.py) against the template the unmodified reference
+    pipeline (OpPartition -> RampFirstFitOpPlacer -> SRPT schedulers -> FirstFitDepPlacer, lowered by lower_job) produced for
+    the same graph at degree 16 on an empty 64-worker cluster (tests/golden/resnet64_deg16_full.npz): the partitioned graph,
+    op costs, parent counts, job-local placement, op priorities and the flow / non-flow split are IDENTICAL; only the dep
+    run times (the reference's collective formulas, actions/utils.py:40-99, are not restated) and the priorities derived
+    from them differ."""
+    import numpy as np
+    from golden_io import Golden
+    from ddls_b200 import synth
+    from ddls_b200.template_builder import build_template, RampShape
+    ref = Golden('resnet64_deg16_full').templates[0]
+    mine = build_template(synth.resnet_like_graph(), 16, RampShape(4, 4, 4))
+    assert (mine.n_ops, mine.n_deps, mine.n_workers, mine.n_channels) == (ref.n_ops, ref.n_deps, ref.n_workers, ref.n_channels)
+    for f in ('row_ptr', 'dep_dst', 'op_cost', 'op_n_parents', 'op_worker', 'op_prio', 'dep_is_flow'):
+        np.testing.assert_array_equal(np.asarray(getattr(mine, f)), np.asarray(getattr(ref, f)), err_msg=f)
+    nonflow = np.asarray(ref.dep_is_flow) == 0
+    assert (np.asarray(mine.dep_run_time)[nonflow] == 0).all() and (np.asarray(ref.dep_run_time)[nonflow] == 0).all()
