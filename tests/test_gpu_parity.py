@@ -411,3 +411,24 @@ def test_register_rejects_non_flow_dep_with_run_time(eng_mod):
     with pytest.raises(Exception, match='non-flow dep'):
         eng.register_template(t)
     eng.close()
+
+
+@pytest.mark.parametrize('cta_threads,M', [('128', 4500), ('256', 9000)])
+def test_op_frontier_larger_than_a_cta_can_mask(cta_threads, M, eng_mod, oracle_lib):
+    """More ready ops than 32 per thread of the CTA (the per-thread winner bit mask runs out: the kernel falls back to
+    re-reading the per-worker arg-max slots and clears them with an extra pass)."""
+    import os
+    t = _fan_template(M, 6, seed=M)
+    want = oracle_lib.run_lookahead(t)
+    os.environ['RAMP_LOOKAHEAD_MODE'] = 'cta'
+    os.environ['RAMP_LOOKAHEAD_CTA_THREADS'] = cta_threads
+    try:
+        eng = eng_mod.RampEngine(n_episodes=1, n_cluster_workers=8, max_jobs=1, trace_cap=1 << 15)
+    finally:
+        os.environ.pop('RAMP_LOOKAHEAD_MODE', None)
+        os.environ.pop('RAMP_LOOKAHEAD_CTA_THREADS', None)
+    tid = eng.register_template(t)
+    res, _ = eng.run_lookaheads(np.full(3, tid, dtype=np.int32))
+    assert (res['status'] == 0).all() and (res['n_ticks'] == want['n_ticks']).all()
+    assert (res['jct'] == want['jct']).all() and (res['comm'] == want['comm']).all() and (res['comp'] == want['comp']).all()
+    eng.close()
