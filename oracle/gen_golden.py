@@ -176,6 +176,12 @@ CASES = {
     # (N=5,280 ops, E=132,016 deps, T=1,169 ticks) -- one job, one lookahead of the reference itself
     'resnet64_deg16_full': dict(graphs=[synth.resnet_like_graph()], shape=(4, 4, 4), n_jobs=1, max_partitions=16,
                                 interarrival=1000.0, frac=(1.0, 1.0), actor='sipml', seed=1),
+    'resnet64_deg8_full': dict(graphs=[synth.resnet_like_graph()], shape=(4, 4, 4), n_jobs=1, max_partitions=8,
+                               interarrival=1000.0, frac=(1.0, 1.0), actor='sipml', seed=1),
+    'resnet64_deg4_full': dict(graphs=[synth.resnet_like_graph()], shape=(4, 4, 4), n_jobs=1, max_partitions=4,
+                               interarrival=1000.0, frac=(1.0, 1.0), actor='sipml', seed=1),
+    'resnet64_deg2_full': dict(graphs=[synth.resnet_like_graph()], shape=(4, 4, 4), n_jobs=1, max_partitions=2,
+                               interarrival=1000.0, frac=(1.0, 1.0), actor='sipml', seed=1),
     'residual32_deg16': dict(graphs=[synth.residual_small_graph()], shape=(4, 4, 2), n_jobs=3, max_partitions=16,
                              interarrival=1000.0, frac=(0.1, 1.0), actor='sipml', seed=1),
 }
