@@ -257,7 +257,9 @@ __device__ __forceinline__ double util_sum(const double* term, int n_rec) {
 //   G  op winners: same; completed -> the CSR rows of all ops completed in this tick are appended to the flow frontier /
 //      the non-flow list as one flattened, coalesced copy (first ticked next tick == the RCE:429 snapshot). (RCE:691-716)
 //   I,J lane 0 accumulates t / comm / comp and the trace in tick order                              (RCE:442-445, 777-791)
-#define RAMP_U 4            // batch depth: independent loads in flight per lane per phase
+#ifndef RAMP_U
+#define RAMP_U 2            // batch depth: independent loads in flight per lane per phase (2 measured best on B200: 4 -1.2 %, 8 -7 %)
+#endif
 #ifndef RAMP_OPS_CAP
 #define RAMP_OPS_CAP 48     // op-frontier records kept in shared memory per buffer (overflow goes to HBM)
 #endif

@@ -3,8 +3,7 @@
 cp ddls_b200/libramp_b200.so /tmp/lib_orig.so
 for lib in build_variants/lib_*.so; do
   cp $lib ddls_b200/libramp_b200.so
-  echo "== $(basename $lib)"
-  timeout 120 python scripts/step_profile.py 2>&1 | cut -c1-75 | head -3
-  timeout 120 python bench.py --steps 16 --warmup 8 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']))"
+  echo -n "== $(basename $lib): "
+  timeout 120 python bench.py --steps 32 --warmup 8 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('bench', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value']))"
 done
 cp /tmp/lib_orig.so ddls_b200/libramp_b200.so
