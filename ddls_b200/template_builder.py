@@ -56,8 +56,9 @@ def _sub_id(op, k):
     return f'{op}{chr(97 + k)}'                                   # partitioners/utils.py:76
 
 
-def partition_graph(fwd: ForwardGraph, degree: int, quantum: float):
-    """Returns (nodes: {id(str): (cost, mem)}, edges: {(u, v): size}, n_splits per original op)."""
+def partition_graph(fwd: ForwardGraph, degree: int, quantum: float, with_adjacency: bool = False):
+    """Returns (nodes: {id(str): (cost, mem)}, edges: {(u, v): size}, n_splits per original op); with_adjacency adds the
+    successor / predecessor lists in networkx's adjacency (insertion) order, which the reference's agents iterate in."""
     n = fwd.n
     mem = {}
     cost = {}
@@ -128,17 +129,123 @@ def partition_graph(fwd: ForwardGraph, degree: int, quantum: float):
         if e in size:
             size[e] = sz
     nodes = {k: (cost[k], mem[k]) for k in cost}
+    if with_adjacency:
+        return nodes, size, splits, succ, pred
     return nodes, size, splits
 
 
+# Block of servers RampFirstFitOpPlacer picks for a job of `degree` sub-ops per op on an EMPTY 4x4x4 cluster, in sorted
+# server-id order (probed from the unmodified reference, oracle/gen_golden.py runs; sub-op k goes to the k-th server)
+REFERENCE_BLOCK_4x4x4 = {
+    1: [(0, 0, 0)],
+    2: [(0, 0, 0), (1, 0, 0)],
+    4: [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0)],
+    8: [(c, r, s_) for c in range(2) for r in range(2) for s_ in range(2)],
+    16: [(c, r, 0) for c in range(4) for r in range(4)],
+}
+
+
+def _all_reduce_time(message_size, node_ids, racks, cgs, x, data_rate, latency, io_latency, cont_racks=1):
+    """calc_ramp_all_reduce_collective_communication_run_time (actions/utils.py:40-88), same numpy calls in the same order."""
+    mem_frq, peak, bytes_per_comp = 2e12, 130e12, 2
+
+    def trx(cg, d, J):                                            # effective_trx_per_comm, actions/utils.py:101-106
+        if d == 1:
+            return 0
+        return 1 + (min(cg // J, cg // (d - 1)) - 1)
+
+    def add_time(data_sz, devices):                               # get_parallel_add_comp_time_single, actions/utils.py:108-118
+        n_op = np.ceil(np.log2(devices))
+        n_bytes = (devices + 1) * bytes_per_comp
+        ai = n_op / n_bytes
+        total_ops = n_op * (data_sz / devices) / bytes_per_comp
+        return total_ops / np.min([mem_frq * ai, peak])
+    data_per_tx = data_rate / x
+    sub = [cgs, min(cgs, node_ids), racks, np.ceil(node_ids / x)]
+    bw = [trx(x, d, cont_racks) * data_per_tx for d in sub]
+    msg = [np.ceil(message_size / sub[0])]
+    for i in sub[1:]:
+        msg.append(np.ceil(msg[-1] / i))
+    comm, comp = 0.0, 0.0
+    for step, d in enumerate(sub):
+        if d > 1:
+            comp += add_time(msg[step] * d, d)
+            comm += latency + 2 * io_latency + msg[step] / bw[step]
+    return 2 * comm + comp
+
+
+def reference_dep_run_times(fwd: ForwardGraph, nodes, size, splits, succ, pred, coords_of_op, shape: RampShape):
+    """update_dep_run_times (actions/utils.py:13-393) for one job: deps of a partitioned op whose parent and child servers
+    coincide form an all-reduce collective, the backward sub-ops' mutual sync edges form 2-dep collectives, everything
+    else is a one-to-one transfer; one-to-one times are applied last.  coords_of_op: op id -> (cg, rack, server) of its server.
+    Returns {(u, v): init_run_time}."""
+    n = fwd.n
+    x = shape.c
+    rt = {}
+
+    def collective_time(deps):
+        cgs, racks, nodes_, servers, message = set(), set(), set(), set(), 0
+        for (u, v) in deps:                                       # get_collective_info, actions/utils.py:168-245
+            for op in (u, v):
+                c, r, s_ = coords_of_op[op]
+                cgs.add(c); racks.add(r); nodes_.add(s_); servers.add((c, r, s_))
+            message += size[(u, v)]
+        if len(servers) == 1:
+            return 0
+        return _all_reduce_time(message, len(nodes_), len(racks), len(cgs), x, shape.channel_bandwidth, shape.latency,
+                                shape.io_latency)
+    collectives, one_to_one = [], []
+    for i in range(1, n + 1):
+        b = 2 * n - (i - 1)
+        k = splits[i]
+        if k > 1:
+            fdeps, bdeps, sync, seen = [], [], [], set()
+            for j in range(k):
+                fs = _sub_id(str(i), j)
+                fdeps.extend((fs, v) for v in succ[fs])
+                bs = _sub_id(str(b), j)
+                for p in pred[bs]:
+                    if p in succ[bs]:                             # bidirectional sync edge
+                        if (p, bs) not in seen and (bs, p) not in seen:
+                            sync.append([(p, bs), (bs, p)])
+                            seen.add((p, bs))
+                    else:
+                        bdeps.append((p, bs))
+            for deps in (fdeps, bdeps):
+                if sorted(coords_of_op[u] for (u, _) in deps) == sorted(coords_of_op[v] for (_, v) in deps):
+                    collectives.append(deps)
+                else:
+                    one_to_one.extend(deps)
+            collectives.extend(sync)
+        else:
+            one_to_one.extend((str(i), v) for v in succ[str(i)])
+            one_to_one.extend((p, str(b)) for p in pred[str(b)])
+    for deps in collectives:
+        t = collective_time(deps)
+        for d in deps:
+            rt[d] = t
+    for (u, v) in one_to_one:                                     # set_one_to_one_dep_run_time, actions/utils.py:146-166
+        if coords_of_op[u] == coords_of_op[v] or size[(u, v)] == 0:
+            rt[(u, v)] = 0
+        else:
+            rt[(u, v)] = shape.latency + 2 * shape.io_latency + size[(u, v)] / shape.channel_bandwidth
+    return rt
+
+
 def build_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_start: int = 0, quantum: float = 0.01,
-                   num_training_steps: int = 50, model_id: int = 0, max_acceptable_frac: float = 1.0) -> LoweredJob:
-    """Partition ``fwd`` to ``degree``, place it on workers [block_start, block_start+degree) and lower it."""
+                   num_training_steps: int = 50, model_id: int = 0, max_acceptable_frac: float = 1.0,
+                   run_times: str = 'one_to_one') -> LoweredJob:
+    """Partition ``fwd`` to ``degree``, place it on workers [block_start, block_start+degree) and lower it.
+
+    run_times='one_to_one' (default, the bench's stand-in): every flow takes the one-to-one transfer time.
+    run_times='reference': the reference's update_dep_run_times (collectives) and SRPT dep priorities over ALL deps in graph
+    edge order, on the block RampFirstFitOpPlacer picks on an empty 4x4x4 cluster -- reproduces the reference pipeline's
+    lowered job array for array (tests/test_lowering_roundtrip.py against tests/golden/resnet64_deg*_full.npz)."""
     if degree != 1 and degree % 2 != 0:
         raise Exception(f'Invalid num_partitions={degree}; RAMP placer expects even numbers.')   # op_partition.py:26-27
     if block_start + max(degree, 1) > shape.n_workers:
         raise Exception('worker block does not fit in the cluster')
-    nodes, size, _ = partition_graph(fwd, degree, quantum)
+    nodes, size, splits, succ, pred = partition_graph(fwd, degree, quantum, with_adjacency=True)
     op_ids = sorted(nodes)                                        # string sort == RCE:56
     idx = {op: i for i, op in enumerate(op_ids)}
     N = len(op_ids)
@@ -164,6 +271,19 @@ def build_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_start
     sw, dw = op_worker[src].astype(np.int64), op_worker[dst].astype(np.int64)
     is_flow = ((sw != dw) & (sizes != 0)).astype(np.uint8)        # RCE:531-536 (one worker per server RCE:180)
     run_time = np.where(is_flow == 1, shape.latency + 2 * shape.io_latency + sizes / shape.channel_bandwidth, 0.0)
+    all_dep_order = None
+    if run_times == 'reference':
+        if (shape.c, shape.r, shape.s) != (4, 4, 4) or degree not in REFERENCE_BLOCK_4x4x4 or block_start != 0:
+            raise Exception("run_times='reference' is available for the probed empty-cluster blocks of a 4x4x4 RAMP only")
+        block = REFERENCE_BLOCK_4x4x4[degree]
+        coords_of_op = {o: block[int(op_worker[idx[o]])] for o in op_ids}
+        worker_ids = [f'node_{c}-{r}-{s_}_worker_0' for (c, r, s_) in block[:len(used)]]
+        rt_map = reference_dep_run_times(fwd, nodes, size, splits, succ, pred, coords_of_op, shape)
+        run_time = np.array([float(rt_map[(u, v)]) for (u, v, _) in dep_ids], dtype=np.float64)
+        run_time = np.where(is_flow == 1, run_time, 0.0)          # RCE:542-560
+        dep_index = {(u, v): e for e, (u, v, _) in enumerate(dep_ids)}
+        all_dep_order = [dep_index[(u, v)] for u in nodes for v in succ[u]]    # job.computation_graph.edges order
+        sched_cost = np.array([float(rt_map[(u, v)]) for (u, v, _) in dep_ids], dtype=np.float64)
     W = len(used)
     chan_key = sw * W + dw
     flow_keys = np.unique(chan_key[is_flow == 1])
@@ -185,7 +305,14 @@ def build_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_start
         order = members[np.argsort(-op_cost[members], kind='stable')]
         op_prio[order] = np.arange(len(order))
     dep_prio = np.zeros(E, dtype=np.int64)
-    if len(fl):
+    if all_dep_order is not None:
+        # SRPTDepScheduler (srpt_dep_scheduler.py:14-83): ALL deps in graph edge order, stable descending sort by run time
+        ordered = np.array(all_dep_order, dtype=np.int64)
+        ranked = ordered[np.argsort(-sched_cost[ordered], kind='stable')]
+        prio_all = np.zeros(E, dtype=np.int64)
+        prio_all[ranked] = np.arange(E)
+        dep_prio[fl] = prio_all[fl]                               # the lowering reads priorities of placed flows only
+    elif len(fl):
         order = fl[np.argsort(-run_time[fl], kind='stable')]
         dep_prio[order] = np.arange(len(order))
 

@@ -84,3 +84,33 @@ def test_synthetic_builder_matches_reference_pipeline_structure():
         np.testing.assert_array_equal(np.asarray(getattr(mine, f)), np.asarray(getattr(ref, f)), err_msg=f)
     nonflow = np.asarray(ref.dep_is_flow) == 0
     assert (np.asarray(mine.dep_run_time)[nonflow] == 0).all() and (np.asarray(ref.dep_run_time)[nonflow] == 0).all()
+
+
+@pytest.mark.parametrize('degree', [2, 4, 8, 16])
+def test_reference_run_time_formulas_reproduce_reference_pipeline(degree, oracle_lib):
+    """run_times='reference' restates update_dep_run_times (collective all-reduce / sync / one-to-one, actions/utils.py:13-393)
+    and the SRPT dep schedule: against the job the unmodified reference lowered for the same graph (empty 64-worker cluster)
+    EVERY array is identical except the dep priorities inside groups of equal run time -- the reference breaks those ties in
+    the iteration order of a Python set of strings (DepPlacement.jobdeps, dep_placement.py:16), i.e. by string hash -- and the
+    lookahead on the generated job equals the reference's recorded (jct, comm, comp) and tick trace bit for bit."""
+    import numpy as np
+    from golden_io import Golden
+    from ddls_b200 import synth
+    from ddls_b200.template_builder import build_template, RampShape
+    g = Golden(f'resnet64_deg{degree}_full')
+    ref, la = g.templates[0], g.lookahead(0)
+    mine = build_template(synth.resnet_like_graph(), degree, RampShape(4, 4, 4), run_times='reference')
+    for f in ('row_ptr', 'dep_dst', 'op_cost', 'op_n_parents', 'op_worker', 'op_prio', 'dep_is_flow', 'dep_channel', 'dep_run_time'):
+        np.testing.assert_array_equal(np.asarray(getattr(mine, f)), np.asarray(getattr(ref, f)), err_msg=f)
+    # priorities: both are SRPT orders (non-increasing run time along increasing priority); only the order inside groups
+    # of equal run time (and where the non-flow members of a collective fall inside their group) may differ
+    rt, pm, pr = np.asarray(ref.dep_run_time), np.asarray(mine.dep_prio), np.asarray(ref.dep_prio)
+    flow = np.nonzero(np.asarray(ref.dep_is_flow) == 1)[0]
+    for prio in (pm, pr):
+        along = rt[flow][np.argsort(prio[flow], kind='stable')]
+        assert (np.diff(along) <= 0).all()
+        assert len(np.unique(prio[flow])) == len(flow)
+    out = oracle_lib.run_lookahead(mine)
+    np.testing.assert_array_equal(out['trace_tick'], la['trace_tick'])
+    np.testing.assert_array_equal(out['trace_n_active'], la['trace_n'])
+    assert (out['jct'], out['comm'], out['comp']) == (la['jct'], la['comm'], la['comp'])
