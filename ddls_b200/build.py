@@ -5,13 +5,13 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libramp_b200.so')
-SOURCES = [os.path.join(HERE, 'csrc', 'ramp_engine.cu')]
-DEPS = SOURCES + [os.path.join(HERE, 'csrc', 'ramp_kernels.cuh'),
+SOURCES = [os.path.join(HERE, 'csrc', 'ramp_engine.cu'), os.path.join(HERE, 'csrc', 'ramp_expand.cpp')]
+DEPS = SOURCES + [os.path.join(HERE, 'csrc', 'ramp_kernels.cuh'), os.path.join(HERE, 'csrc', 'ramp_lookahead_cta.cuh'),
                   os.path.join(os.path.dirname(HERE), 'include', 'ramp_b200.h')]
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-fmad=false',            # no FMA contraction: f64 results must equal CPython's
-              '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static']
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off', '-shared', '-cudart', 'static']
 
 
 def nvcc_path():

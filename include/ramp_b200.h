@@ -221,6 +221,39 @@ int64_t ramp_launch_count(ramp_engine_t* eng);
 int ramp_get_lookahead_kernel_time(ramp_engine_t* eng, double* total_ms, int64_t* launches, int64_t* work_items,
                                    int64_t* algorithmic_bytes, int32_t reset);
 
+/* ---- native template expansion: what OpPartition / update_dep_run_times / the SRPT schedulers /
+ * FirstFitDepPlacer compute for ONE job placed on a block of servers (sub-op k of every split op on server k), without
+ * the reference's Python objects.  Replaces RJPE:320-360 + agents/partitioners/utils.py:42-110 + actions/utils.py:13-393 +
+ * srpt_*_scheduler.py for that case; the Python twin is ddls_b200/template_builder.py.  Host-only: needs no GPU. ---- */
+typedef struct {
+    int32_t n_fwd;                /* forward ops 1..n of the un-mirrored job graph (ddls/utils.py:278-340)          */
+    int32_t n_edges;
+    const double*  fwd_cost;      /* [n] forward_compute_time                                                       */
+    const double*  bwd_cost;      /* [n] backward_compute_time                                                      */
+    const double*  act_size;      /* [n] activation_size                                                            */
+    const double*  par_size;      /* [n] parameter_size                                                             */
+    const int32_t* edge_src;      /* [n_edges] 1-based forward op ids                                               */
+    const int32_t* edge_dst;
+} ramp_forward_graph_t;
+
+typedef struct {
+    int32_t n_servers;            /* servers of the block, in sorted server-id order                                */
+    int32_t num_communication_groups;  /* of the whole topology (x in actions/utils.py:40)                          */
+    const int32_t* coords;        /* [n_servers][3] (communication group, rack, server)                             */
+    double channel_bandwidth, latency, io_latency;   /* topologies/ramp.py:27, heuristic_config.yaml:73-82          */
+} ramp_block_t;
+
+enum { RAMP_RUN_TIMES_ONE_TO_ONE = 0, RAMP_RUN_TIMES_REFERENCE = 1 };
+
+/* Fills `out` with malloc'ed arrays (release with ramp_free_expanded_job).  Optional outputs the mount scalars
+ * (ramp_action_t) are summed from -- call once with NULLs to learn n_ops / n_deps: dep_size_out [n_deps] edge sizes,
+ * op_mem_out [n_ops] memory costs, node_order_out [n_ops] op indices in the job graph's node order (the order the
+ * reference's Python sums run in, JOB:224-248). */
+int ramp_expand_template(const ramp_forward_graph_t* graph, int32_t degree, double min_op_run_time_quantum,
+                         const ramp_block_t* block, int32_t run_time_mode, int32_t num_training_steps,
+                         ramp_lowered_job_t* out, double* dep_size_out, double* op_mem_out, int32_t* node_order_out);
+void ramp_free_expanded_job(ramp_lowered_job_t* job);
+
 #ifdef __cplusplus
 }
 #endif

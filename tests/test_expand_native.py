@@ -1,0 +1,62 @@
+"""Native template expansion (include/ramp_b200.h: ramp_expand_template, ddls_b200/csrc/ramp_expand.cpp)
+against its Python twin (ddls_b200/template_builder.py, itself pinned against the reference pipeline's lowered jobs in
+tests/test_lowering_roundtrip.py) and, transitively and directly, against the reference's own fixtures.  Host-only code:
+runs without a GPU."""
+import numpy as np
+import pytest
+
+from golden_io import Golden
+from ddls_b200 import synth
+from ddls_b200.expand import expand_template
+from ddls_b200.template_builder import build_template, RampShape
+
+ARRAYS = ('row_ptr', 'dep_dst', 'op_cost', 'op_n_parents', 'op_worker', 'op_prio', 'dep_is_flow', 'dep_channel',
+          'dep_run_time', 'dep_prio')
+GRAPHS = {
+    'resnet': lambda: synth.resnet_like_graph(n_blocks=4, name='res4'),
+    'residual': synth.residual_small_graph,
+    'chain': lambda: synth.chain_graph(6, 'chain6'),
+    'transformer': lambda: synth.transformer_like_graph(n_layers=2, name='tfm2', seed=9),
+}
+
+
+@pytest.mark.parametrize('mode', ['one_to_one', 'reference'])
+@pytest.mark.parametrize('degree', [1, 2, 4, 8, 16])
+@pytest.mark.parametrize('gname', sorted(GRAPHS))
+def test_native_expansion_equals_python_builder(gname, degree, mode):
+    g = GRAPHS[gname]()
+    shape = RampShape(4, 4, 4)
+    a = build_template(g, degree, shape, run_times=mode)
+    b = expand_template(g, degree, shape, run_times=mode)
+    assert (a.n_ops, a.n_deps, a.n_workers, a.n_channels) == (b.n_ops, b.n_deps, b.n_workers, b.n_channels)
+    for f in ARRAYS:
+        np.testing.assert_array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(b, f)), err_msg=f)     # bit-exact f64
+    assert a.mount == b.mount
+
+
+@pytest.mark.parametrize('block_start', [16, 48])
+def test_native_expansion_other_blocks_and_topologies(block_start):
+    g = synth.residual_small_graph()
+    for shape in (RampShape(4, 4, 4), RampShape(8, 8, 4), RampShape(4, 4, 8)):
+        a = build_template(g, 8, shape, block_start=block_start)
+        b = expand_template(g, 8, shape, block_start=block_start)
+        for f in ARRAYS:
+            np.testing.assert_array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(b, f)), err_msg=f)
+        assert a.mount == b.mount
+
+
+@pytest.mark.parametrize('degree', [2, 4, 8, 16])
+def test_native_expansion_reproduces_reference_lowered_job(degree):
+    """Directly against the job the unmodified reference lowered (empty 64-worker cluster, bench graph): every array but the
+    hash-ordered priority ties inside groups of equal run time (see tests/test_lowering_roundtrip.py)."""
+    ref = Golden(f'resnet64_deg{degree}_full').templates[0]
+    mine = expand_template(synth.resnet_like_graph(), degree, RampShape(4, 4, 4), run_times='reference')
+    for f in ARRAYS[:-1]:
+        np.testing.assert_array_equal(np.asarray(getattr(mine, f)), np.asarray(getattr(ref, f)), err_msg=f)
+
+
+def test_native_expansion_rejects_bad_arguments():
+    with pytest.raises(Exception):
+        expand_template(synth.chain_graph(4, 'c4'), 3, RampShape(2, 2, 2))           # odd degree (op_partition.py:26-27)
+    with pytest.raises(Exception):
+        expand_template(synth.chain_graph(4, 'c4'), 16, RampShape(2, 2, 2))          # block larger than the cluster
