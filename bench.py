@@ -432,6 +432,7 @@ def run_b200_arm(args, rank, world, local_rank):
         }
         if args.config == 'cfg3-resnet50-64w':
             line['python_reference'] = python_reference_note()
+            line['template_expansion'] = template_expansion_note()
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args, wl)
         print(json.dumps(line), flush=True)
@@ -456,6 +457,28 @@ def python_reference_note():
                           'informational, not the reference arm'}
     except Exception:
         return None
+
+
+def template_expansion_note():
+    """Host-side secondary: the native expansion of this config's job into a lowered job, per partition degree,
+    next to the reference's own agents (whole env-step of the unmodified reference, from the fixtures)."""
+    try:
+        from ddls_b200 import synth
+        from ddls_b200.expand import expand_template
+        from ddls_b200.template_builder import RampShape
+        g, shape, out = synth.resnet_like_graph(), RampShape(4, 4, 4), {}
+        for deg in (2, 4, 8, 16):
+            expand_template(g, deg, shape, run_times='reference')
+            t0 = time.perf_counter()
+            for _ in range(3):
+                expand_template(g, deg, shape, run_times='reference')
+            out[deg] = (time.perf_counter() - t0) / 3 * 1e3
+        ref = python_reference_note() or {}
+        return {'native_ms_by_degree': out, 'reference_env_step_s_by_degree': ref.get('seconds_per_env_step_by_degree'),
+                'what': 'ramp_expand_template (host C++; partition + dep run times + SRPT priorities + channels -> lowered job, '
+                        'bit-identical to the reference pipeline up to hash-ordered priority ties, tests/test_expand_native.py)'}
+    except Exception as ex:
+        return {'error': str(ex)[:200]}
 
 
 def _scratch_gb(wl):

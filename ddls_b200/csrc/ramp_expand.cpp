@@ -94,6 +94,12 @@ template <class T> T* dup(const std::vector<T>& v) {
 
 extern "C" {
 
+void ramp_free_expanded_aux(ramp_expanded_aux_t* a) {
+    if (!a) return;
+    free(a->dep_size); free(a->op_mem); free(a->node_order);
+    memset(a, 0, sizeof(*a));
+}
+
 void ramp_free_expanded_job(ramp_lowered_job_t* j) {
     if (!j) return;
     free((void*)j->op_cost); free((void*)j->op_prio); free((void*)j->op_worker); free((void*)j->op_n_parents);
@@ -103,8 +109,7 @@ void ramp_free_expanded_job(ramp_lowered_job_t* j) {
 }
 
 int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double quantum, const ramp_block_t* blk,
-                         int32_t run_time_mode, int32_t num_training_steps, ramp_lowered_job_t* out, double* dep_size_out,
-                         double* op_mem_out, int32_t* node_order_out) {
+                         int32_t run_time_mode, int32_t num_training_steps, ramp_lowered_job_t* out, ramp_expanded_aux_t* aux) {
     if (!g || !blk || !out || g->n_fwd < 1 || degree < 1 || (degree != 1 && degree % 2 != 0) || blk->n_servers < degree)
         return RAMP_ERR_BAD_ARG;
     const int n = g->n_fwd;
@@ -316,9 +321,12 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
     out->op_cost = dup(op_cost); out->op_prio = dup(op_prio); out->op_worker = dup(op_worker); out->op_n_parents = dup(n_parents);
     out->row_ptr = dup(row_ptr); out->dep_dst = dup(dep_dst); out->dep_run_time = dup(run_time); out->dep_prio = dup(dep_prio);
     out->dep_channel = dup(dep_channel); out->dep_is_flow = dup(is_flow);
-    if (dep_size_out) memcpy(dep_size_out, sizes.data(), sizeof(double) * (size_t)E);
-    if (op_mem_out) for (int i = 0; i < N; ++i) op_mem_out[i] = G.nodes[by_id[i]].mem;
-    if (node_order_out) for (int i = 0; i < N; ++i) node_order_out[i] = idx[alive[i]];     // op indices in graph (dict) order
+    if (aux) {
+        std::vector<double> op_mem(N);
+        std::vector<int32_t> order(N);
+        for (int i = 0; i < N; ++i) { op_mem[i] = G.nodes[by_id[i]].mem; order[i] = idx[alive[i]]; }   // op indices in graph (dict) order
+        aux->dep_size = dup(sizes); aux->op_mem = dup(op_mem); aux->node_order = dup(order);
+    }
     return RAMP_OK;
 }
 

@@ -19,6 +19,10 @@ class _FwdGraph(C.Structure):
                 ('act_size', C.c_void_p), ('par_size', C.c_void_p), ('edge_src', C.c_void_p), ('edge_dst', C.c_void_p)]
 
 
+class _Aux(C.Structure):
+    _fields_ = [('dep_size', C.c_void_p), ('op_mem', C.c_void_p), ('node_order', C.c_void_p)]
+
+
 class _Block(C.Structure):
     _fields_ = [('n_servers', C.c_int32), ('num_communication_groups', C.c_int32), ('coords', C.c_void_p),
                 ('channel_bandwidth', C.c_double), ('latency', C.c_double), ('io_latency', C.c_double)]
@@ -44,8 +48,9 @@ def expand_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_star
                     run_times: str = 'one_to_one') -> LoweredJob:
     L = engine.load_library()
     L.ramp_expand_template.restype = C.c_int
-    L.ramp_expand_template.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
-                                       C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ramp_expand_template.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.ramp_free_expanded_aux.restype = None
+    L.ramp_free_expanded_aux.argtypes = [C.c_void_p]
     L.ramp_free_expanded_job.restype = None
     L.ramp_free_expanded_job.argtypes = [C.c_void_p]
     if degree != 1 and degree % 2 != 0:
@@ -60,17 +65,14 @@ def expand_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_star
     coords = np.ascontiguousarray(block_coords(shape, degree, block_start, run_times), dtype=np.int32)
     blk = _Block(len(coords), shape.c, coords.ctypes.data, shape.channel_bandwidth, shape.latency, shape.io_latency)
     mode = 1 if run_times == 'reference' else 0
-    out = engine._LoweredJob()
-    engine._check(L.ramp_expand_template(C.byref(g), degree, quantum, C.byref(blk), mode, num_training_steps, C.byref(out), None, None, None))
+    out, aux = engine._LoweredJob(), _Aux()
+    engine._check(L.ramp_expand_template(C.byref(g), degree, quantum, C.byref(blk), mode, num_training_steps, C.byref(out), C.byref(aux)))
     N, E = out.n_ops, out.n_deps
-    L.ramp_free_expanded_job(C.byref(out))
-    sizes, op_mem, order = np.empty(E, dtype=np.float64), np.empty(N, dtype=np.float64), np.empty(N, dtype=np.int32)
-    engine._check(L.ramp_expand_template(C.byref(g), degree, quantum, C.byref(blk), mode, num_training_steps, C.byref(out),
-                                         sizes.ctypes.data, op_mem.ctypes.data, order.ctypes.data))
 
     def arr(ptr, n, dt):
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy() if n else np.zeros(0, dtype=dt)
     try:
+        sizes, op_mem, order = arr(aux.dep_size, E, np.float64), arr(aux.op_mem, N, np.float64), arr(aux.node_order, N, np.int32)
         op_cost = arr(out.op_cost, N, np.float64)
         is_flow = arr(out.dep_is_flow, E, np.uint8)
         seq_time = float(sum(float(op_cost[i]) for i in order)) * num_training_steps            # JOB:224-235, graph order
@@ -87,5 +89,6 @@ def expand_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_star
                         dep_is_flow=is_flow, mount=mount, model=fwd.name)
     finally:
         L.ramp_free_expanded_job(C.byref(out))
+        L.ramp_free_expanded_aux(C.byref(aux))
     lj.seq_time = seq_time
     return lj.canonicalise()

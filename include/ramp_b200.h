@@ -245,13 +245,19 @@ typedef struct {
 
 enum { RAMP_RUN_TIMES_ONE_TO_ONE = 0, RAMP_RUN_TIMES_REFERENCE = 1 };
 
-/* Fills `out` with malloc'ed arrays (release with ramp_free_expanded_job).  Optional outputs the mount scalars
- * (ramp_action_t) are summed from -- call once with NULLs to learn n_ops / n_deps: dep_size_out [n_deps] edge sizes,
- * op_mem_out [n_ops] memory costs, node_order_out [n_ops] op indices in the job graph's node order (the order the
- * reference's Python sums run in, JOB:224-248). */
+/* What the mount scalars (ramp_action_t) are summed from: edge sizes, op memory costs, and the op indices in the job
+ * graph's node order (the order the reference's Python sums run in, JOB:224-248). */
+typedef struct {
+    double*  dep_size;            /* [n_deps] */
+    double*  op_mem;              /* [n_ops]  */
+    int32_t* node_order;          /* [n_ops]  */
+} ramp_expanded_aux_t;
+
+/* Fills `out` (and `aux` if not NULL) with malloc'ed arrays; release with ramp_free_expanded_job / ramp_free_expanded_aux. */
 int ramp_expand_template(const ramp_forward_graph_t* graph, int32_t degree, double min_op_run_time_quantum,
                          const ramp_block_t* block, int32_t run_time_mode, int32_t num_training_steps,
-                         ramp_lowered_job_t* out, double* dep_size_out, double* op_mem_out, int32_t* node_order_out);
+                         ramp_lowered_job_t* out, ramp_expanded_aux_t* aux);
+void ramp_free_expanded_aux(ramp_expanded_aux_t* aux);
 void ramp_free_expanded_job(ramp_lowered_job_t* job);
 
 #ifdef __cplusplus
