@@ -1,21 +1,15 @@
 """The drop-in class keeps the reference's call signatures.  Needs the read-only reference checkout (through
-the oracle's import shim), so it runs in the build container only and is skipped on the GPU box."""
+oracle/ref_shim.py), so it runs in the build container only and is skipped on the GPU box."""
 import inspect
-import os
-import sys
 
 import pytest
 
-REF = '/root/reference'
+from oracle import ref_shim
 
 
-@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout not present (GPU box)')
+@pytest.mark.skipif(not ref_shim.reference_available(), reason='reference checkout not present (GPU box)')
 def test_dropin_class_signatures_match_reference():
-    from oracle import ref_shim
-    if hasattr(ref_shim, 'install'):
-        ref_shim.install()
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    ref_shim.install()
     from ddls.environments.ramp_cluster.ramp_cluster_environment import RampClusterEnvironment as Ref
     from ddls_b200.host.cluster import RampClusterEnvironment as Mine
     for method in ('__init__', 'reset', 'step', 'is_done'):
