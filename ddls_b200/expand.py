@@ -45,7 +45,9 @@ def block_coords(shape: RampShape, degree: int, block_start: int = 0, run_times:
 
 def expand_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_start: int = 0, quantum: float = 0.01,
                     num_training_steps: int = 50, model_id: int = 0, max_acceptable_frac: float = 1.0,
-                    run_times: str = 'one_to_one') -> LoweredJob:
+                    run_times: str = 'one_to_one', coords=None) -> LoweredJob:
+    """coords: explicit (cg, rack, server) of the block's servers in sorted server-id order (e.g. from placer.first_fit_place);
+    overrides block_start / the probed empty-cluster blocks."""
     L = engine.load_library()
     L.ramp_expand_template.restype = C.c_int
     L.ramp_expand_template.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
@@ -55,14 +57,15 @@ def expand_template(fwd: ForwardGraph, degree: int, shape: RampShape, block_star
     L.ramp_free_expanded_job.argtypes = [C.c_void_p]
     if degree != 1 and degree % 2 != 0:
         raise Exception(f'Invalid num_partitions={degree}; RAMP placer expects even numbers.')   # op_partition.py:26-27
-    if block_start + max(degree, 1) > shape.n_workers:
+    if coords is None and block_start + max(degree, 1) > shape.n_workers:
         raise Exception('worker block does not fit in the cluster')
     f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     fc, bc, ac, pc = f64(fwd.fwd), f64(fwd.bwd), f64(fwd.act), f64(fwd.par)
     es = np.ascontiguousarray([u for (u, _) in fwd.edges], dtype=np.int32)
     ed = np.ascontiguousarray([v for (_, v) in fwd.edges], dtype=np.int32)
     g = _FwdGraph(fwd.n, len(fwd.edges), fc.ctypes.data, bc.ctypes.data, ac.ctypes.data, pc.ctypes.data, es.ctypes.data, ed.ctypes.data)
-    coords = np.ascontiguousarray(block_coords(shape, degree, block_start, run_times), dtype=np.int32)
+    coords = np.ascontiguousarray(block_coords(shape, degree, block_start, run_times) if coords is None else sorted(coords),
+                                  dtype=np.int32).reshape(-1, 3)
     blk = _Block(len(coords), shape.c, coords.ctypes.data, shape.channel_bandwidth, shape.latency, shape.io_latency)
     mode = 1 if run_times == 'reference' else 0
     out, aux = engine._LoweredJob(), _Aux()

@@ -60,3 +60,47 @@ def test_native_expansion_rejects_bad_arguments():
         expand_template(synth.chain_graph(4, 'c4'), 3, RampShape(2, 2, 2))           # odd degree (op_partition.py:26-27)
     with pytest.raises(Exception):
         expand_template(synth.chain_graph(4, 'c4'), 16, RampShape(2, 2, 2))          # block larger than the cluster
+
+
+# graphs / topologies of the seeded reference episodes behind tests/golden/placer_cases.json (oracle/gen_golden.py CASES,
+# restated here because that script imports the reference) and how many placements each episode recorded
+EPISODES = [
+    ('chain8_busy', lambda: [synth.chain_graph(6, 'chain6')], (2, 2, 2), 14),
+    ('mixed16', lambda: [synth.chain_graph(5, 'chain5'), synth.resnet_like_graph(n_blocks=2, stem=2, name='res2', seed=7, body_per_block=3),
+                         synth.transformer_like_graph(n_layers=1, name='tfm1', seed=4)], (2, 2, 4), 15),
+    ('mixed64_busy', lambda: [synth.chain_graph(4, 'chain4'), synth.resnet_like_graph(n_blocks=1, stem=2, name='res1', seed=11, body_per_block=2),
+                              synth.transformer_like_graph(n_layers=1, name='tfm1b', seed=6)], (4, 4, 4), 24),
+    ('res16_flood', lambda: [synth.resnet_like_graph(n_blocks=1, stem=1, name='res1s', seed=3, body_per_block=2)], (2, 2, 4), 6),
+    ('tfm32_acceptable', lambda: [synth.transformer_like_graph(n_layers=2, name='tfm2', seed=9)], (4, 4, 2), 6),
+    ('residual32_deg16', lambda: [synth.residual_small_graph()], (4, 4, 2), 3),
+]
+
+
+def test_placer_plus_native_expansion_reproduce_reference_jobs_on_busy_clusters():
+    """The whole host chain of SURVEY 8f-1/-4 -- ddls_b200/placer.py picks the servers, ramp_expand_template builds the job --
+    against every job the unmodified reference's agents lowered in six seeded busy-cluster episodes (67 jobs: chain, ResNet-like
+    and transformer-like graphs, degrees 2-16, four topologies): every array equal but the hash-ordered priority ties."""
+    import json
+    import os
+    from ddls_b200.placer import first_fit_place
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'placer_cases.json')))
+    at, checked = 0, 0
+    for name, graphs, shape, n_cases in EPISODES:
+        g = Golden(name)
+        mine_cases, at = cases[at:at + n_cases], at + n_cases
+        tids = [int(t) for t in g.d['step_tid'] if t >= 0]
+        placed = [c for c in mine_cases if c['placement'] is not None]
+        assert len(placed) == len(tids)
+        for c, tid in zip(placed, tids):
+            ref = g.templates[tid]
+            fwd = [x for x in graphs() if x.n == len(c['nodes']) and np.allclose(np.add(x.act, x.par), c['mem'])]
+            assert len(fwd) == 1
+            ramp = {tuple(k): {'mem': m, 'job_idxs': set(j)} for k, m, j in c['ramp']}
+            where = first_fit_place(c['nodes'], c['mem'], c['in_edges'], c['out_edges'], dict(zip(c['mp_split_ids'], c['mp_splits'])),
+                                    ramp, tuple(c['shape']), [tuple(s) for s in c['servers']], c['job_idx'])
+            degree = max(c['mp_splits']) if c['mp_splits'] else 1
+            mine = expand_template(fwd[0], degree, RampShape(*shape), run_times='reference', coords=sorted(set(where.values())))
+            for f in ARRAYS[:-1]:
+                np.testing.assert_array_equal(np.asarray(getattr(mine, f)), np.asarray(getattr(ref, f)), err_msg=f'{name} tid {tid} {f}')
+            checked += 1
+    assert checked == 67
