@@ -330,4 +330,107 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
     return RAMP_OK;
 }
 
+// RampFirstFitOpPlacer (agents/placers/ramp_first_fit_op_placer.py:27-113 + agents/placers/utils.py:68-582) for one job on
+// a cluster whose servers are described by free memory and a busy flag; the Python twin is ddls_b200/placer.py.
+int ramp_first_fit_place(const ramp_forward_graph_t* g, const int32_t* splits, const ramp_cluster_state_t* st,
+                         int32_t* server_out, int32_t* offset_out) {
+    if (!g || !splits || !st || !server_out || !offset_out || g->n_fwd < 1) return RAMP_ERR_BAD_ARG;
+    const int n = g->n_fwd, C = st->shape[0], R = st->shape[1], S = st->shape[2];
+    const int n_servers = C * R * S;
+    auto sid = [&](int c, int r, int s) { return (c * R + r) * S + s; };
+    std::vector<double> mem(st->free_mem, st->free_mem + n_servers);
+    std::vector<std::vector<int>> parents(n + 1), children(n + 1);
+    for (int e = 0; e < g->n_edges; ++e) {
+        const int u = g->edge_src[e], v = g->edge_dst[e];
+        if (u < 1 || u > n || v < 1 || v > n) return RAMP_ERR_BAD_ARG;
+        parents[v].push_back(u); children[u].push_back(v);
+    }
+    // topo_sort (utils.py:100-115)
+    std::vector<std::vector<int>> left = parents;
+    std::vector<int> sequence, queue;
+    for (int v = 1; v <= n; ++v) if (left[v].empty()) { queue.push_back(v); sequence.push_back(v); }
+    for (size_t q = 0; q < queue.size(); ++q) {
+        const int v = queue[q];
+        for (int c : children[v]) {
+            erase_first(left[c], v);
+            if (left[c].empty()) { queue.push_back(c); sequence.push_back(c); }
+        }
+    }
+    std::vector<std::vector<int>> where(n + 1);
+    auto check_block = [&](const std::vector<int>& block, double op_size) {     // utils.py:215-233
+        if (block.empty()) return false;
+        for (int s : block) {
+            if (s < 0) return false;
+            if (st->busy[s]) return false;
+            if (mem[s] < op_size) return false;
+        }
+        return true;
+    };
+    auto get_block = [&](int bc, int br, int bs, int i, int j, int k) {          // utils.py:464-489
+        std::vector<int> block;
+        if (bs == -1) {
+            for (int m = 0; m < bc; ++m) {
+                const int c = (i + m) % (C + 1), r = (j + m) % (R + 1), s = k % S;
+                block.push_back((c < C && r < R) ? sid(c, r, s) : -1);           // the reference would raise KeyError here
+            }
+        } else {
+            for (int c = 0; c < bc; ++c) for (int r = 0; r < br; ++r) for (int s = 0; s < bs; ++s)
+                block.push_back(sid((i + c) % C, (j + r) % R, (k + s) % S));
+        }
+        return block;
+    };
+    for (int op : sequence) {
+        const int split = std::max(splits[op - 1], 1);
+        const double need = g->act_size[op - 1] + g->par_size[op - 1];
+        bool placed = false;
+        for (int p : parents[op]) {                                               // parent_collective_placement, utils.py:258-314
+            const std::vector<int>& sv = where[p];
+            if ((int)sv.size() != split) continue;
+            double avail = 0.0;
+            for (int s : sv) avail += mem[s];
+            if (avail >= need) {
+                for (int s : sv) { mem[s] -= need / split; where[op].push_back(s); }
+                placed = true;
+                break;
+            }
+        }
+        if (placed) continue;
+        if (split > n_servers) return 1;                                          // regular_collective_placement, utils.py:333-383
+        const double op_size = need / split;
+        std::vector<std::tuple<int, int, int>> shapes;
+        for (int i = 1; i <= split; ++i) {                                        // get_factor_pairs + get_block_shapes
+            if (split % i) continue;
+            const int p0 = split / i, p1 = i;
+            const double var = std::sqrt((double)p0);
+            if (std::fmod(var, 1.0) == 0.0 && var <= C && var <= R && p1 <= S) shapes.push_back({(int)var, (int)var, p1});
+            if (p0 > C || p0 > R || p1 > S) continue;
+            shapes.push_back({p0, 1, p1});
+            shapes.push_back({p0, p1, 1});
+        }
+        shapes.push_back({split, split, -1});
+        shapes.push_back({split, 1, 1});
+        std::vector<int> block;
+        bool found = false;
+        for (auto& sh : shapes) {                                                 // ff_block, utils.py:394-443
+            const int bc = std::get<0>(sh), br = std::get<1>(sh), bs = std::get<2>(sh);
+            const int I = C - bc + 1, J = R - br + 1, K = S - bs + 1;
+            if (I <= 0 || J <= 0 || K <= 0) continue;
+            for (int i = 0; i < I && !found; ++i) for (int j = 0; j < J && !found; ++j) for (int k = 0; k < K && !found; ++k) {
+                block = get_block(bc, br, bs, i, j, k);
+                if (check_block(block, op_size)) found = true;
+            }
+            if (found) break;
+        }
+        if (!found) return 1;
+        for (int s : block) { mem[s] -= op_size; where[op].push_back(s); }
+    }
+    int at = 0;
+    for (int op = 1; op <= n; ++op) {
+        offset_out[op - 1] = at;
+        for (int s : where[op]) server_out[at++] = s;
+    }
+    offset_out[n] = at;
+    return RAMP_OK;
+}
+
 }  // extern "C"

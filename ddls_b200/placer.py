@@ -134,3 +134,54 @@ def first_fit_place(nodes: Sequence[str], mem: Sequence[float], in_edges: Dict[s
             ramp[s]['mem'] -= op_size
             put(op, split, j, s)
     return out
+
+
+def first_fit_place_native(n_fwd: int, mem: Sequence[float], edges: Sequence[Tuple[int, int]], splits: Sequence[int],
+                           free_mem: Dict[Server, float], busy: Dict[Server, bool], shape: Server) -> Optional[Dict[str, Server]]:
+    """Same decision through the C ABI (include/ramp_b200.h: ramp_first_fit_place; csrc/ramp_expand.cpp).  Forward ops are
+    1..n_fwd in node order, `edges` in the graph's edge order; returns the same mapping as first_fit_place."""
+    import ctypes as C
+    import numpy as np
+    from . import engine
+    from .expand import _FwdGraph
+
+    class _State(C.Structure):
+        _fields_ = [('shape', C.c_int32 * 3), ('_pad', C.c_int32), ('free_mem', C.c_void_p), ('busy', C.c_void_p)]
+    L = engine.load_library()
+    L.ramp_first_fit_place.restype = C.c_int
+    L.ramp_first_fit_place.argtypes = [C.c_void_p] * 5
+    c_, r_, s_ = shape
+    idx = lambda sv: (sv[0] * r_ + sv[1]) * s_ + sv[2]
+    fm = np.zeros(c_ * r_ * s_, dtype=np.float64)
+    bz = np.zeros(c_ * r_ * s_, dtype=np.uint8)
+    for sv, m in free_mem.items():
+        fm[idx(sv)] = m
+    for sv, b in busy.items():
+        bz[idx(sv)] = 1 if b else 0
+    memv = np.ascontiguousarray(mem, dtype=np.float64)
+    zero = np.zeros(n_fwd, dtype=np.float64)
+    es = np.ascontiguousarray([u for (u, _) in edges], dtype=np.int32)
+    ed = np.ascontiguousarray([v for (_, v) in edges], dtype=np.int32)
+    g = _FwdGraph(n_fwd, len(edges), zero.ctypes.data, zero.ctypes.data, memv.ctypes.data, zero.ctypes.data, es.ctypes.data, ed.ctypes.data)
+    st = _State((C.c_int32 * 3)(c_, r_, s_), 0, fm.ctypes.data, bz.ctypes.data)
+    sp = np.ascontiguousarray(splits, dtype=np.int32)
+    server_out = np.zeros(int(np.maximum(sp, 1).sum()), dtype=np.int32)
+    offset_out = np.zeros(n_fwd + 1, dtype=np.int32)
+    rc = L.ramp_first_fit_place(C.byref(g), sp.ctypes.data, C.byref(st), server_out.ctypes.data, offset_out.ctypes.data)
+    if rc == 1:
+        return None
+    engine._check(rc)
+    out: Dict[str, Server] = {}
+    for i in range(1, n_fwd + 1):
+        k = max(int(sp[i - 1]), 1)
+        for j in range(k):
+            sv = int(server_out[offset_out[i - 1] + j])
+            coord = (sv // (r_ * s_), (sv // s_) % r_, sv % s_)
+            fwd_id, bwd_id = str(i), backward_op_id(str(i), n_fwd)
+            if k > 1:
+                out[partitioned_op_id(fwd_id, j)] = coord
+                out[partitioned_op_id(bwd_id, j)] = coord
+            else:
+                out[fwd_id] = coord
+                out[bwd_id] = coord
+    return out

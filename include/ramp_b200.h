@@ -258,6 +258,21 @@ int ramp_expand_template(const ramp_forward_graph_t* graph, int32_t degree, doub
                          const ramp_block_t* block, int32_t run_time_mode, int32_t num_training_steps,
                          ramp_lowered_job_t* out, ramp_expanded_aux_t* aux);
 void ramp_free_expanded_aux(ramp_expanded_aux_t* aux);
+
+/* RampFirstFitOpPlacer.get (agents/placers/ramp_first_fit_op_placer.py:27-113, agents/placers/utils.py:68-582) for one job:
+ * which server every (sub-)op goes to on a possibly busy cluster.  Server index = (cg * racks + rack) * servers + server. */
+typedef struct {
+    int32_t shape[3];             /* communication groups, racks per group, servers per rack (ramp.py:36-41)        */
+    int32_t _pad;
+    const double*  free_mem;      /* [servers] memory_capacity - memory_occupied of the server's worker (utils.py:235) */
+    const uint8_t* busy;          /* [servers] a job is mounted there (one job per worker, ramp_rules.py:6-39)       */
+} ramp_cluster_state_t;
+
+/* splits[n_fwd]: sub-ops per forward op (1 = unsplit).  server_out: servers of op 1's sub-ops 0.., then op 2's ... (the
+ * backward op shares them); offset_out[n_fwd + 1]: where each op's servers start.  Returns RAMP_OK, 1 if the job cannot be
+ * placed (the reference then leaves it out of the Action and RCE:914-919 blocks it), or a negative RAMP_ERR_*. */
+int ramp_first_fit_place(const ramp_forward_graph_t* graph, const int32_t* splits, const ramp_cluster_state_t* state,
+                         int32_t* server_out, int32_t* offset_out);
 void ramp_free_expanded_job(ramp_lowered_job_t* job);
 
 #ifdef __cplusplus

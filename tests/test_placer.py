@@ -29,3 +29,19 @@ def test_first_fit_matches_reference(i):
     else:
         assert got is not None
         assert {k: list(v) for k, v in got.items()} == c['placement']
+
+
+@pytest.mark.parametrize('i', range(len(CASES)))
+def test_native_first_fit_matches_reference(i):
+    """The same decisions through the C ABI (ramp_first_fit_place)."""
+    from ddls_b200.placer import first_fit_place_native
+    c = CASES[i]
+    n = len(c['nodes'])
+    assert c['nodes'] == [str(k) for k in range(1, n + 1)]
+    split_of = dict(zip(c['mp_split_ids'], c['mp_splits']))
+    got = first_fit_place_native(n, c['mem'], [(int(u), int(v)) for u, v in c['edges']], [split_of.get(str(k), 1) for k in range(1, n + 1)],
+                                 {tuple(k): m for k, m, _ in c['ramp']}, {tuple(k): bool(j) for k, _, j in c['ramp']}, tuple(c['shape']))
+    if c['placement'] is None:
+        assert got is None
+    else:
+        assert got is not None and {k: list(v) for k, v in got.items()} == c['placement']
