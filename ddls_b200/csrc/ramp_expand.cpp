@@ -114,6 +114,11 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
         return RAMP_ERR_BAD_ARG;
     const int n = g->n_fwd;
     Graph G;
+    {   // every forward edge fans out to at most degree^2 edges per direction, every split backward op adds degree^2 sync edges
+        const size_t est = (size_t)(2 * g->n_edges + 1 + n) * (size_t)degree * (size_t)degree + 16;
+        G.size.reserve(est * 2);
+        G.nodes.reserve((size_t)2 * n * (degree + 1) + 4);
+    }
     std::vector<int> fwd_node(n + 1), bwd_node(n + 1);
     std::vector<double> mem0(n + 1);
     for (int i = 1; i <= n; ++i) {                               // utils.py:432 memory_cost = activation + parameter
@@ -140,6 +145,7 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
         splits[i] = (int)k;
     }
     std::unordered_map<uint64_t, double> in_feat, out_feat;
+    in_feat.reserve(G.size.bucket_count()); out_feat.reserve(G.size.bucket_count());
     std::vector<uint64_t> in_order, out_order;                   // insertion order is irrelevant for the override below
     std::vector<std::vector<int>> fsubs(n + 1), bsubs(n + 1);
     for (int i = 1; i <= n; ++i) {
@@ -205,6 +211,7 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
     std::vector<double> sizes(E), run_time(E), sched_cost(E);
     std::vector<uint8_t> is_flow(E);
     std::unordered_map<uint64_t, int> dep_index;
+    dep_index.reserve((size_t)E * 2);
     for (int e = 0; e < E; ++e) {
         row_ptr[idx[deps[e].u] + 1]++;
         dep_dst[e] = idx[deps[e].v];
