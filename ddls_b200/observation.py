@@ -5,7 +5,7 @@ Restates RampJobPartitioningObservation._encode_obs and the feature functions it
 encode, :358-621 features) on the job's arrays instead of networkx / dict objects: per-op and per-dep features are
 vectorised divisions, graph features are a dozen min-max normalisations, the action mask needs only the number of free
 workers and the RAMP shape.  Pinned against 81 observations recorded from the unmodified reference
-(tests/test_observation.py, fixture tests/golden/obs_cases.npz from oracle/gen_obs_cases.py)."""
+(tests/test_observation.py, fixture tests/fixtures/obs_cases.npz from oracle/gen_obs_cases.py)."""
 from __future__ import annotations
 
 import math

@@ -4,7 +4,7 @@ Restates RampFirstFitOpPlacer (agents/placers/ramp_first_fit_op_placer.py:27-113
 (agents/placers/utils.py: get_allocation_preamble :68, topo_sort :100, parent_collective_placement :258,
 regular_collective_placement :333, find_sub_block :385, ff_block :394, get_factor_pairs :445, get_block :464,
 get_block_shapes :491, allocate :532, check_block :215) on plain dicts; pinned against the reference's recorded decisions in
-tests/test_placer.py (fixture tests/golden/placer_cases.json).  SURVEY.md 8f rows 1 and 4 (host side)."""
+tests/test_placer.py (fixture tests/fixtures/placer_cases.json).  SURVEY.md 8f rows 1 and 4 (host side)."""
 from __future__ import annotations
 
 import math

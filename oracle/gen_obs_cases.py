@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE -- records observations of the unmodified reference's RampJobPartitioningObservation in seeded
 episodes together with everything the encoder read (job graph, job details, jobs_params, cluster scalars) as
-tests/golden/obs_cases.npz, the fixture ddls_b200/observation.py is pinned against (tests/test_observation.py).
+tests/fixtures/obs_cases.npz, the fixture ddls_b200/observation.py is pinned against (tests/test_observation.py).
 Build container only (needs the reference)."""
 import os
 import random
@@ -82,7 +82,7 @@ def main():
     finally:
         O.RampJobPartitioningObservation._encode_obs = orig
     out['n_cases'] = np.array(n)
-    path = os.path.join(ROOT, 'tests', 'golden', 'obs_cases.npz')
+    path = os.path.join(ROOT, 'tests', 'fixtures', 'obs_cases.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB,', n, 'cases')
 

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE -- records what the unmodified reference's RampFirstFitOpPlacer decided in seeded busy-cluster episodes
-(inputs: cluster occupancy per server, forward graph, split counts; output: op -> server) as tests/golden/placer_cases.json,
+(inputs: cluster occupancy per server, forward graph, split counts; output: op -> server) as tests/fixtures/placer_cases.json,
 the fixture ddls_b200/placer.py is pinned against (tests/test_placer.py).  Build container only (needs the reference)."""
 import json
 import os
@@ -71,7 +71,7 @@ def main():
             print(name, len(records) - n0, 'placements recorded,', sum(1 for r in records[n0:] if r['placement'] is None), 'failed')
     finally:
         P.RampFirstFitOpPlacer.get = orig_get
-    path = os.path.join(ROOT, 'tests', 'golden', 'placer_cases.json')
+    path = os.path.join(ROOT, 'tests', 'fixtures', 'placer_cases.json')
     json.dump(records, open(path, 'w'))
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB,', len(records), 'cases')
 

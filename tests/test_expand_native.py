@@ -62,7 +62,7 @@ def test_native_expansion_rejects_bad_arguments():
         expand_template(synth.chain_graph(4, 'c4'), 16, RampShape(2, 2, 2))          # block larger than the cluster
 
 
-# graphs / topologies of the seeded reference episodes behind tests/golden/placer_cases.json (oracle/gen_golden.py CASES,
+# graphs / topologies of the seeded reference episodes behind tests/fixtures/placer_cases.json (oracle/gen_golden.py CASES,
 # restated here because that script imports the reference) and how many placements each episode recorded
 EPISODES = [
     ('chain8_busy', lambda: [synth.chain_graph(6, 'chain6')], (2, 2, 2), 14),
@@ -83,7 +83,7 @@ def test_placer_plus_native_expansion_reproduce_reference_jobs_on_busy_clusters(
     import json
     import os
     from ddls_b200.placer import first_fit_place
-    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'placer_cases.json')))
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fixtures', 'placer_cases.json')))
     at, checked = 0, 0
     for name, graphs, shape, n_cases in EPISODES:
         g = Golden(name)

@@ -1,5 +1,5 @@
 """ddls_b200/observation.py against 81 observations recorded from the unmodified reference's encoder in seeded episodes
-(tests/golden/obs_cases.npz, written by oracle/gen_obs_cases.py): every array of the observation dict identical."""
+(tests/fixtures/obs_cases.npz, written by oracle/gen_obs_cases.py): every array of the observation dict identical."""
 import os
 
 import numpy as np
@@ -7,7 +7,7 @@ import pytest
 
 from ddls_b200.observation import encode_observation
 
-D = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'obs_cases.npz'))
+D = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fixtures', 'obs_cases.npz'))
 N_CASES = int(D['n_cases'])
 KEYS = ('action_set', 'action_mask', 'node_features', 'edge_features', 'graph_features', 'edges_src', 'edges_dst',
         'node_split', 'edge_split')

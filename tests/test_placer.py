@@ -1,5 +1,5 @@
 """ddls_b200/placer.py against the decisions the unmodified reference's RampFirstFitOpPlacer took in seeded busy-cluster
-episodes (tests/golden/placer_cases.json, written by oracle/gen_placer_cases.py): same servers for every sub-op, same failures."""
+episodes (tests/fixtures/placer_cases.json, written by oracle/gen_placer_cases.py): same servers for every sub-op, same failures."""
 import json
 import os
 
@@ -7,7 +7,7 @@ import pytest
 
 from ddls_b200.placer import first_fit_place
 
-PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'placer_cases.json')
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'fixtures', 'placer_cases.json')
 CASES = json.load(open(PATH))
 
 
