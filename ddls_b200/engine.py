@@ -119,7 +119,8 @@ EXPORTED_SYMBOLS = ['ramp_last_error', 'ramp_engine_create', 'ramp_engine_destro
                     'ramp_get_episode_state', 'ramp_episode_state_device', 'ramp_export_episode_state_to',
                     'ramp_get_memo_stats', 'ramp_get_memo_stats_ex',
                     'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_launch_count',
-                    'ramp_get_lookahead_kernel_time', 'ramp_expand_template', 'ramp_free_expanded_job', 'ramp_free_expanded_aux', 'ramp_first_fit_place']
+                    'ramp_get_lookahead_kernel_time', 'ramp_expand_template', 'ramp_free_expanded_job', 'ramp_free_expanded_aux', 'ramp_first_fit_place',
+                    'ramp_quotient_template', 'ramp_free_quotient']
 
 
 def _check(rc):

@@ -275,6 +275,34 @@ int ramp_first_fit_place(const ramp_forward_graph_t* graph, const int32_t* split
                          int32_t* server_out, int32_t* offset_out);
 void ramp_free_expanded_job(ramp_lowered_job_t* job);
 
+/* ---- symmetry quotient of a lowered job (host-only; ddls_b200/csrc/ramp_quotient.cpp).  ramp_register_template applies it
+ * by itself; it is exported so that tests can check it without a GPU.  The quotient job is what _run_lookahead
+ * (RCE:379-467) is simulated on: one op per class of ops that provably tick in lock step (e.g. the n sub-ops of a
+ * partitioned op, agents/partitioners/utils.py:42-110), one dep entry per (class of deps, group of identical channels).
+ *   op_weight     class size: what a winning class adds to the trace's active-worker count (RCE:709-715)
+ *   op_threshold  n_parents x class size: the class is readied when its counter passes through it (JOB:525-536)
+ *   dep_inc       members of the entry: what its completion adds to the child class's counter
+ *   op_class[N], dep_entry[E]: where every original op / dep went.  Keys are unique ranks (larger wins). ---- */
+typedef struct {
+    int32_t n_ops, n_deps, n_workers, n_channels;     /* classes, entries, worker groups, channel groups */
+    double*   op_cost;
+    uint32_t* op_key;
+    uint32_t* op_worker;
+    uint32_t* op_weight;
+    uint32_t* op_threshold;
+    int32_t*  row_ptr;
+    int32_t*  dep_dst;
+    double*   dep_run_time;
+    uint32_t* dep_key;
+    uint32_t* dep_channel;       /* 0xFFFFFFFF = none */
+    uint8_t*  dep_is_flow;
+    uint32_t* dep_inc;
+    int32_t*  op_class;
+    int32_t*  dep_entry;
+} ramp_quotient_t;
+int ramp_quotient_template(const ramp_lowered_job_t* job, ramp_quotient_t* out);
+void ramp_free_quotient(ramp_quotient_t* q);
+
 #ifdef __cplusplus
 }
 #endif
