@@ -72,6 +72,7 @@ struct HostTemplate {
     void* blob = nullptr;        // single device allocation holding all arrays
     std::vector<unsigned char> bytes;  // canonical host bytes for exact-duplicate detection
     uint64_t hash = 0;
+    void* res_blob = nullptr;    // device copy of the quotient blob (thread-per-lookahead kernel), null if not resident
 };
 
 }  // namespace
@@ -136,7 +137,26 @@ struct ramp_engine {
     WorkItem* d_items_big = nullptr;
     cudaStream_t stream2 = nullptr;  // big lookaheads run concurrently with the small ones
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // resident (quotient) templates: thread-per-lookahead kernel
+    int use_resident = 1;        // RAMP_RESIDENT=0: register every template for the warp / CTA kernels only
+    int use_quotient = 1;        // RAMP_QUOTIENT=0: resident blobs are built from the unfolded job (identity quotient)
+    int32_t res_max_bytes = 96 * 1024;   // largest quotient blob that goes resident (RAMP_RESIDENT_MAX_KB)
+    int n_resident = 0, n_nonresident = 0;
+    int32_t res_tmpl_cap = 0, res_n_cap = 0, res_spill_ops = 0, res_spill_deps = 0;
+    int res_grid = 0;
+    size_t res_smem = 0;
+    unsigned char* d_res_scratch = nullptr;
+    uint64_t res_scratch_stride = 0;
+    int res_scratch_grid = 0;
+    WorkItem* d_items_res = nullptr;
+    WorkItem* d_chunk_items = nullptr;   // [B][32]
+    ChunkDesc* d_chunks = nullptr;       // [B]
+    int32_t* d_tcount = nullptr;         // [max_templates + 1]
+    int32_t* d_tbase = nullptr;
+    int32_t* d_rank = nullptr;           // [B]
     // standalone lookahead buffers
+    WorkItem* sa_chunk_items = nullptr;
+    ChunkDesc* sa_chunks = nullptr;
     ResultSlots sa_res{};
     int32_t sa_cap = 0;
     WorkItem* sa_items = nullptr;
@@ -306,6 +326,133 @@ void make_rank_keys(const int64_t* prio, int32_t n, std::vector<uint32_t>& key) 
     for (int32_t r = 0; r < n; ++r) key[order[r]] = (uint32_t)(n - r);
 }
 
+
+// ---- resident (quotient) templates ---------------------------------------------------------------------------
+int bits_for_u64(uint64_t max_value) { int b = 1; while ((max_value >> b) != 0) ++b; return b; }
+
+// Packs a quotient job (ramp_quotient.cpp) into the blob the thread-per-lookahead kernel bulk-copies into shared memory
+// (layout: ResHeader, ramp_lookahead_thread.cuh).  Returns false when the job is not eligible: blob larger than
+// max_bytes, class sizes / counters beyond 16 bits, or a dep word wider than 64 bits.
+bool build_resident_blob(const ramp_lowered_job_t* j, const ramp_quotient_t& q, int32_t max_bytes, std::vector<unsigned char>& blob) {
+    const int32_t N = q.n_ops, E = q.n_deps;
+    if (N < 1 || q.n_workers > 0xFFFF || q.n_channels >= 0xFFFF) return false;
+    std::vector<uint64_t> in_total(N, 0);
+    uint32_t max_key = 1, max_inc = 1;
+    for (int32_t k = 0; k < E; ++k) {
+        in_total[q.dep_dst[k]] += q.dep_inc[k];
+        max_key = std::max(max_key, q.dep_key[k]);
+        max_inc = std::max(max_inc, q.dep_inc[k]);
+    }
+    for (int32_t c = 0; c < N; ++c)
+        if (q.op_weight[c] > 0xFFFF || in_total[c] > 0xFFFF || q.op_threshold[c] > 0xFFFFFFFFu) return false;   // u16 counters never wrap
+    const int kbits = bits_for_u64(max_key), cbits = bits_for_u64((uint64_t)q.n_channels + 1);
+    const int ibits = bits_for_u64(max_inc), nbits = bits_for_u64((uint64_t)N);
+    if (kbits + cbits + 1 + ibits + nbits > 64 || kbits > 32 || cbits > 31 || ibits > 31) return false;
+    std::vector<int32_t> in_deg(N, 0), src;
+    for (int32_t k = 0; k < E; ++k) in_deg[q.dep_dst[k]]++;
+    for (int32_t c = 0; c < N; ++c) if (in_deg[c] == 0) src.push_back(c);
+    ResHeader h{};
+    h.n_ops = N; h.n_deps = E; h.n_workers = q.n_workers; h.n_channels = q.n_channels;
+    h.n_src = (int32_t)src.size(); h.num_training_steps = j->num_training_steps; h.orig_workers = j->n_workers;
+    h.kmask = (uint32_t)((1ull << kbits) - 1ull); h.cmask = (uint32_t)((1ull << cbits) - 1ull); h.imask = (uint32_t)((1ull << ibits) - 1ull);
+    h.cshift = kbits; h.fshift = kbits + cbits; h.ishift = kbits + cbits + 1; h.dshift = kbits + cbits + 1 + ibits;
+    size_t off = sizeof(ResHeader);
+    const size_t off_rec = off;                 off += align_up((uint64_t)N * 16, 16);
+    h.off_op_row = (int32_t)off;                off += align_up((uint64_t)N * 8, 16);
+    h.off_op_thr = (int32_t)off;                off += align_up((uint64_t)N * 4, 16);
+    h.off_dep_kd = (int32_t)off;                off += align_up((uint64_t)std::max(E, 1) * 8, 16);
+    h.off_dep_rt = (int32_t)off;                off += align_up((uint64_t)std::max(E, 1) * 8, 16);
+    h.off_src = (int32_t)off;                   off += align_up((uint64_t)std::max<size_t>(src.size(), 1) * 4, 16);
+    if (off > (size_t)max_bytes) return false;
+    h.total_bytes = (int32_t)off;
+    blob.assign(off, 0);
+    memcpy(blob.data(), &h, sizeof(h));
+    struct OpRec { double cost; uint32_t key; uint32_t worker; };
+    OpRec* rec = reinterpret_cast<OpRec*>(blob.data() + off_rec);
+    int32_t* row = reinterpret_cast<int32_t*>(blob.data() + h.off_op_row);
+    uint32_t* thr = reinterpret_cast<uint32_t*>(blob.data() + h.off_op_thr);
+    unsigned long long* kd = reinterpret_cast<unsigned long long*>(blob.data() + h.off_dep_kd);
+    double* rt = reinterpret_cast<double*>(blob.data() + h.off_dep_rt);
+    for (int32_t c = 0; c < N; ++c) {
+        rec[c] = OpRec{q.op_cost[c] + 0.0, q.op_key[c], q.op_worker[c] | (q.op_weight[c] << 16)};
+        row[2 * c] = q.row_ptr[c]; row[2 * c + 1] = q.row_ptr[c + 1] - q.row_ptr[c];
+        thr[c] = q.op_threshold[c];
+    }
+    for (int32_t k = 0; k < E; ++k) {
+        const unsigned long long chan = (q.dep_channel[k] == 0xFFFFFFFFu) ? (unsigned long long)h.cmask : (unsigned long long)q.dep_channel[k];
+        kd[k] = (unsigned long long)q.dep_key[k] | (chan << h.cshift) | ((unsigned long long)(q.dep_is_flow[k] ? 1 : 0) << h.fshift)
+                | ((unsigned long long)q.dep_inc[k] << h.ishift) | ((unsigned long long)q.dep_dst[k] << h.dshift);
+        rt[k] = q.dep_run_time[k] + 0.0;
+    }
+    if (!src.empty()) memcpy(blob.data() + h.off_src, src.data(), sizeof(int32_t) * src.size());
+    return true;
+}
+
+// the identity quotient: every op its own class (RAMP_QUOTIENT=0; lets the tests run the thread kernel on unfolded jobs)
+int identity_quotient(const ramp_lowered_job_t* j, ramp_quotient_t* q) {
+    memset(q, 0, sizeof(*q));
+    const int32_t N = j->n_ops, E = j->n_deps;
+    std::vector<uint32_t> ok, dk;
+    make_rank_keys(j->op_prio, N, ok);
+    make_rank_keys(j->dep_prio, E, dk);
+    q->n_ops = N; q->n_deps = E; q->n_workers = j->n_workers; q->n_channels = j->n_channels;
+    q->op_cost = (double*)malloc(sizeof(double) * N); q->op_key = (uint32_t*)malloc(4 * (size_t)N); q->op_worker = (uint32_t*)malloc(4 * (size_t)N);
+    q->op_weight = (uint32_t*)malloc(4 * (size_t)N); q->op_threshold = (uint32_t*)malloc(4 * (size_t)N); q->row_ptr = (int32_t*)malloc(4 * ((size_t)N + 1));
+    const size_t e1 = std::max(E, 1);
+    q->dep_dst = (int32_t*)malloc(4 * e1); q->dep_run_time = (double*)malloc(8 * e1); q->dep_key = (uint32_t*)malloc(4 * e1);
+    q->dep_channel = (uint32_t*)malloc(4 * e1); q->dep_is_flow = (uint8_t*)malloc(e1); q->dep_inc = (uint32_t*)malloc(4 * e1);
+    q->op_class = (int32_t*)malloc(4 * (size_t)N); q->dep_entry = (int32_t*)malloc(4 * e1);
+    for (int32_t i = 0; i < N; ++i) {
+        q->op_cost[i] = j->op_cost[i]; q->op_key[i] = ok[i]; q->op_worker[i] = j->op_worker[i]; q->op_weight[i] = 1;
+        q->op_threshold[i] = j->op_n_parents[i]; q->row_ptr[i] = j->row_ptr[i]; q->op_class[i] = i;
+    }
+    q->row_ptr[N] = j->row_ptr[N];
+    for (int32_t k = 0; k < E; ++k) {
+        q->dep_dst[k] = j->dep_dst[k]; q->dep_run_time[k] = j->dep_run_time[k]; q->dep_key[k] = dk[k];
+        q->dep_channel[k] = (j->dep_channel[k] == RAMP_NO_CHANNEL) ? 0xFFFFFFFFu : (uint32_t)j->dep_channel[k];
+        q->dep_is_flow[k] = j->dep_is_flow[k] ? 1 : 0; q->dep_inc[k] = 1; q->dep_entry[k] = k;
+    }
+    return RAMP_OK;
+}
+
+// shared memory / grid / HBM slabs of the thread-per-lookahead kernel for the resident templates registered so far
+int ensure_thread_scratch(ramp_engine* e) {
+    const size_t smem = thread_smem_bytes(e->res_tmpl_cap, e->res_n_cap);
+    if (smem > 220 * 1024) return set_error(RAMP_ERR_CAPACITY, "resident templates need %zu B of shared memory (max 220 KiB)", smem);
+    if (smem != e->res_smem || e->res_grid == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(ramp_lookahead_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(ramp_lookahead_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, RAMP_SMEM_CARVEOUT));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ramp_lookahead_thread_kernel, 32, smem));
+        if (occ < 1) occ = 1;
+        // one chunk = up to 32 lookaheads; enough resident CTAs for every episode to miss at once, at most 2 per SM
+        const int want = (e->cfg.n_episodes + 31) / 32 + 8;
+        e->res_grid = std::max(1, std::min(std::min(e->sm_count * occ, e->sm_count * 2), want));
+        e->res_smem = smem;
+    }
+    const uint64_t stride = thread_scratch_bytes(e->res_spill_ops, e->res_spill_deps, e->cfg.trace_cap);
+    if (stride != e->res_scratch_stride || e->res_grid != e->res_scratch_grid || !e->d_res_scratch) {
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        if (e->d_res_scratch) cudaFree(e->d_res_scratch);
+        e->d_res_scratch = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_res_scratch, stride * (uint64_t)e->res_grid));
+        e->res_scratch_stride = stride;
+        e->res_scratch_grid = e->res_grid;
+    }
+    return RAMP_OK;
+}
+
+ThreadArgs make_thread_args(ramp_engine* e, const ChunkDesc* chunks, const int32_t* n_chunks, int32_t* cursor, const WorkItem* items,
+                            const ResultSlots& res, const TracePool& pool, MemoStats* stats) {
+    ThreadArgs a{};
+    a.templates = e->d_templates; a.chunks = chunks; a.n_chunks = n_chunks; a.cursor = cursor; a.items = items;
+    a.scratch = e->d_res_scratch; a.scratch_stride = e->res_scratch_stride;
+    a.res = res; a.pool = pool; a.trace_cap = e->cfg.trace_cap;
+    a.tmpl_cap = e->res_tmpl_cap; a.n_cap = e->res_n_cap; a.spill_ops = e->res_spill_ops; a.spill_deps = e->res_spill_deps;
+    a.stats = stats;
+    return a;
+}
+
 }  // namespace
 
 extern "C" {
@@ -341,9 +488,18 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
         if (lookahead_cta_kernel_for(nt) == nullptr) { delete e; return set_error(RAMP_ERR_BAD_ARG, "RAMP_LOOKAHEAD_CTA_THREADS must be 64, 128 or 256"); }
         e->cta_nt = nt;
     }
-    if (const char* v = getenv("RAMP_LOOKAHEAD_MODE")) e->mode = !strcmp(v, "warp") ? 1 : !strcmp(v, "cta") ? 2 : 0;
+    if (const char* v = getenv("RAMP_LOOKAHEAD_MODE")) {
+        // warp / cta: every template goes to that kernel (no resident quotient blobs); thread_unfolded: the thread kernel on
+        // the unfolded job (identity quotient); anything else: automatic (resident whenever the quotient blob fits)
+        e->mode = !strcmp(v, "warp") ? 1 : !strcmp(v, "cta") ? 2 : 0;
+        if (e->mode != 0) e->use_resident = 0;
+        if (!strcmp(v, "thread_unfolded")) e->use_quotient = 0;
+    }
     if (const char* v = getenv("RAMP_BIG_THRESHOLD")) e->big_threshold = atoll(v);
     if (const char* v = getenv("RAMP_DEBUG")) e->debug = atoi(v);
+    if (const char* v = getenv("RAMP_RESIDENT")) e->use_resident = atoi(v);
+    if (const char* v = getenv("RAMP_QUOTIENT")) e->use_quotient = atoi(v);
+    if (const char* v = getenv("RAMP_RESIDENT_MAX_KB")) e->res_max_bytes = atoi(v) * 1024;
     if (const char* v = getenv("RAMP_SPLIT_ALPHA")) e->split_alpha = atof(v);
     if (const char* v = getenv("RAMP_USE_CTA256")) e->use_cta256 = atoi(v);
     if (const char* v = getenv("RAMP_DENSE_FACTOR")) e->dense_factor = atof(v);
@@ -380,6 +536,13 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
 
     CUDA_TRY(cudaMalloc(&e->d_items, sizeof(WorkItem) * B));
     CUDA_TRY(cudaMalloc(&e->d_items_big, sizeof(WorkItem) * B));
+    CUDA_TRY(cudaMalloc(&e->d_items_res, sizeof(WorkItem) * B));
+    CUDA_TRY(cudaMalloc(&e->d_chunk_items, sizeof(WorkItem) * (size_t)B * 32));
+    CUDA_TRY(cudaMalloc(&e->d_chunks, sizeof(ChunkDesc) * B));
+    CUDA_TRY(cudaMalloc(&e->d_tcount, sizeof(int32_t) * ((size_t)cfg.max_templates + 1)));
+    CUDA_TRY(cudaMemset(e->d_tcount, 0, sizeof(int32_t) * ((size_t)cfg.max_templates + 1)));
+    CUDA_TRY(cudaMalloc(&e->d_tbase, sizeof(int32_t) * ((size_t)cfg.max_templates + 1)));
+    CUDA_TRY(cudaMalloc(&e->d_rank, sizeof(int32_t) * B));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
@@ -420,7 +583,9 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     if (!e) return RAMP_OK;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
-    for (auto& t : e->templates) cudaFree(t.blob);
+    for (auto& t : e->templates) { cudaFree(t.blob); cudaFree(t.res_blob); }
+    cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank);
+    cudaFree(e->d_res_scratch); cudaFree(e->sa_chunk_items); cudaFree(e->sa_chunks);
     cudaFree(e->d_templates); cudaFree(e->d_memo_keys); cudaFree(e->d_memo_vals); cudaFree(e->d_memo_keys2);
     free_result_slots(e->res); free_result_slots(e->sa_res);
     cudaFree(e->pool.n_active); cudaFree(e->pool.tick); cudaFree(e->pool.top);
@@ -543,12 +708,38 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
     d.kd_kmask = kd_kmask; d.kd_cmask = kd_cmask; d.kd_cshift = kd_cshift; d.kd_fshift = kd_fshift; d.kd_dshift = kd_dshift; d._pad1 = 0;
     d.scratch_bytes = scratch_bytes_for(N, E);
     d.algorithmic_bytes_static = 20ull * (uint64_t)N + 19ull * (uint64_t)E + 24ull;
+    // ---- symmetry quotient -> resident blob for the thread-per-lookahead kernel ----
+    d.res_blob = nullptr; d.res_bytes = 0; d.res_n_ops = 0; d.res_n_deps = 0; d._pad2 = 0;
+    if (e->use_resident) {
+        ramp_quotient_t q{};
+        const int qrc = e->use_quotient ? ramp_quotient_template(j, &q) : identity_quotient(j, &q);
+        if (qrc != RAMP_OK) { cudaFree(ht.blob); return set_error(qrc, "ramp_quotient_template failed (%d)", qrc); }
+        std::vector<unsigned char> rblob;
+        if (build_resident_blob(j, q, e->res_max_bytes, rblob)) {
+            cudaError_t ce = cudaMalloc(&ht.res_blob, rblob.size());
+            if (ce == cudaSuccess) ce = cudaMemcpy(ht.res_blob, rblob.data(), rblob.size(), cudaMemcpyHostToDevice);
+            if (ce != cudaSuccess) { ramp_free_quotient(&q); cudaFree(ht.blob); return set_error(RAMP_ERR_CUDA, "resident blob upload failed: %s", cudaGetErrorString(ce)); }
+            d.res_blob = (const unsigned char*)ht.res_blob; d.res_bytes = (int32_t)rblob.size();
+            d.res_n_ops = q.n_ops; d.res_n_deps = q.n_deps;
+            d.size_class = 2;
+            e->res_tmpl_cap = std::max(e->res_tmpl_cap, (int32_t)align_up((uint64_t)rblob.size(), 128));
+            e->res_n_cap = std::max(e->res_n_cap, (int32_t)align_up((uint64_t)q.n_ops, 2));
+            e->res_spill_ops = std::max(e->res_spill_ops, q.n_ops);
+            e->res_spill_deps = std::max(e->res_spill_deps, std::max(q.n_deps, 1));
+        }
+        if (e->debug) fprintf(stderr, "[ramp] template %d: N=%d E=%d W=%d C=%d -> quotient N=%d E=%d W=%d C=%d, %s (%zu B)\n", (int)e->templates.size(),
+                              N, E, W, C, q.n_ops, q.n_deps, q.n_workers, q.n_channels, d.res_blob ? "resident" : "not resident", rblob.size());
+        ramp_free_quotient(&q);
+    }
+    if (d.size_class == 2) e->n_resident++; else e->n_nonresident++;
     const int32_t id = (int32_t)e->templates.size();
     CUDA_TRY(cudaMemcpy(e->d_templates + id, &d, sizeof(TemplateDev), cudaMemcpyHostToDevice));
-    e->max_scratch = std::max(e->max_scratch, d.scratch_bytes);
-    e->max_w = std::max(e->max_w, W);
-    e->max_c = std::max(e->max_c, std::max(C, 1));
-    if (d.par_in_smem) e->par_cap = std::max(e->par_cap, (int32_t)align_up((uint64_t)N, 16));
+    if (d.size_class != 2) {       // the warp / CTA kernels' slabs and shared-memory tables are sized by the jobs that use them
+        e->max_scratch = std::max(e->max_scratch, d.scratch_bytes);
+        e->max_w = std::max(e->max_w, W);
+        e->max_c = std::max(e->max_c, std::max(C, 1));
+        if (d.par_in_smem) e->par_cap = std::max(e->par_cap, (int32_t)align_up((uint64_t)N, 16));
+    }
     e->templates.push_back(std::move(ht));
     *id_out = id;
     return RAMP_OK;
@@ -599,7 +790,8 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
         // allowed: every action must then be Action(); still need a scratch-less plan
     }
     CUDA_TRY(cudaSetDevice(e->cfg.device));
-    if (!e->templates.empty()) { int rc = ensure_scratch(e); if (rc != RAMP_OK) return rc; }
+    if (e->n_nonresident > 0) { int rc = ensure_scratch(e); if (rc != RAMP_OK) return rc; }
+    if (e->n_resident > 0) { int rc = ensure_thread_scratch(e); if (rc != RAMP_OK) return rc; }
     const int B = e->cfg.n_episodes;
     cudaStream_t st = e->stream;
     CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(int32_t), st));   // both work lists' counts and cursors
@@ -608,11 +800,26 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
     p.ep = e->ep; p.memo.keys = e->d_memo_keys; p.memo.mask = e->memo_cap - 1; p.memo.mode = e->cfg.memo_mode;
     p.memo.vals = e->d_memo_vals; p.memo.keys2 = e->d_memo_keys2; p.memo.mask2 = e->memo_cap2 - 1;
     p.memo.slot2_base = (int32_t)e->memo_cap + e->cfg.n_episodes;
-    p.items = e->d_items; p.items_big = e->d_items_big; p.counters = e->d_counters; p.stats = e->d_stats;
+    p.items = e->d_items; p.items_big = e->d_items_big; p.items_res = e->d_items_res; p.counters = e->d_counters; p.stats = e->d_stats;
     ramp_plan_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
     e->launches++;
     if (!e->templates.empty()) {
         if (e->ev_pending >= MAX_EVENT_PAIRS) { CUDA_TRY(cudaStreamSynchronize(st)); int rc = resolve_events(e); if (rc) return rc; }
+        CUDA_TRY(cudaEventRecord(e->ev_a[e->ev_pending], st));
+        if (e->n_resident > 0) {
+            // memo misses on resident templates: grouped by template into chunks of <= 32, one THREAD per lookahead.  No
+            // host read-back: the counts stay on the device, idle CTAs find the chunk cursor exhausted and exit.
+            BucketArgs ba{};
+            ba.items = e->d_items_res; ba.n_items = &e->d_counters->n_work_res; ba.n_templates = (int32_t)e->templates.size();
+            ba.tcount = e->d_tcount; ba.tbase = e->d_tbase; ba.chunk_items = e->d_chunk_items; ba.chunks = e->d_chunks;
+            ba.n_chunks = &e->d_counters->n_chunks; ba.cursor = &e->d_counters->chunk_cursor; ba.rank = e->d_rank;
+            ramp_bucket_kernel<<<1, 1024, 0, st>>>(ba);
+            ThreadArgs ta = make_thread_args(e, e->d_chunks, &e->d_counters->n_chunks, &e->d_counters->chunk_cursor, e->d_chunk_items,
+                                             e->res, e->pool, e->d_stats);
+            ramp_lookahead_thread_kernel<<<e->res_grid, 32, e->res_smem, st>>>(ta);
+            e->launches += 2;
+        }
+        if (e->n_nonresident > 0) {
         // the number of memo misses of each size class decides the kernel shapes: a 16-byte read-back (~10 us) against
         // multi-ms kernels
         CUDA_TRY(cudaMemcpyAsync(e->h_n_work, &e->d_counters->n_work, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
@@ -622,7 +829,6 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
             LookaheadArgs a = make_lookahead_args(e, e->d_items, e->d_counters, e->res, true, e->d_stats);
             LookaheadArgs ab = a;
             ab.items = e->d_items_big; ab.n_work = &e->d_counters->n_work_big; ab.cursor = &e->d_counters->work_cursor_big;
-            CUDA_TRY(cudaEventRecord(e->ev_a[e->ev_pending], st));
             const int wpb = e->nt / 32;
             const int warp_slots = e->grid * wpb;
             // The big lookaheads set the step's latency, the small ones its load.  While everything fits the SMs' warp slots
@@ -676,9 +882,10 @@ int ramp_step_device(ramp_engine_t* e, const ramp_action_t* d_actions, int32_t f
                 }
                 e->launches++;
             }
-            CUDA_TRY(cudaEventRecord(e->ev_b[e->ev_pending], st));
-            e->ev_pending++;
         }
+        }
+        CUDA_TRY(cudaEventRecord(e->ev_b[e->ev_pending], st));
+        e->ev_pending++;
     }
     StepArgs s{};
     s.actions = d_actions; s.ep = e->ep; s.res = e->res; s.pool = e->pool; s.counters = e->d_counters;
@@ -817,28 +1024,61 @@ int ramp_run_lookaheads(ramp_engine_t* e, const int32_t* template_ids, int32_t n
     for (int32_t k = 0; k < n; ++k)
         if (template_ids[k] < 0 || template_ids[k] >= (int32_t)e->templates.size())
             return set_error(RAMP_ERR_BAD_ARG, "template id %d at %d is not registered", template_ids[k], k);
-    int rc = ensure_scratch(e);
-    if (rc != RAMP_OK) return rc;
+    std::vector<int32_t> res_idx, old_idx;
+    for (int32_t k = 0; k < n; ++k) (e->templates[template_ids[k]].dev.size_class == 2 ? res_idx : old_idx).push_back(k);
+    int rc = RAMP_OK;
+    if (!old_idx.empty()) { rc = ensure_scratch(e); if (rc != RAMP_OK) return rc; }
+    if (!res_idx.empty()) { rc = ensure_thread_scratch(e); if (rc != RAMP_OK) return rc; }
     cudaStream_t st = e->stream;
     if (n > e->sa_cap) {
         CUDA_TRY(cudaStreamSynchronize(st));
-        free_result_slots(e->sa_res); cudaFree(e->sa_items);
+        free_result_slots(e->sa_res); cudaFree(e->sa_items); cudaFree(e->sa_chunk_items); cudaFree(e->sa_chunks);
         if (alloc_result_slots(e->sa_res, n) != RAMP_OK) return RAMP_ERR_CUDA;
         CUDA_TRY(cudaMalloc(&e->sa_items, sizeof(WorkItem) * n));
+        CUDA_TRY(cudaMalloc(&e->sa_chunk_items, sizeof(WorkItem) * (size_t)n * 32));
+        CUDA_TRY(cudaMalloc(&e->sa_chunks, sizeof(ChunkDesc) * n));
         e->sa_cap = n;
     }
     if (!e->sa_counters) CUDA_TRY(cudaMalloc(&e->sa_counters, sizeof(Counters)));
-    std::vector<WorkItem> items(n);
-    for (int32_t k = 0; k < n; ++k) { items[k].template_id = template_ids[k]; items[k].slot = k; items[k].episode = -1; items[k].n_mounted_workers = 0; }
-    Counters c{}; c.n_work = n;
-    CUDA_TRY(cudaMemcpyAsync(e->sa_items, items.data(), sizeof(WorkItem) * n, cudaMemcpyHostToDevice, st));
+    std::vector<WorkItem> items(old_idx.size());
+    for (size_t q = 0; q < old_idx.size(); ++q) {
+        const int32_t k = old_idx[q];
+        items[q].template_id = template_ids[k]; items[q].slot = k; items[q].episode = -1; items[q].n_mounted_workers = 0;
+    }
+    // resident templates: chunks of <= 32 items of one template, built here (the step path builds them on the device)
+    std::vector<ChunkDesc> chunks;
+    std::vector<WorkItem> chunk_items;
+    {
+        std::vector<int32_t> order(res_idx);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return template_ids[x] < template_ids[y]; });
+        for (size_t q = 0; q < order.size();) {
+            const int32_t t = template_ids[order[q]];
+            size_t r = q;
+            while (r < order.size() && template_ids[order[r]] == t && r - q < 32) ++r;
+            ChunkDesc cd; cd.template_id = t; cd.count = (int32_t)(r - q);
+            chunks.push_back(cd);
+            const size_t base = chunk_items.size();
+            chunk_items.resize(base + 32);
+            for (size_t x = q; x < r; ++x) {
+                WorkItem& it = chunk_items[base + (x - q)];
+                it.template_id = t; it.slot = order[x]; it.episode = -1; it.n_mounted_workers = 0;
+            }
+            q = r;
+        }
+    }
+    Counters c{}; c.n_work = (int32_t)old_idx.size(); c.n_chunks = (int32_t)chunks.size();
+    if (!items.empty()) CUDA_TRY(cudaMemcpyAsync(e->sa_items, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, st));
+    if (!chunks.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(e->sa_chunks, chunks.data(), sizeof(ChunkDesc) * chunks.size(), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(e->sa_chunk_items, chunk_items.data(), sizeof(WorkItem) * chunk_items.size(), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaMemcpyAsync(e->sa_counters, &c, sizeof(Counters), cudaMemcpyHostToDevice, st));
     // traces of standalone runs go to a private pool sized n x trace_cap when requested
     TracePool priv{};
     const bool want_trace = trace_n && trace_tick && trace_cap > 0;
     unsigned long long* d_top = nullptr;
     if (want_trace) {
-        priv.len = (uint64_t)n * (uint64_t)std::min(trace_cap, e->cfg.trace_cap);
+        priv.len = (uint64_t)n * (uint64_t)e->cfg.trace_cap;      // the kernels allocate n_ticks entries per lookahead; truncated on copy-out
         CUDA_TRY(cudaMalloc(&priv.n_active, sizeof(int32_t) * priv.len));
         CUDA_TRY(cudaMalloc(&priv.tick, sizeof(double) * priv.len));
         CUDA_TRY(cudaMalloc(&d_top, sizeof(unsigned long long)));
@@ -850,11 +1090,22 @@ int ramp_run_lookaheads(ramp_engine_t* e, const int32_t* template_ids, int32_t n
     cudaEvent_t ea = e->ev_a[MAX_EVENT_PAIRS - 1], eb = e->ev_b[MAX_EVENT_PAIRS - 1];
     if (e->ev_pending >= MAX_EVENT_PAIRS - 1) { CUDA_TRY(cudaStreamSynchronize(st)); rc = resolve_events(e); if (rc) return rc; }
     CUDA_TRY(cudaEventRecord(ea, st));
-    int n_big = 0;
-    for (int32_t k = 0; k < n; ++k) n_big += e->templates[template_ids[k]].dev.size_class;
-    launch_lookahead(e, a, n, n_big, st);
+    if (!chunks.empty()) {
+        TracePool tp = want_trace ? priv : e->pool;
+        if (!want_trace) tp.top = nullptr;
+        ThreadArgs ta = make_thread_args(e, e->sa_chunks, &e->sa_counters->n_chunks, &e->sa_counters->chunk_cursor, e->sa_chunk_items,
+                                         e->sa_res, tp, nullptr);
+        const int g = std::max(1, std::min(e->res_grid, (int)chunks.size()));
+        ramp_lookahead_thread_kernel<<<g, 32, e->res_smem, st>>>(ta);
+        e->launches++;
+    }
+    if (!old_idx.empty()) {
+        int n_big = 0;
+        for (int32_t k : old_idx) n_big += e->templates[template_ids[k]].dev.size_class == 1 ? 1 : 0;
+        launch_lookahead(e, a, (int)old_idx.size(), n_big, st);
+        e->launches++;
+    }
     CUDA_TRY(cudaEventRecord(eb, st));
-    e->launches++;
     CUDA_TRY(cudaGetLastError());
     std::vector<double> jct(n), comm(n), comp(n);
     std::vector<int32_t> nt(n), stt(n);

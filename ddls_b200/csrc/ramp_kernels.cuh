@@ -34,7 +34,8 @@ struct TemplateDev {
     int32_t n_ops, n_deps, n_workers, n_channels;
     int32_t num_training_steps, model_id, degree, n_src;
     int32_t canon_id;           // id of the first registered byte-identical template (exact memo key)
-    int32_t size_class;         // 0: small (one warp per lookahead is fastest), 1: big (one CTA per lookahead is fastest)
+    int32_t size_class;         // 0: small (one warp per lookahead is fastest), 1: big (one CTA per lookahead is fastest),
+                                // 2: resident (quotient blob in shared memory, one THREAD per lookahead)
     int32_t par_in_smem;        // parent counters fit the shared-memory byte counters (max in-degree <= 255, N <= par_cap)
     int32_t _pad0;
     const int4*     op_rec;       // [N] by op index: {cost.lo, cost.hi, key, worker}
@@ -50,6 +51,11 @@ struct TemplateDev {
     const int32_t*  src_ops;      // [n_src] ops with in-degree 0: the initial ops_ready (JOB:474-481)
     uint64_t scratch_bytes;       // HBM-side dynamic state one running lookahead of this template may need
     uint64_t algorithmic_bytes_static; // 20 N + 19 E + 24, + 12 T added per run
+    // symmetry quotient (ramp_quotient.cpp) packed for the thread-per-lookahead kernel (ramp_lookahead_thread.cuh): one blob
+    // that is bulk-copied into shared memory; null when the job is not resident-eligible (size_class 0 / 1 then)
+    const unsigned char* res_blob;
+    int32_t res_bytes;            // multiple of 16
+    int32_t res_n_ops, res_n_deps, _pad2;
 };
 
 struct WorkItem {
@@ -85,9 +91,13 @@ struct Counters {               // the first four words are zeroed at the start 
     int32_t work_cursor_big;
     int32_t err_episode;        // first episode that recorded an error (+1), 0 if none
     int32_t err_status;
+    int32_t n_work_res;         // work list 2: lookaheads on resident (quotient) templates; zeroed at the start of every step
+    int32_t n_chunks;           // chunks ramp_bucket_kernel made of list 2
+    int32_t chunk_cursor;
+    int32_t _pad;
 };
 
-struct MemoStats { unsigned long long lookups, hits, lookaheads, alg_bytes, shared_hits; };
+struct MemoStats { unsigned long long lookups, hits, lookaheads, alg_bytes, shared_hits, quotient_bytes; };
 
 // running-job table fields (SoA: [field][row][episode])
 enum { RF_JCT = 0, RF_STARTED, RF_COMM, RF_COMP, RF_UTIL, RF_PART_OP_MEM, RF_PART_DEP, RF_FLOW, RF_ORIG_OP_MEM,
@@ -710,6 +720,7 @@ __global__ void __launch_bounds__(WPB * 32) ramp_lookahead_kernel(const Lookahea
 
 }  // namespace ramp
 #include "ramp_lookahead_cta.cuh"
+#include "ramp_lookahead_thread.cuh"
 namespace ramp {
 
 // ---------------------------------------------------------------------------------------------------
@@ -723,6 +734,7 @@ struct PlanArgs {
     MemoTable memo;
     WorkItem* items;                // [B] small lookaheads
     WorkItem* items_big;            // [B] big lookaheads
+    WorkItem* items_res;            // [B] lookaheads on resident templates
     Counters* counters;
     MemoStats* stats;
 };
@@ -797,7 +809,8 @@ __global__ void ramp_plan_kernel(const PlanArgs p) {
     ei[EI_PLAN_RAN * B + b] = ran ? 1 : 0;
     if (ran) {
         WorkItem it; it.template_id = act.template_id; it.slot = slot; it.episode = b; it.n_mounted_workers = act.n_mounted_workers;
-        if (T.size_class) p.items_big[atomicAdd(&p.counters->n_work_big, 1)] = it;
+        if (T.size_class == 2) p.items_res[atomicAdd(&p.counters->n_work_res, 1)] = it;
+        else if (T.size_class) p.items_big[atomicAdd(&p.counters->n_work_big, 1)] = it;
         else p.items[atomicAdd(&p.counters->n_work, 1)] = it;
     }
 }

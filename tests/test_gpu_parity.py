@@ -27,7 +27,9 @@ def eng_mod():
     return engine
 
 
-MODES = ['warp', 'cta']      # both lookahead kernels: one warp per lookahead / one CTA per lookahead
+# every lookahead kernel: one THREAD per lookahead on the symmetry quotient (the default whenever the quotient fits shared
+# memory), the same kernel on the unfolded job, one warp per lookahead, one CTA per lookahead
+MODES = ['thread', 'thread_unfolded', 'warp', 'cta']
 
 
 def _run_all_templates(engine, templates, n_cluster_workers=64, repeat=1, mode='auto'):
@@ -284,7 +286,8 @@ def test_infinite_tick_raises_like_reference(eng_mod):
     eng.close()
 
 
-@pytest.mark.parametrize('mode,cta_threads', [('warp', '0'), ('cta', '64'), ('cta', '128'), ('cta', '256'), ('auto', '0')])
+@pytest.mark.parametrize('mode,cta_threads', [('warp', '0'), ('cta', '64'), ('cta', '128'), ('cta', '256'), ('auto', '0'),
+                                               ('thread_unfolded', '0')])
 def test_many_mixed_items_per_launch(mode, cta_threads, eng_mod, oracle_lib):
     """Hundreds of lookaheads of four very different sizes in one launch, persistent CTAs/warps processing several items
     each: every result equals the oracle's (this configuration once exposed a shared-memory race in the CTA kernel)."""
@@ -376,7 +379,8 @@ def _fan_template(M, W, seed):
                       mount=MountScalars(n_mounted_workers=W)).canonicalise()
 
 
-@pytest.mark.parametrize('mode,cta_threads', [('warp', '0'), ('cta', '64'), ('cta', '128'), ('cta', '256')])
+@pytest.mark.parametrize('mode,cta_threads', [('warp', '0'), ('cta', '64'), ('cta', '128'), ('cta', '256'), ('thread', '0'),
+                                               ('thread_unfolded', '0')])
 @pytest.mark.parametrize('M,W', [(200, 4), (3000, 6)])
 def test_wide_fan_overflows_every_shared_memory_list(M, W, mode, cta_threads, eng_mod, oracle_lib):
     import os
