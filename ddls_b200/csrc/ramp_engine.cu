@@ -154,6 +154,7 @@ struct ramp_engine {
     int32_t* d_tcount = nullptr;         // [max_templates + 1]
     int32_t* d_tbase = nullptr;
     int32_t* d_rank = nullptr;           // [B]
+    TemplateHints* d_hints = nullptr;    // [max_templates]
     // standalone lookahead buffers
     WorkItem* sa_chunk_items = nullptr;
     ChunkDesc* sa_chunks = nullptr;
@@ -347,7 +348,7 @@ bool build_resident_blob(const ramp_lowered_job_t* j, const ramp_quotient_t& q, 
         if (q.op_weight[c] > 0xFFFF || in_total[c] > 0xFFFF || q.op_threshold[c] > 0xFFFFFFFFu) return false;   // u16 counters never wrap
     const int kbits = bits_for_u64(max_key), cbits = bits_for_u64((uint64_t)q.n_channels + 1);
     const int ibits = bits_for_u64(max_inc), nbits = bits_for_u64((uint64_t)N);
-    if (kbits + cbits + 1 + ibits + nbits > 64 || kbits > 32 || cbits > 31 || ibits > 31) return false;
+    if (kbits + cbits > 32 || 1 + ibits + nbits > 32) return false;     // dep word = two 32-bit halves
     std::vector<int32_t> in_deg(N, 0), src;
     for (int32_t k = 0; k < E; ++k) in_deg[q.dep_dst[k]]++;
     for (int32_t c = 0; c < N; ++c) if (in_deg[c] == 0) src.push_back(c);
@@ -355,7 +356,7 @@ bool build_resident_blob(const ramp_lowered_job_t* j, const ramp_quotient_t& q, 
     h.n_ops = N; h.n_deps = E; h.n_workers = q.n_workers; h.n_channels = q.n_channels;
     h.n_src = (int32_t)src.size(); h.num_training_steps = j->num_training_steps; h.orig_workers = j->n_workers;
     h.kmask = (uint32_t)((1ull << kbits) - 1ull); h.cmask = (uint32_t)((1ull << cbits) - 1ull); h.imask = (uint32_t)((1ull << ibits) - 1ull);
-    h.cshift = kbits; h.fshift = kbits + cbits; h.ishift = kbits + cbits + 1; h.dshift = kbits + cbits + 1 + ibits;
+    h.cshift = kbits; h.fshift = 0; h.ishift = 1; h.dshift = 1 + ibits;
     size_t off = sizeof(ResHeader);
     const size_t off_rec = off;                 off += align_up((uint64_t)N * 16, 16);
     h.off_op_row = (int32_t)off;                off += align_up((uint64_t)N * 8, 16);
@@ -380,8 +381,9 @@ bool build_resident_blob(const ramp_lowered_job_t* j, const ramp_quotient_t& q, 
     }
     for (int32_t k = 0; k < E; ++k) {
         const unsigned long long chan = (q.dep_channel[k] == 0xFFFFFFFFu) ? (unsigned long long)h.cmask : (unsigned long long)q.dep_channel[k];
-        kd[k] = (unsigned long long)q.dep_key[k] | (chan << h.cshift) | ((unsigned long long)(q.dep_is_flow[k] ? 1 : 0) << h.fshift)
-                | ((unsigned long long)q.dep_inc[k] << h.ishift) | ((unsigned long long)q.dep_dst[k] << h.dshift);
+        const uint32_t lo = q.dep_key[k] | (uint32_t)(chan << h.cshift);
+        const uint32_t hi = (q.dep_is_flow[k] ? 1u : 0u) | (q.dep_inc[k] << h.ishift) | ((uint32_t)q.dep_dst[k] << h.dshift);
+        kd[k] = (unsigned long long)lo | ((unsigned long long)hi << 32);
         rt[k] = q.dep_run_time[k] + 0.0;
     }
     if (!src.empty()) memcpy(blob.data() + h.off_src, src.data(), sizeof(int32_t) * src.size());
@@ -449,7 +451,7 @@ ThreadArgs make_thread_args(ramp_engine* e, const ChunkDesc* chunks, const int32
     a.scratch = e->d_res_scratch; a.scratch_stride = e->res_scratch_stride;
     a.res = res; a.pool = pool; a.trace_cap = e->cfg.trace_cap;
     a.tmpl_cap = e->res_tmpl_cap; a.n_cap = e->res_n_cap; a.spill_ops = e->res_spill_ops; a.spill_deps = e->res_spill_deps;
-    a.stats = stats;
+    a.stats = stats; a.hints = e->d_hints;
     return a;
 }
 
@@ -543,6 +545,8 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     CUDA_TRY(cudaMemset(e->d_tcount, 0, sizeof(int32_t) * ((size_t)cfg.max_templates + 1)));
     CUDA_TRY(cudaMalloc(&e->d_tbase, sizeof(int32_t) * ((size_t)cfg.max_templates + 1)));
     CUDA_TRY(cudaMalloc(&e->d_rank, sizeof(int32_t) * B));
+    CUDA_TRY(cudaMalloc(&e->d_hints, sizeof(TemplateHints) * (size_t)cfg.max_templates));
+    CUDA_TRY(cudaMemset(e->d_hints, 0, sizeof(TemplateHints) * (size_t)cfg.max_templates));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
@@ -584,7 +588,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     for (auto& t : e->templates) { cudaFree(t.blob); cudaFree(t.res_blob); }
-    cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank);
+    cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank); cudaFree(e->d_hints);
     cudaFree(e->d_res_scratch); cudaFree(e->sa_chunk_items); cudaFree(e->sa_chunks);
     cudaFree(e->d_templates); cudaFree(e->d_memo_keys); cudaFree(e->d_memo_vals); cudaFree(e->d_memo_keys2);
     free_result_slots(e->res); free_result_slots(e->sa_res);

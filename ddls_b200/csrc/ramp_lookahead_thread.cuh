@@ -45,14 +45,19 @@ namespace ramp {
 struct ResHeader {
     int32_t n_ops, n_deps, n_workers, n_channels;      // classes, entries, worker groups, channel groups
     int32_t n_src, num_training_steps, orig_workers, _pad0;
-    uint32_t kmask, cmask, imask, _pad1;               // dep word: key | chan << cshift | flow << fshift | inc << ishift | child << dshift
-    int32_t cshift, fshift, ishift, dshift;
+    uint32_t kmask, cmask, imask, _pad1;               // dep word lo: key | channel group << cshift (all ones: none);
+    int32_t cshift, fshift, ishift, dshift;            // dep word hi: flow | inc << 1 | child << dshift  (fshift = 0, ishift = 1)
     int32_t off_op_row, off_op_thr, off_dep_kd, off_dep_rt;   // byte offsets from the blob start (op records follow the header)
     int32_t off_src, total_bytes, _pad2, _pad3;
 };
 static_assert(sizeof(ResHeader) == 96, "resident header is 96 bytes");
 
 struct ChunkDesc { int32_t template_id, count; };      // up to 32 work items of one template; items at [chunk * 32 + lane]
+
+// recorded by the first lookahead of a template that completes (deterministic per template): lets later ones write their trace
+// in place and keep every list in shared memory
+struct __align__(16) TemplateHints { int32_t n_ticks, max_o, max_f, max_nf; };   // read / written as ONE 16-byte access
+
 
 struct ThreadArgs {
     const TemplateDev* templates;
@@ -69,16 +74,17 @@ struct ThreadArgs {
     int32_t n_cap;                  // parent-counter slots per lane in shared memory
     int32_t spill_ops, spill_deps;  // per-lane spill capacities (entries) in the HBM slab
     MemoStats* stats;
+    TemplateHints* hints;           // [max_templates], zero = nothing recorded yet
 };
 
 __host__ __device__ inline size_t thread_smem_bytes(int tmpl_cap, int n_cap) {
-    size_t per_lane = (size_t)RAMP_T_FCAP * 16 + (size_t)RAMP_T_OCAP * 20 + (size_t)RAMP_T_NFCAP * 8
+    size_t per_lane = (size_t)RAMP_T_FCAP * 16 + (size_t)RAMP_T_OCAP * 20 + (size_t)RAMP_T_NFCAP * 4
                       + (size_t)(RAMP_T_WCAP + RAMP_T_CCAP) * 4 + (size_t)n_cap * 2;
     return (size_t)tmpl_cap + 32 * per_lane + 64;
 }
 __host__ __device__ inline uint64_t thread_scratch_bytes(int spill_ops, int spill_deps, int trace_cap) {
-    // per lane: ops spill (record 16 + index 4), flows spill (16), non-flow spill (8), temp trace (tick 8 + n 4)
-    const uint64_t per_lane = (uint64_t)spill_ops * 20 + (uint64_t)spill_deps * 24 + (uint64_t)trace_cap * 12;
+    // per lane: ops spill (record 16 + index 4), flows spill (16), non-flow spill (4), temp trace (tick 8 + n 4)
+    const uint64_t per_lane = (uint64_t)spill_ops * 20 + (uint64_t)spill_deps * 20 + (uint64_t)trace_cap * 12;
     return align_up(per_lane * 32, 256);
 }
 
@@ -143,57 +149,306 @@ __global__ void __launch_bounds__(1024) ramp_bucket_kernel(const BucketArgs a) {
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// lane-interleaved arrays: element k of this lane at base[k * 32 + lane]; the first CAP entries in shared memory,
-// the rest in the CTA's HBM slab
-// one ready op class: {remaining.lo, remaining.hi, key, worker group | class size << 16} + its class index;
-// one ready flow entry: {remaining.lo, remaining.hi, dep word.lo, dep word.hi}: nothing the tick loop needs is behind a second load
+// Lane-interleaved per-lane lists (element k of this lane at base[k * 32 + lane]).  SPILL: entries past the shared-memory
+// capacity live in the CTA's HBM slab; !SPILL: the template's recorded frontier sizes (TemplateHints) fit the capacity.
+//   ready op class   {remaining.lo, remaining.hi, key, worker group | class size << 16} + its class index
+//   ready flow entry {remaining.lo, remaining.hi, dep word lo (key | channel group << cshift), dep word hi (flow | inc << 1 | child << dshift)}
+//   ready non-flow   dep word hi
+// nothing the tick loop needs about a ready item is behind a second load
+template <bool SPILL>
 struct LaneOps {
     int4* a_sm; int32_t* i_sm; int4* a_gl; int32_t* i_gl; int lane;
-    __device__ __forceinline__ int4 rec(int k) const { return (k < RAMP_T_OCAP) ? a_sm[k * 32 + lane] : a_gl[(size_t)(k - RAMP_T_OCAP) * 32 + lane]; }
-    __device__ __forceinline__ int idx(int k) const { return (k < RAMP_T_OCAP) ? i_sm[k * 32 + lane] : i_gl[(size_t)(k - RAMP_T_OCAP) * 32 + lane]; }
+    __device__ __forceinline__ int4 rec(int k) const {
+        if (!SPILL || k < RAMP_T_OCAP) return a_sm[k * 32 + lane];
+        return a_gl[(size_t)(k - RAMP_T_OCAP) * 32 + lane];
+    }
+    __device__ __forceinline__ int idx(int k) const {
+        if (!SPILL || k < RAMP_T_OCAP) return i_sm[k * 32 + lane];
+        return i_gl[(size_t)(k - RAMP_T_OCAP) * 32 + lane];
+    }
     __device__ __forceinline__ void put(int k, const int4 r, int i) const {
-        if (k < RAMP_T_OCAP) { a_sm[k * 32 + lane] = r; i_sm[k * 32 + lane] = i; }
+        if (!SPILL || k < RAMP_T_OCAP) { a_sm[k * 32 + lane] = r; i_sm[k * 32 + lane] = i; }
         else { a_gl[(size_t)(k - RAMP_T_OCAP) * 32 + lane] = r; i_gl[(size_t)(k - RAMP_T_OCAP) * 32 + lane] = i; }
     }
 };
+template <bool SPILL>
 struct LaneFlows {
     int4* sm; int4* gl; int lane;
-    __device__ __forceinline__ int4 get(int k) const { return (k < RAMP_T_FCAP) ? sm[k * 32 + lane] : gl[(size_t)(k - RAMP_T_FCAP) * 32 + lane]; }
-    __device__ __forceinline__ void put(int k, const int4 v) const { if (k < RAMP_T_FCAP) sm[k * 32 + lane] = v; else gl[(size_t)(k - RAMP_T_FCAP) * 32 + lane] = v; }
+    __device__ __forceinline__ int4 get(int k) const {
+        if (!SPILL || k < RAMP_T_FCAP) return sm[k * 32 + lane];
+        return gl[(size_t)(k - RAMP_T_FCAP) * 32 + lane];
+    }
+    __device__ __forceinline__ void put(int k, const int4 v) const {
+        if (!SPILL || k < RAMP_T_FCAP) sm[k * 32 + lane] = v; else gl[(size_t)(k - RAMP_T_FCAP) * 32 + lane] = v;
+    }
 };
+template <bool SPILL>
 struct LaneNF {
-    unsigned long long* sm; unsigned long long* gl; int lane;
-    __device__ __forceinline__ unsigned long long get(int k) const { return (k < RAMP_T_NFCAP) ? sm[k * 32 + lane] : gl[(size_t)(k - RAMP_T_NFCAP) * 32 + lane]; }
-    __device__ __forceinline__ void put(int k, unsigned long long v) const { if (k < RAMP_T_NFCAP) sm[k * 32 + lane] = v; else gl[(size_t)(k - RAMP_T_NFCAP) * 32 + lane] = v; }
+    uint32_t* sm; uint32_t* gl; int lane;
+    __device__ __forceinline__ uint32_t get(int k) const {
+        if (!SPILL || k < RAMP_T_NFCAP) return sm[k * 32 + lane];
+        return gl[(size_t)(k - RAMP_T_NFCAP) * 32 + lane];
+    }
+    __device__ __forceinline__ void put(int k, uint32_t v) const {
+        if (!SPILL || k < RAMP_T_NFCAP) sm[k * 32 + lane] = v; else gl[(size_t)(k - RAMP_T_NFCAP) * 32 + lane] = v;
+    }
 };
-__device__ __forceinline__ unsigned long long kd_of(const int4 f) { return ((unsigned long long)(uint32_t)f.w << 32) | (unsigned long long)(uint32_t)f.z; }
+
+struct LaneCtx {                      // what one lane's lookahead works on
+    const unsigned char* tm;         // template blob in shared memory
+    int4* f_sm; int4* o_sm; uint32_t* nf_sm; int32_t* oi_sm; uint32_t* wk_sm; uint32_t* ck_sm; uint16_t* cnt_sm;
+    int4* f_gl; int4* o_gl; uint32_t* nf_gl; int32_t* oi_gl;
+    int32_t* tr_n; double* tr_tick;  // trace destination: element k at [k * tr_stride]
+    int tr_stride, tr_cap;
+    int lane, n_cap;
+};
+
+struct LaneResult { double t, comm, comp; int tick_no, status, max_o, max_f, max_nf; };
+
+// _run_lookahead for one lane.  SPILL = false: every frontier fits its shared-memory capacity (TemplateHints);
+// SIMPLE = true: one worker group and at most one channel group (the usual quotient of a partitioned job): the winner is the
+// largest key, no tables.
+template <bool SPILL, bool SIMPLE>
+__device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
+    const int lane = x.lane;
+    const ResHeader& H = *reinterpret_cast<const ResHeader*>(x.tm);
+    const int4* op_rec = reinterpret_cast<const int4*>(x.tm + sizeof(ResHeader));                  // {cost.lo, cost.hi, key, worker | weight << 16}
+    const int2* op_row = reinterpret_cast<const int2*>(x.tm + H.off_op_row);
+    const uint32_t* op_thr = reinterpret_cast<const uint32_t*>(x.tm + H.off_op_thr);
+    const uint2* dep_kd = reinterpret_cast<const uint2*>(x.tm + H.off_dep_kd);
+    const double* dep_rt = reinterpret_cast<const double*>(x.tm + H.off_dep_rt);
+    const int32_t* src_ops = reinterpret_cast<const int32_t*>(x.tm + H.off_src);
+    const int N = H.n_ops, E = H.n_deps, W = H.n_workers, C = H.n_channels;
+    const uint32_t kmask = H.kmask, cmask = H.cmask, imask = H.imask;
+    const int csh = H.cshift, dsh = H.dshift;
+    const bool tab_w = (W <= RAMP_T_WCAP), tab_c = (C <= RAMP_T_CCAP);
+    const LaneOps<SPILL> ops{x.o_sm, x.oi_sm, x.o_gl, x.oi_gl, lane};
+    const LaneFlows<SPILL> flows{x.f_sm, x.f_gl, lane};
+    const LaneNF<SPILL> nfs{x.nf_sm, x.nf_gl, lane};
+    uint16_t* cnt = x.cnt_sm + lane;
+    uint32_t* wk = x.wk_sm + lane;
+    uint32_t* ck = x.ck_sm + lane;
+    const double INF = __longlong_as_double(RAMP_INF_BITS);
+
+    for (int i = 0; i < N && i < x.n_cap; ++i) cnt[i * 32] = 0;
+    int nO = H.n_src, nF = 0, nNF = 0;
+    for (int k = 0; k < nO; ++k) { const int op = src_ops[k]; ops.put(k, op_rec[op], op); }       // RCE:1334
+    LaneResult R;
+    R.t = 0.0; R.comm = 0.0; R.comp = 0.0; R.tick_no = 0; R.max_o = nO; R.max_f = 0; R.max_nf = 0;
+    R.status = (N <= x.n_cap) ? RAMP_ST_OK : RAMP_ST_TABLE_FULL;                                    // cannot happen (eligibility)
+    int ops_completed = 0, deps_completed = 0;
+    int32_t* tn_ptr = x.tr_n;
+    double* tt_ptr = x.tr_tick;
+
+    while (R.status == RAMP_ST_OK) {
+        // ---- A, B: winners per worker group: largest key; t_op = min of their remaining times ----
+        double t_op = INF;
+        int n_active = 0;
+        uint32_t best_w = 0u;                 // SIMPLE: the winner's key
+        if (nO > 0) {
+            if (SIMPLE) {
+                _Pragma("unroll 1")
+                for (int k = 0; k < nO; ++k) {
+                    const int4 r = ops.rec(k);
+                    if ((uint32_t)r.z > best_w) { best_w = (uint32_t)r.z; t_op = __hiloint2double(r.y, r.x); n_active = (int)((uint32_t)r.w >> 16); }
+                }
+            } else if (tab_w) {
+                _Pragma("unroll 1")
+                for (int w = 0; w < W; ++w) wk[w * 32] = 0u;
+                _Pragma("unroll 1")
+                for (int k = 0; k < nO; ++k) {
+                    const int4 r = ops.rec(k);
+                    const int w = r.w & 0xffff;
+                    if ((uint32_t)r.z > wk[w * 32]) wk[w * 32] = (uint32_t)r.z;
+                }
+                _Pragma("unroll 1")
+                for (int k = 0; k < nO; ++k) {
+                    const int4 r = ops.rec(k);
+                    if (wk[(r.w & 0xffff) * 32] == (uint32_t)r.z) {
+                        const double rem = __hiloint2double(r.y, r.x);
+                        t_op = (rem < t_op) ? rem : t_op;
+                        n_active += (int)((uint32_t)r.w >> 16);
+                    }
+                }
+            } else {
+                // more worker groups than table slots: pairwise comparison; the winners are marked in bit 31 of the key
+                // (keys are ranks <= N < 2^31) for phase G, which clears the mark
+                _Pragma("unroll 1")
+                for (int k = 0; k < nO; ++k) {
+                    int4 r = ops.rec(k);
+                    bool win = true;
+                    _Pragma("unroll 1")
+                    for (int j = 0; j < nO && win; ++j) {
+                        const int4 r2 = ops.rec(j);
+                        if ((r2.w & 0xffff) == (r.w & 0xffff) && ((uint32_t)r2.z & 0x7fffffffu) > (uint32_t)r.z) win = false;
+                    }
+                    if (win) {
+                        const double rem = __hiloint2double(r.y, r.x);
+                        t_op = (rem < t_op) ? rem : t_op;
+                        n_active += (int)((uint32_t)r.w >> 16);
+                        r.z = (int)((uint32_t)r.z | 0x80000000u);
+                        ops.put(k, r, ops.idx(k));
+                    }
+                }
+            }
+        }
+        // ---- C, D ----
+        const bool any_nf = nNF > 0;
+        double t_comm = 0.0;
+        if (!any_nf) {
+            t_comm = INF;
+            if (nF > 0) {
+                if (SIMPLE) {
+                    uint32_t best = 0u;
+                    _Pragma("unroll 1")
+                    for (int k = 0; k < nF; ++k) {
+                        const int4 f = flows.get(k);
+                        if (((uint32_t)f.z >> csh) == cmask) continue;                               // no channel: ticks, never a winner
+                        const uint32_t key = (uint32_t)f.z & kmask;
+                        const double rem = __hiloint2double(f.y, f.x);
+                        if (key > best) { best = key; t_comm = rem; }
+                        else if (key == best) t_comm = (rem < t_comm) ? rem : t_comm;
+                    }
+                } else if (tab_c) {
+                    _Pragma("unroll 1")
+                    for (int q = 0; q < C; ++q) ck[q * 32] = 0u;
+                    _Pragma("unroll 1")
+                    for (int k = 0; k < nF; ++k) {
+                        const uint32_t lo = (uint32_t)flows.get(k).z;
+                        const uint32_t q = lo >> csh;
+                        if (q != cmask) { const uint32_t key = lo & kmask; if (key > ck[q * 32]) ck[q * 32] = key; }
+                    }
+                    _Pragma("unroll 1")
+                    for (int k = 0; k < nF; ++k) {
+                        const int4 f = flows.get(k);
+                        const uint32_t q = (uint32_t)f.z >> csh;
+                        if (q != cmask && ck[q * 32] == ((uint32_t)f.z & kmask)) {
+                            const double rem = __hiloint2double(f.y, f.x);
+                            t_comm = (rem < t_comm) ? rem : t_comm;
+                        }
+                    }
+                } else {
+                    _Pragma("unroll 1")
+                    for (int k = 0; k < nF; ++k) {
+                        const int4 f = flows.get(k);
+                        const uint32_t q = (uint32_t)f.z >> csh;
+                        if (q == cmask) continue;
+                        const uint32_t key = (uint32_t)f.z & kmask;
+                        bool win = true;
+                        _Pragma("unroll 1")
+                        for (int j = 0; j < nF && win; ++j) {
+                            const uint32_t lo2 = (uint32_t)flows.get(j).z;
+                            if ((lo2 >> csh) == q && (lo2 & kmask) > key) win = false;
+                        }
+                        if (win) { const double rem = __hiloint2double(f.y, f.x); t_comm = (rem < t_comm) ? rem : t_comm; }
+                    }
+                }
+            }
+        }
+        // ---- E, I, J ----
+        const double tick = (t_comm < t_op) ? t_comm : t_op;
+        {
+            if ((!any_nf) && (nF > 0)) R.comm = __dadd_rn(R.comm, tick);                             // RCE:434-439, 777-791
+            if (n_active > 0) R.comp = __dadd_rn(R.comp, tick);
+            R.t = __dadd_rn(R.t, tick);
+            if (R.tick_no < x.tr_cap) { *tn_ptr = n_active; *tt_ptr = tick; tn_ptr += x.tr_stride; tt_ptr += x.tr_stride; }
+            else R.status = RAMP_ST_TRACE_OVERFLOW;
+            ++R.tick_no;
+        }
+        // ---- H ----
+        int tailO = nO;                       // ops readied in this tick are appended behind the current frontier
+        auto complete_dep = [&](const uint32_t hi) {                                                // JOB:525-536
+            const int child = (int)(hi >> dsh);
+            const uint32_t inc = (hi >> 1) & imask;
+            const uint32_t old = cnt[child * 32];
+            const uint32_t thr = op_thr[child];
+            const uint32_t neu = old + inc;
+            cnt[child * 32] = (uint16_t)neu;
+            if (old < thr && thr <= neu) { ops.put(tailO, op_rec[child], child); ++tailO; }         // JOB:531 for every member
+        };
+        if (any_nf) {
+            _Pragma("unroll 1")
+            for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
+            deps_completed += nNF;
+            nNF = 0;
+        } else {
+            int p = 0;
+            _Pragma("unroll 1")
+            for (int k = 0; k < nF; ++k) {
+                int4 f = flows.get(k);
+                const double r2 = tick_down(__hiloint2double(f.y, f.x), tick);                      // JOB:561
+                if (r2 == 0.0) { complete_dep((uint32_t)f.w); ++deps_completed; }                   // JOB:562
+                else { f.x = __double2loint(r2); f.y = __double2hiint(r2); flows.put(p, f); ++p; }
+            }
+            nF = p;
+        }
+        // ---- G ----
+        int p = 0;
+        _Pragma("unroll 1")
+        for (int k = 0; k < nO; ++k) {
+            int4 r = ops.rec(k);
+            const int op = ops.idx(k);
+            bool win;
+            if (SIMPLE) win = (uint32_t)r.z == best_w;
+            else if (tab_w) win = wk[(r.w & 0xffff) * 32] == (uint32_t)r.z;
+            else { win = r.z < 0; r.z &= 0x7fffffff; }
+            if (win) {                                                                              // this tick's winner
+                const double rem = tick_down(__hiloint2double(r.y, r.x), tick);                     // JOB:555
+                if (rem == 0.0) {                                                                   // JOB:556
+                    ++ops_completed;
+                    const int2 row = op_row[op];
+                    _Pragma("unroll 1")
+                    for (int e = row.x; e < row.x + row.y; ++e) {                                   // JOB:496-506
+                        const uint2 kd = dep_kd[e];
+                        if (kd.y & 1u) {
+                            const double rt = dep_rt[e];
+                            flows.put(nF, make_int4(__double2loint(rt), __double2hiint(rt), (int)kd.x, (int)kd.y));
+                            ++nF;
+                        } else { nfs.put(nNF, kd.y); ++nNF; }
+                    }
+                    continue;
+                }
+                r.x = __double2loint(rem); r.y = __double2hiint(rem);
+            }
+            ops.put(p, r, op); ++p;
+        }
+        _Pragma("unroll 1")
+        for (int k = nO; k < tailO; ++k, ++p) { if (p != k) ops.put(p, ops.rec(k), ops.idx(k)); }
+        nO = p;
+        if (SPILL) {                          // the sizes the fast path relies on next time (TemplateHints)
+            R.max_o = (tailO > R.max_o) ? tailO : R.max_o;
+            R.max_f = (nF > R.max_f) ? nF : R.max_f;
+            R.max_nf = (nNF > R.max_nf) ? nNF : R.max_nf;
+        }
+        // ---- K, L ----
+        if ((ops_completed == N) && (deps_completed == E)) break;                                   // JOB:549-551
+        if (isinf(tick)) { R.status = RAMP_ST_INFINITE_TICK; break; }                               // RCE:462
+    }
+    return R;
+}
 
 __global__ void __launch_bounds__(32) ramp_lookahead_thread_kernel(const ThreadArgs a) {
     extern __shared__ __align__(128) unsigned char smem_thr[];
     __shared__ __align__(8) unsigned long long mbar;
     const int lane = threadIdx.x;
-    unsigned char* tm = smem_thr;                                   // template blob
     unsigned char* st = smem_thr + a.tmpl_cap;                      // per-lane state, by decreasing alignment
-    int4* f_sm = reinterpret_cast<int4*>(st);                                            // [FCAP][32]
-    int4* o_sm = f_sm + RAMP_T_FCAP * 32;                                                // [OCAP][32]
-    unsigned long long* nf_sm = reinterpret_cast<unsigned long long*>(o_sm + RAMP_T_OCAP * 32);   // [NFCAP][32]
-    int32_t*  oi_sm = reinterpret_cast<int32_t*>(nf_sm + RAMP_T_NFCAP * 32);            // [OCAP][32]
-    uint32_t* wk_sm = reinterpret_cast<uint32_t*>(oi_sm + RAMP_T_OCAP * 32);             // [WCAP][32]
-    uint32_t* ck_sm = wk_sm + RAMP_T_WCAP * 32;                                          // [CCAP][32]
-    uint16_t* cnt_sm = reinterpret_cast<uint16_t*>(ck_sm + RAMP_T_CCAP * 32);            // [n_cap][32]
-
+    LaneCtx x;
+    x.tm = smem_thr;                                                // template blob
+    x.f_sm = reinterpret_cast<int4*>(st);                                                // [FCAP][32]
+    x.o_sm = x.f_sm + RAMP_T_FCAP * 32;                                                  // [OCAP][32]
+    x.nf_sm = reinterpret_cast<uint32_t*>(x.o_sm + RAMP_T_OCAP * 32);                    // [NFCAP][32]
+    x.oi_sm = reinterpret_cast<int32_t*>(x.nf_sm + RAMP_T_NFCAP * 32);                   // [OCAP][32]
+    x.wk_sm = reinterpret_cast<uint32_t*>(x.oi_sm + RAMP_T_OCAP * 32);                   // [WCAP][32]
+    x.ck_sm = x.wk_sm + RAMP_T_WCAP * 32;                                                // [CCAP][32]
+    x.cnt_sm = reinterpret_cast<uint16_t*>(x.ck_sm + RAMP_T_CCAP * 32);                  // [n_cap][32]
     unsigned char* slab = a.scratch + (uint64_t)blockIdx.x * a.scratch_stride;
-    int4* f_gl = reinterpret_cast<int4*>(slab);                                          // [spill_deps][32]
-    int4* o_gl = f_gl + (size_t)a.spill_deps * 32;                                       // [spill_ops][32]
-    unsigned long long* nf_gl = reinterpret_cast<unsigned long long*>(o_gl + (size_t)a.spill_ops * 32);   // [spill_deps][32]
-    double*  tr_tick = reinterpret_cast<double*>(nf_gl + (size_t)a.spill_deps * 32);    // [trace_cap][32]
-    int32_t* oi_gl = reinterpret_cast<int32_t*>(tr_tick + (size_t)a.trace_cap * 32);    // [spill_ops][32]
-    int32_t* tr_n = oi_gl + (size_t)a.spill_ops * 32;                                    // [trace_cap][32]
-
-    const LaneOps ops{o_sm, oi_sm, o_gl, oi_gl, lane};
-    const LaneFlows flows{f_sm, f_gl, lane};
-    const LaneNF nfs{nf_sm, nf_gl, lane};
-    const double INF = __longlong_as_double(RAMP_INF_BITS);
+    x.f_gl = reinterpret_cast<int4*>(slab);                                              // [spill_deps][32]
+    x.o_gl = x.f_gl + (size_t)a.spill_deps * 32;                                         // [spill_ops][32]
+    double* tmp_tick = reinterpret_cast<double*>(x.o_gl + (size_t)a.spill_ops * 32);     // [trace_cap][32]
+    x.nf_gl = reinterpret_cast<uint32_t*>(tmp_tick + (size_t)a.trace_cap * 32);          // [spill_deps][32]
+    x.oi_gl = reinterpret_cast<int32_t*>(x.nf_gl + (size_t)a.spill_deps * 32);           // [spill_ops][32]
+    int32_t* tmp_n = x.oi_gl + (size_t)a.spill_ops * 32;                                 // [trace_cap][32]
+    x.lane = lane; x.n_cap = a.n_cap;
 
     if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
@@ -219,7 +474,7 @@ __global__ void __launch_bounds__(32) ramp_lookahead_thread_kernel(const ThreadA
                 const uint32_t bytes = (uint32_t)TD.res_bytes;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(tm)), "l"(TD.res_blob), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
+                             ::"r"(smem_u32(smem_thr)), "l"(TD.res_blob), "r"(bytes), "r"(smem_u32(&mbar)) : "memory");
             }
             asm volatile(
                 "{\n"
@@ -233,237 +488,82 @@ __global__ void __launch_bounds__(32) ramp_lookahead_thread_kernel(const ThreadA
             phase ^= 1u;
             loaded = ch.template_id;
         }
+        // what an earlier lookahead of this template recorded: number of ticks and the largest frontiers (deterministic per
+        // template).  With it the trace goes straight to an exactly-sized pool allocation and no list can leave shared memory.
+        TemplateHints hint;
+        { const int4 hv = __ldcg(reinterpret_cast<const int4*>(&a.hints[ch.template_id])); hint.n_ticks = hv.x; hint.max_o = hv.y; hint.max_f = hv.z; hint.max_nf = hv.w; }
+        const bool fast = hint.n_ticks > 0 && hint.n_ticks <= a.trace_cap && hint.max_o <= RAMP_T_OCAP && hint.max_f <= RAMP_T_FCAP
+                          && hint.max_nf <= RAMP_T_NFCAP;
         if (lane < ch.count) {
             const WorkItem item = a.items[(size_t)c * 32 + lane];
-            const ResHeader& H = *reinterpret_cast<const ResHeader*>(tm);
-            const int4* op_rec = reinterpret_cast<const int4*>(tm + sizeof(ResHeader));           // {cost.lo, cost.hi, key, worker | weight << 16}
-            const int2* op_row = reinterpret_cast<const int2*>(tm + H.off_op_row);
-            const uint32_t* op_thr = reinterpret_cast<const uint32_t*>(tm + H.off_op_thr);
-            const unsigned long long* dep_kd = reinterpret_cast<const unsigned long long*>(tm + H.off_dep_kd);
-            const double* dep_rt = reinterpret_cast<const double*>(tm + H.off_dep_rt);
-            const int32_t* src_ops = reinterpret_cast<const int32_t*>(tm + H.off_src);
-            const int N = H.n_ops, E = H.n_deps, W = H.n_workers, C = H.n_channels;
-            const uint32_t kmask = H.kmask, cmask = H.cmask, imask = H.imask;
-            const int csh = H.cshift, fsh = H.fshift, ish = H.ishift, dsh = H.dshift;
-            const bool one_w = (W == 1), one_c = (C <= 1);
-            const bool tab_w = (W <= RAMP_T_WCAP), tab_c = (C <= RAMP_T_CCAP);
-            for (int i = 0; i < N && i < a.n_cap; ++i) cnt_sm[i * 32 + lane] = 0;
-
-            int nO = H.n_src, nF = 0, nNF = 0;
-            for (int k = 0; k < nO; ++k) { const int op = src_ops[k]; ops.put(k, op_rec[op], op); }   // RCE:1334
-            int ops_completed = 0, deps_completed = 0, tick_no = 0;
-            int status = (N <= a.n_cap) ? RAMP_ST_OK : RAMP_ST_TABLE_FULL;                           // cannot happen (eligibility)
-            double t = 0.0, comm = 0.0, comp = 0.0;
-
-            while (status == RAMP_ST_OK) {
-                // ---- A, B: winners per worker group: largest key; t_op = min of their remaining times ----
-                double t_op = INF;
-                int n_active = 0;
-                uint32_t best_w = 0u;                 // one worker group: the winner's key
-                if (nO > 0) {
-                    if (one_w) {
-                        for (int k = 0; k < nO; ++k) {
-                            const int4 r = ops.rec(k);
-                            if ((uint32_t)r.z > best_w) { best_w = (uint32_t)r.z; t_op = __hiloint2double(r.y, r.x); n_active = (int)((uint32_t)r.w >> 16); }
-                        }
-                    } else if (tab_w) {
-                        for (int w = 0; w < W; ++w) wk_sm[w * 32 + lane] = 0u;
-                        for (int k = 0; k < nO; ++k) {
-                            const int4 r = ops.rec(k);
-                            const int w = r.w & 0xffff;
-                            if ((uint32_t)r.z > wk_sm[w * 32 + lane]) wk_sm[w * 32 + lane] = (uint32_t)r.z;
-                        }
-                        for (int k = 0; k < nO; ++k) {
-                            const int4 r = ops.rec(k);
-                            if (wk_sm[(r.w & 0xffff) * 32 + lane] == (uint32_t)r.z) {
-                                const double rem = __hiloint2double(r.y, r.x);
-                                t_op = (rem < t_op) ? rem : t_op;
-                                n_active += (int)((uint32_t)r.w >> 16);
-                            }
-                        }
-                    } else {
-                        // more worker groups than table slots: pairwise comparison; the winners are marked in bit 31 of the key
-                        // (keys are ranks <= N < 2^31) for phase G, which clears the mark
-                        for (int k = 0; k < nO; ++k) {
-                            int4 r = ops.rec(k);
-                            bool win = true;
-                            for (int j = 0; j < nO && win; ++j) {
-                                const int4 r2 = ops.rec(j);
-                                if ((r2.w & 0xffff) == (r.w & 0xffff) && ((uint32_t)r2.z & 0x7fffffffu) > (uint32_t)r.z) win = false;
-                            }
-                            if (win) {
-                                const double rem = __hiloint2double(r.y, r.x);
-                                t_op = (rem < t_op) ? rem : t_op;
-                                n_active += (int)((uint32_t)r.w >> 16);
-                                r.z = (int)((uint32_t)r.z | 0x80000000u);
-                                ops.put(k, r, ops.idx(k));
-                            }
-                        }
-                    }
-                }
-                // ---- C, D ----
-                const bool any_nf = nNF > 0;
-                double t_comm = 0.0;
-                if (!any_nf) {
-                    t_comm = INF;
-                    if (nF > 0) {
-                        if (one_c) {
-                            uint32_t best = 0u;
-                            for (int k = 0; k < nF; ++k) {
-                                const int4 f = flows.get(k);
-                                const unsigned long long kd = kd_of(f);
-                                if (((uint32_t)(kd >> csh) & cmask) == cmask) continue;               // no channel: ticks, never a winner
-                                const uint32_t key = (uint32_t)kd & kmask;
-                                const double rem = __hiloint2double(f.y, f.x);
-                                if (key > best) { best = key; t_comm = rem; }
-                                else if (key == best) t_comm = (rem < t_comm) ? rem : t_comm;
-                            }
-                        } else if (tab_c) {
-                            for (int q = 0; q < C; ++q) ck_sm[q * 32 + lane] = 0u;
-                            for (int k = 0; k < nF; ++k) {
-                                const unsigned long long kd = kd_of(flows.get(k));
-                                const uint32_t q = (uint32_t)(kd >> csh) & cmask;
-                                if (q != cmask) {
-                                    const uint32_t key = (uint32_t)kd & kmask;
-                                    if (key > ck_sm[q * 32 + lane]) ck_sm[q * 32 + lane] = key;
-                                }
-                            }
-                            for (int k = 0; k < nF; ++k) {
-                                const int4 f = flows.get(k);
-                                const unsigned long long kd = kd_of(f);
-                                const uint32_t q = (uint32_t)(kd >> csh) & cmask;
-                                if (q != cmask && ck_sm[q * 32 + lane] == ((uint32_t)kd & kmask)) {
-                                    const double rem = __hiloint2double(f.y, f.x);
-                                    t_comm = (rem < t_comm) ? rem : t_comm;
-                                }
-                            }
-                        } else {
-                            for (int k = 0; k < nF; ++k) {
-                                const int4 f = flows.get(k);
-                                const unsigned long long kd = kd_of(f);
-                                const uint32_t q = (uint32_t)(kd >> csh) & cmask;
-                                if (q == cmask) continue;
-                                const uint32_t key = (uint32_t)kd & kmask;
-                                bool win = true;
-                                for (int j = 0; j < nF && win; ++j) {
-                                    const unsigned long long kd2 = kd_of(flows.get(j));
-                                    if (((uint32_t)(kd2 >> csh) & cmask) == q && ((uint32_t)kd2 & kmask) > key) win = false;
-                                }
-                                if (win) { const double rem = __hiloint2double(f.y, f.x); t_comm = (rem < t_comm) ? rem : t_comm; }
-                            }
-                        }
-                    }
-                }
-                // ---- E, I, J ----
-                const double tick = (t_comm < t_op) ? t_comm : t_op;
-                {
-                    const bool ticked_ops = n_active > 0;
-                    const bool ticked_flows = (!any_nf) && (nF > 0);                                  // RCE:434-439
-                    if (ticked_flows) comm = __dadd_rn(comm, tick);
-                    if (ticked_ops) comp = __dadd_rn(comp, tick);
-                    t = __dadd_rn(t, tick);
-                    if (tick_no < a.trace_cap) { tr_n[(size_t)tick_no * 32 + lane] = n_active; tr_tick[(size_t)tick_no * 32 + lane] = tick; }
-                    else status = RAMP_ST_TRACE_OVERFLOW;
-                    ++tick_no;
-                }
-                // ---- H ----
-                int tailO = nO;                       // ops readied in this tick are appended behind the current frontier
-                auto complete_dep = [&](const unsigned long long kd) {                              // JOB:525-536
-                    const int child = (int)(kd >> dsh);
-                    const uint32_t inc = (uint32_t)(kd >> ish) & imask;
-                    const uint32_t old = cnt_sm[child * 32 + lane];
-                    const uint32_t thr = op_thr[child];
-                    const uint32_t neu = old + inc;
-                    cnt_sm[child * 32 + lane] = (uint16_t)neu;
-                    if (old < thr && thr <= neu) { ops.put(tailO, op_rec[child], child); ++tailO; }   // JOB:531 for every member
-                };
-                if (any_nf) {
-                    for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
-                    deps_completed += nNF;
-                    nNF = 0;
-                } else {
-                    int p = 0;
-                    for (int k = 0; k < nF; ++k) {
-                        int4 f = flows.get(k);
-                        const double r2 = tick_down(__hiloint2double(f.y, f.x), tick);              // JOB:561
-                        if (r2 == 0.0) { complete_dep(kd_of(f)); ++deps_completed; }                // JOB:562
-                        else { f.x = __double2loint(r2); f.y = __double2hiint(r2); flows.put(p, f); ++p; }
-                    }
-                    nF = p;
-                }
-                // ---- G ----
-                int p = 0;
-                for (int k = 0; k < nO; ++k) {
-                    int4 r = ops.rec(k);
-                    const int op = ops.idx(k);
-                    bool win;
-                    if (one_w) win = (uint32_t)r.z == best_w;
-                    else if (tab_w) win = wk_sm[(r.w & 0xffff) * 32 + lane] == (uint32_t)r.z;
-                    else { win = r.z < 0; r.z &= 0x7fffffff; }
-                    if (win) {                                                                      // this tick's winner
-                        const double rem = tick_down(__hiloint2double(r.y, r.x), tick);             // JOB:555
-                        if (rem == 0.0) {                                                           // JOB:556
-                            ++ops_completed;
-                            const int2 row = op_row[op];
-                            for (int e = row.x; e < row.x + row.y; ++e) {                           // JOB:496-506
-                                const unsigned long long kd = dep_kd[e];
-                                if ((kd >> fsh) & 1ull) {
-                                    const double rt = dep_rt[e];
-                                    flows.put(nF, make_int4(__double2loint(rt), __double2hiint(rt), (int)(uint32_t)kd, (int)(uint32_t)(kd >> 32)));
-                                    ++nF;
-                                } else { nfs.put(nNF, kd); ++nNF; }
-                            }
-                            continue;
-                        }
-                        r.x = __double2loint(rem); r.y = __double2hiint(rem);
-                    }
-                    ops.put(p, r, op); ++p;
-                }
-                for (int k = nO; k < tailO; ++k, ++p) { if (p != k) ops.put(p, ops.rec(k), ops.idx(k)); }
-                nO = p;
-                // ---- K, L ----
-                const bool finished = (ops_completed == N) && (deps_completed == E);               // JOB:549-551
-                if (finished) break;
-                if (isinf(tick)) { status = RAMP_ST_INFINITE_TICK; break; }                         // RCE:462
+            const ResHeader& H = *reinterpret_cast<const ResHeader*>(x.tm);
+            const bool simple = (H.n_workers == 1) && (H.n_channels <= 1);
+            long long off = -1;
+            int status0 = RAMP_ST_OK;
+            const bool direct = fast && a.pool.top != nullptr;          // trace written in place
+            if (direct) {
+                const unsigned long long o = atomicAdd(a.pool.top, (unsigned long long)hint.n_ticks);
+                if (o + (unsigned long long)hint.n_ticks <= a.pool.len) off = (long long)o; else status0 = RAMP_ST_TRACE_OVERFLOW;
+            }
+            if (off >= 0) { x.tr_n = a.pool.n_active + off; x.tr_tick = a.pool.tick + off; x.tr_stride = 1; x.tr_cap = hint.n_ticks; }
+            else { x.tr_n = tmp_n + lane; x.tr_tick = tmp_tick + lane; x.tr_stride = 32; x.tr_cap = a.trace_cap; }
+            LaneResult R;
+            if (fast) R = simple ? thread_lookahead<false, true>(x) : thread_lookahead<false, false>(x);
+            else R = simple ? thread_lookahead<true, true>(x) : thread_lookahead<true, false>(x);
+            int status = (R.status == RAMP_ST_OK) ? status0 : R.status;
+            if (direct && status == RAMP_ST_OK && R.tick_no != hint.n_ticks) status = RAMP_ST_TRACE_OVERFLOW;   // cannot happen
+            if (!fast && status == RAMP_ST_OK) {                      // every lane of the chunk writes the same values
+                *reinterpret_cast<int4*>(&a.hints[ch.template_id]) = make_int4(R.tick_no, R.max_o, R.max_f, R.max_nf);
             }
 
             // ---- results (RCE:450-452) ----
-            const int n_rec = tick_no < a.trace_cap ? tick_no : a.trace_cap;
+            const int n_rec = R.tick_no < x.tr_cap ? R.tick_no : x.tr_cap;
             const double steps = (double)H.num_training_steps;
-            const double jct = __dmul_rn(t, steps);
+            const double jct = __dmul_rn(R.t, steps);
             const int nmw = item.n_mounted_workers > 0 ? item.n_mounted_workers : H.orig_workers;
             const bool can_util = (status == RAMP_ST_OK);
-            long long off = -1;
-            if (a.pool.top != nullptr) {
+            if (!direct && a.pool.top != nullptr) {
                 const unsigned long long o = atomicAdd(a.pool.top, (unsigned long long)n_rec);
                 if (o + (unsigned long long)n_rec <= a.pool.len) off = (long long)o;
                 else if (status == RAMP_ST_OK) status = RAMP_ST_TRACE_OVERFLOW;
             }
             double util = 0.0;
-            {                                                                                       // RCE:830-832, tick order
+            {
+                // RCE:830-832: util = sum over ticks, in tick order, of (n_active / n_mounted_workers) * (tick / jct).  A term
+                // with n_active == 0 or tick == 0 is +0.0 (jct > 0 finite) and adding +0.0 leaves the non-negative sum as it
+                // is, so those ticks are skipped (about two thirds of them); n_active / n_mounted_workers is re-used while
+                // n_active repeats.  Same f64 operations on the same values for every term that can change the sum.
                 const double dn = (double)nmw;
-                int32_t* pn = (off >= 0) ? a.pool.n_active + off : nullptr;
-                double* pt = (off >= 0) ? a.pool.tick + off : nullptr;
+                const bool copy = (!direct) && off >= 0;
+                int32_t* pn = copy ? a.pool.n_active + off : nullptr;
+                double* pt = copy ? a.pool.tick + off : nullptr;
+                const int32_t* sn = x.tr_n; const double* stt = x.tr_tick; const int sstr = x.tr_stride;
+                const bool skip_zero = can_util && (jct > 0.0) && !isinf(jct);
+                int last_n = -1;
+                double last_q = 0.0;
 #pragma unroll 4
                 for (int k = 0; k < n_rec; ++k) {
-                    const int nk = tr_n[(size_t)k * 32 + lane];
-                    const double tk = tr_tick[(size_t)k * 32 + lane];
-                    if (pn) { pn[k] = nk; pt[k] = tk; }
-                    if (can_util) util = __dadd_rn(util, __dmul_rn(__ddiv_rn((double)nk, dn), __ddiv_rn(tk, jct)));
+                    const int nk = sn[(size_t)k * sstr];
+                    const double tk = stt[(size_t)k * sstr];
+                    if (copy) { pn[k] = nk; pt[k] = tk; }
+                    if (!can_util) continue;
+                    if (skip_zero && (nk == 0 || tk == 0.0)) continue;
+                    if (nk != last_n) { last_n = nk; last_q = __ddiv_rn((double)nk, dn); }
+                    util = __dadd_rn(util, __dmul_rn(last_q, __ddiv_rn(tk, jct)));
                 }
             }
             a.res.jct[item.slot] = jct;
-            a.res.comm[item.slot] = __dmul_rn(comm, steps);
-            a.res.comp[item.slot] = __dmul_rn(comp, steps);
-            a.res.n_ticks[item.slot] = tick_no;
+            a.res.comm[item.slot] = __dmul_rn(R.comm, steps);
+            a.res.comp[item.slot] = __dmul_rn(R.comp, steps);
+            a.res.n_ticks[item.slot] = R.tick_no;
             a.res.util[item.slot] = can_util ? util : 0.0;
             a.res.util_nmw[item.slot] = can_util ? nmw : -1;
             a.res.trace_off[item.slot] = off;
             a.res.status[item.slot] = status;
             if (a.stats) {
                 atomicAdd(&a.stats->lookaheads, 1ull);
-                atomicAdd(&a.stats->alg_bytes, (unsigned long long)(TD.algorithmic_bytes_static + 12ull * (unsigned long long)tick_no));
-                atomicAdd(&a.stats->quotient_bytes, (unsigned long long)(20ull * N + 19ull * E + 24ull + 12ull * (unsigned long long)tick_no));
+                atomicAdd(&a.stats->alg_bytes, (unsigned long long)(TD.algorithmic_bytes_static + 12ull * (unsigned long long)R.tick_no));
+                atomicAdd(&a.stats->quotient_bytes, (unsigned long long)(20ull * H.n_ops + 19ull * H.n_deps + 24ull + 12ull * (unsigned long long)R.tick_no));
             }
         }
         __syncwarp();
