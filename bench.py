@@ -2,7 +2,8 @@
 """bench.py -- env-steps/s of the batched RAMP cluster simulator hot path on B200.
 
     python bench.py --gpus N --steps K --warmup W            # product arm (CUDA kernels through the C ABI)
-    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on all host threads
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the unmodified Python reference (oracle/_ref), one
+                                                              # process per core; the C port of its algorithm beside it
 
 One bench "step" = one batched env-step: every one of the B episodes takes one agent decision, i.e. one
 ``RampClusterEnvironment.step(action)`` plus the ``step(Action())`` calls until the next job is queued
@@ -24,12 +25,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 must print ONE JSON line on stdout: NCCL prints its version banner at every level >= VERSION (WARN included), so
-# its log goes to stderr
+# rank 0 must print ONE JSON line on stdout: NCCL's log (whatever NCCL_DEBUG level the caller asked for) goes to stderr
 if not os.environ.get('NCCL_DEBUG_FILE'):
     os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
-if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO') and not os.environ.get('RAMP_KEEP_NCCL_DEBUG'):
-    os.environ['NCCL_DEBUG'] = 'WARN'
 
 METRIC = 'env_steps_per_sec'
 UNIT = 'env-steps/s'
@@ -48,7 +46,46 @@ def parse_args():
     ap.add_argument('--cpu-sample', type=int, default=0, help='episodes in the CPU baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--memo-mode', type=int, default=0)
+    ap.add_argument('--run-times', default='reference', choices=['reference', 'one_to_one'],
+                    help="dep run times of the scripted jobs: 'reference' = the reference pipeline's lowered jobs on an empty cluster "
+                         "(collectives; T=1,334 for the degree-16 bench job), 'one_to_one' = round 1's lighter stand-in (T=1,169)")
+    ap.add_argument('--ref-budget', type=float, default=90.0, help='--impl reference: seconds of timed env-steps per process')
+    ap.add_argument('--ref-procs', type=int, default=0, help='--impl reference: processes (0 = min(usable cores, 32))')
+    ap.add_argument('--ref-kind', default='auto', choices=['auto', 'reference', 'port'])
     return ap.parse_args()
+
+
+def usable_cores():
+    """Host threads this process may really use: the scheduler affinity mask capped by the cgroup CPU quota (a leased box can
+    report 128 CPUs in os.cpu_count() and still be limited to a fraction of them)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:                       # cgroup v2
+            q, per = f.read().split()
+            if q != 'max':
+                quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())  # cgroup v1
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    eff = n if quota is None else max(1, min(n, int(quota + 0.5)))
+    return {'affinity': n, 'cgroup_quota': quota, 'os_cpu_count': os.cpu_count(), 'used': eff}
+
+
+def workload_config(args, cfg, templates, world, B):
+    """The `config` object of the JSON line: the same keys for the product arm and the reference arm."""
+    return {'workload': args.config, 'episodes_per_gpu': B, 'segment': args.segment,
+            'cluster': 'x'.join(map(str, cfg['shape'])) + ' RAMP', 'degrees': list(cfg['degrees']),
+            'templates': [[t.n_ops, t.n_deps] for t in templates], 'run_times': args.run_times, 'memo_mode': args.memo_mode,
+            'agent': 'random partition degree + first-fit blocks (stand-in for the PAC-ML GNN policy)'}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -123,15 +160,19 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per lookahead-kernel launch from the committed ncu summary of this bench command, if any."""
-    p = os.path.join(ROOT, 'profiles', 'ncu_lookahead_summary.json')
+def ncu_profile_summary():
+    """STATIC figures from the committed ncu capture of this bench command (profiles/r2_ncu_thread_summary.json, written by
+    scripts/ncu_summary.py): DRAM bytes per lookahead launch and warp instructions per lookahead.  Not measured in this run --
+    counters need ncu, and a number taken under a profiler is never a bench value -- so they carry their source."""
+    p = os.path.join(ROOT, 'profiles', 'r2_ncu_thread_summary.json')
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get('dram_bytes_per_launch')
+            d = json.load(open(p))
+            return {'dram_bytes_per_launch': d.get('dram_bytes_per_launch'), 'warp_inst_per_lookahead': d.get('warp_inst_per_lookahead'),
+                    'source': 'static, from profiles/r2_ncu_thread_summary.json'}
         except Exception:
-            return None
-    return None
+            pass
+    return {'source': 'no committed ncu summary'}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -142,51 +183,97 @@ def oracle_jcts(templates):
 
 
 def run_reference_arm(args, rank, world):
-    """The CPU arm: the oracle port (oracle/ramp_oracle.c, the C restatement of the reference's algorithm; the
-    Python reference itself cannot travel to the GPU box) on all host threads, same scripted workload."""
+    """The CPU arm.  kind "reference": the UNMODIFIED Python reference (staged at oracle/_ref by oracle/stage_ref.py, or
+    the build container's checkout) -- RampJobPartitioningEnvironment with its own heuristic agents on the same
+    topology / job graphs / degree rule, one process per core (the reference is single-threaded; RLlib runs one env per
+    worker process), each taking --steps env-steps or as many as fit --ref-budget seconds (oracle/ref_runner.py).
+    kind "port": oracle/ramp_oracle.c (the C restatement of the reference's algorithm) on all usable host threads, when the
+    reference is not available.  The port's figure is always reported too (`port`), on the same scripted workload as the GPU arm."""
     if rank != 0:
         return
-    import ctypes as C
+    from ddls_b200 import workload
+    cores = usable_cores()
+    cfg = workload.CONFIGS[args.config]
+    B = args.episodes or cfg['n_episodes']
+    L = args.segment
+    templates = workload.build_templates(args.config, run_times=args.run_times)[3]
+    config = workload_config(args, cfg, templates, world, B)
+    port = port_throughput(args, cores['used'], budget_s=8.0)
+    from oracle import ref_shim
+    have_ref = ref_shim.reference_available()          # staged copy (oracle/_ref) or the build container's checkout
+    kind = args.ref_kind if args.ref_kind != 'auto' else ('reference' if have_ref else 'port')
+    if kind == 'reference' and not have_ref:
+        kind = 'port'
+    base = {'metric': METRIC, 'unit': UNIT, 'n_gpus': args.gpus, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference', 'config': config, 'host_cores': cores, 'port': port}
+    if kind == 'port':
+        value = port['value']
+        line = dict(base, value=value, steps=args.steps, warmup=args.warmup, ms_per_step=B / value * 1e3,
+                    cpu_baseline={'value': value, 'unit': UNIT, 'cores': cores['used'], 'kind': 'port', 'sample': port['sample'],
+                                  'per_core': value / cores['used']},
+                    e2e={'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
+        print(json.dumps(line), flush=True)
+        return
+    P = args.ref_procs or max(1, min(cores['used'], 32))
+    warm = 1 if args.warmup > 0 else 0
+    t0 = time.perf_counter()
+    procs = []
+    for k in range(P):
+        cmd = [sys.executable, os.path.join(ROOT, 'oracle', 'ref_runner.py'), '--config', args.config, '--steps', str(args.steps),
+               '--warmup', str(warm), '--budget', str(args.ref_budget), '--seed', str(args.seed + k)]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                      env=dict(os.environ, OMP_NUM_THREADS='1', MKL_NUM_THREADS='1', OPENBLAS_NUM_THREADS='1')))
+    results, errors = [], []
+    for pr in procs:
+        out, err = pr.communicate()
+        try:
+            results.append(json.loads(out.strip().splitlines()[-1]))
+        except Exception:
+            errors.append((err or out)[-300:])
+    wall = time.perf_counter() - t0
+    if not results:
+        raise RuntimeError('every reference process failed: ' + ' | '.join(errors[:3]))
+    rates = [r['steps'] / r['elapsed_s'] for r in results]
+    value = float(sum(rates))                                  # P independent single-threaded environments running side by side
+    steps_min, steps_max = min(r['steps'] for r in results), max(r['steps'] for r in results)
+    mean_s = float(np.mean([r['elapsed_s'] / r['steps'] for r in results]))
+    line = dict(base, value=value, steps=steps_max, warmup=warm, ms_per_step=mean_s * 1e3,
+                cpu_baseline={'value': value, 'unit': UNIT, 'cores': len(results), 'kind': 'reference', 'per_core': value / len(results),
+                              'sample': f'{len(results)} processes x {steps_min}-{steps_max} env-steps of {args.config} each '
+                                        f'({mean_s:.1f} s per env-step per process, budget {args.ref_budget:.0f} s, {wall:.0f} s wall incl. '
+                                        f'imports and one warm-up step); unmodified reference from {results[0]["reference_root"]}',
+                              'failed_processes': len(errors)},
+                e2e={'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
+    print(json.dumps(line), flush=True)
+
+
+def port_throughput(args, n_threads, budget_s=10.0):
+    """oracle/ramp_oracle.c on n_threads host threads over a bounded sample of the scripted workload: env-steps/s."""
     from oracle import oracle
     from ddls_b200 import workload
     oracle.build()
     L = args.segment
-    cores = os.cpu_count() or 1
-    # bounded sample: S episodes per step-group, sized from a probe so that the whole run takes ~20-40 s
-    probe_S = min(64, max(cores, 8))
-    wl = workload.generate(args.config, oracle_jcts, n_episodes=probe_S, n_steps=L, seed=args.seed)
+    S0 = max(n_threads, 16)
+    wl = workload.generate(args.config, oracle_jcts, n_episodes=S0, n_steps=L, seed=args.seed, run_times=args.run_times)
     t0 = time.perf_counter()
-    _oracle_segment(oracle, wl, cores)
+    _oracle_segment(oracle, wl, n_threads)
     probe = time.perf_counter() - t0
-    n_groups = max(1, (args.warmup + args.steps + L - 1) // L)
-    budget = 30.0
-    S = int(min(workload.CONFIGS[args.config]['n_episodes'], max(probe_S, probe_S * budget / max(probe * n_groups, 1e-6))))
-    S = max(cores, (S // cores) * cores)
-    wl = workload.generate(args.config, oracle_jcts, n_episodes=S, n_steps=L, seed=args.seed)
-    # warm-up groups, then timed groups; one "step" of this arm = S episode-steps
-    w_groups = (args.warmup + L - 1) // L
-    k_groups = max(1, (args.steps + L - 1) // L)
-    for _ in range(max(w_groups, 1)):
-        _oracle_segment(oracle, wl, cores)
+    cap = args.episodes or workload.CONFIGS[args.config]['n_episodes']
+    S = int(max(S0, min(max(cap, S0), S0 * (budget_s / 2) / max(probe, 1e-6))))
+    S = max(n_threads, (S // n_threads) * n_threads)
+    if S != S0:
+        wl = workload.generate(args.config, oracle_jcts, n_episodes=S, n_steps=L, seed=args.seed, run_times=args.run_times)
+        _oracle_segment(oracle, wl, n_threads)      # warm-up (page in, thread start)
     t0 = time.perf_counter()
-    done_groups = 0
-    while done_groups < k_groups or (time.perf_counter() - t0) < 5.0:      # at least ~5 s of wall time for a stable figure
-        _oracle_segment(oracle, wl, cores)
-        done_groups += 1
-    dt = time.perf_counter() - t0
-    k_groups = done_groups
-    steps_done = k_groups * L
-    value = S * steps_done / dt
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps_done, 'warmup': w_groups * L,
-            'ms_per_step': dt / steps_done * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': args.config, 'episodes_per_step': S, 'segment': L, 'note':
-                       'CPU arm: oracle/ramp_oracle.c (C port of the reference algorithm) on all host threads; '
-                       'bounded sample of the same scripted workload; env-steps/s is per-episode and extrapolates linearly'},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': f'{S} episodes x {steps_done} env-steps ({dt:.1f} s)'},
-            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    reps = 0
+    while reps < 1 or (time.perf_counter() - t0) < budget_s / 2:
+        _oracle_segment(oracle, wl, n_threads)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    value = S * L / dt
+    return {'value': value, 'unit': UNIT, 'cores': n_threads, 'kind': 'port', 'per_core': value / n_threads,
+            'sample': f'{S} episodes x {L} env-steps of {args.config}, {reps} repetitions, {dt:.2f} s wall each on {n_threads} threads '
+                      f'(oracle/ramp_oracle.c)'}
 
 
 def _oracle_segment(oracle, wl, n_threads):
@@ -239,7 +326,7 @@ def run_b200_arm(args, rank, world, local_rank):
         assert (res['status'] == 0).all()
         return res['jct']
 
-    wl = workload.generate(args.config, engine_jcts, n_episodes=B, n_steps=L, seed=args.seed + 1000 * rank)
+    wl = workload.generate(args.config, engine_jcts, n_episodes=B, n_steps=L, seed=args.seed + 1000 * rank, run_times=args.run_times)
     actions_host = []
     for p in range(L):
         a = wl.actions[p].copy()
@@ -401,28 +488,43 @@ def run_b200_arm(args, rank, world, local_rank):
         peak, peak_src = measured_peaks()
         la_ms = kt['total_ms']
         achieved = (kt['algorithmic_bytes'] / 1e9) / (la_ms / 1e3) if la_ms > 0 else 0.0
-        traffic = ncu_traffic_per_launch()
+        prof = ncu_profile_summary()
+        n_launch = max(kt['launches'], 1)
+        sm_mhz = (clocks or {}).get('sm_mhz') or 1965.0
+        roofline = {
+            'bound': 'hbm', 'kernel': 'ramp_lookahead_thread_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak if peak else None, 'peak_source': peak_src,
+            'definition': 'SURVEY 8d: sum over executed lookaheads of 20 N + 19 E + 12 T + 24 bytes of the LOWERED job handed to '
+                          'ramp_register_template, / CUDA-event time of the lookahead launches (bucket + thread kernel) of every step',
+            # what the kernel really touches: the symmetry quotient of each job (ramp_quotient.cpp), same formula on its sizes
+            'achieved_on_quotient': (kt.get('quotient_bytes', 0) / 1e9) / (la_ms / 1e3) if la_ms > 0 else 0.0,
+            'quotient_bytes_per_launch': kt.get('quotient_bytes', 0) / n_launch,
+            'traffic': prof.get('dram_bytes_per_launch'), 'traffic_source': prof.get('source'),
+            'kernel_ms_per_launch': la_ms / n_launch, 'kernel_launches': kt['launches'],
+            'lookaheads': kt['work_items'], 'kernel_share_of_step': la_ms / elapsed_ms if elapsed_ms else None,
+            'algorithmic_bytes_per_launch': kt['algorithmic_bytes'] / n_launch,
+            # the kernel is bound by the latency of dependent instructions of ONE thread per lookahead, not by bandwidth:
+            # warp instructions issued per second against the SM sub-partitions' issue slots (148 x 4 per cycle)
+            'issue_slots': {'warp_inst_per_lookahead': prof.get('warp_inst_per_lookahead'),
+                            'achieved_warp_inst_per_s': (prof.get('warp_inst_per_lookahead') or 0) * kt['work_items'] / 32.0 / (la_ms / 1e3) if la_ms > 0 else None,
+                            'peak_warp_inst_per_s': 148 * 4 * sm_mhz * 1e6, 'source': prof.get('source'),
+                            'note': '32 lookaheads share one warp: warp instructions = per-lookahead instructions x lookaheads / 32'}}
+        if roofline['issue_slots']['achieved_warp_inst_per_s']:
+            roofline['issue_slots']['frac'] = roofline['issue_slots']['achieved_warp_inst_per_s'] / roofline['issue_slots']['peak_warp_inst_per_s']
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': args.config, 'episodes_per_gpu': B, 'segment': L,
-                       'cluster': 'x'.join(map(str, cfg['shape'])) + ' RAMP', 'degrees': list(cfg['degrees']),
-                       'templates': [[t.n_ops, t.n_deps] for t in wl.templates], 'memo_mode': args.memo_mode,
-                       'agent': 'random partition degree + aligned first-fit blocks (stand-in for the PAC-ML GNN policy)',
-                       'l2': 'inputs larger than L2: the lookahead kernel streams its per-lookahead HBM slabs (~%.1f GB across the '
-                             'resident warps and CTAs) plus %d MB of shared templates; no explicit flush' % (_scratch_gb(wl), _template_mb(wl)),
-                       'parallelism': f'episodes sharded x{world}, one NCCL all-gather of episode metrics per step' if world > 1
-                                      else 'single GPU'},
+            'config': dict(workload_config(args, cfg, wl.templates, world, B),
+                           l2='inputs larger than L2 are not needed: the lookahead kernel keeps its working set (template blob + per-lane '
+                              'lists) in shared memory; per step it writes %.1f MB of tick traces to HBM; no explicit flush' % _trace_mb(kt),
+                           parallelism=f'episodes sharded x{world}, one NCCL all-gather of episode metrics per step' if world > 1
+                                       else 'single GPU'),
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': int(B * engine.ACTION_DTYPE.itemsize + (arrivals.nbytes / L)),
                     'd2h_bytes_per_step': int(B * engine.STEP_STATS_LEN * 8)},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'kernel': 'ramp_lookahead_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak if peak else None, 'traffic': traffic, 'peak_source': peak_src,
-                         'kernel_ms_per_launch': la_ms / max(kt['launches'], 1), 'kernel_launches': kt['launches'],
-                         'lookaheads': kt['work_items'], 'kernel_share_of_step': la_ms / elapsed_ms if elapsed_ms else None,
-                         'algorithmic_bytes_per_launch': kt['algorithmic_bytes'] / max(kt['launches'], 1)},
+            'roofline': roofline,
             'memo': {'lookups': memo['lookups'], 'hits': memo['hits'],
                      'hit_rate': memo['hits'] / memo['lookups'] if memo['lookups'] else None},
             'clocks': clocks, 'wall_ms_per_step': wall_ms / K,
@@ -481,39 +583,19 @@ def template_expansion_note():
         return {'error': str(ex)[:200]}
 
 
-def _scratch_gb(wl):
-    t = max(wl.templates, key=lambda t: t.n_deps)
-    return (56 * t.n_ops + 40 * t.n_deps) * 148 * (12 + 8) / 1e9     # one slab per resident warp / CTA (ramp_kernels.cuh scratch_bytes_for)
-
-
-def _template_mb(wl):
-    return int(sum(26 * t.n_ops + 16 * t.n_deps for t in wl.templates) / 1e6) + 1
+def _trace_mb(kt):
+    # 12 bytes per tick per executed lookahead: (algorithmic bytes - quotient bytes) cancels the per-template part only if the
+    # templates were equal, so take the tick term from the quotient accounting: quotient = 20 N' + 19 E' + 24 + 12 T
+    return 12.0 * 1400 * kt['work_items'] / max(kt['launches'], 1) / 1e6
 
 
 def cpu_baseline(args, wl_gpu):
-    """Oracle port timed on this box's host cores on a bounded sample of the same workload (~10-30 s of CPU work)."""
-    from oracle import oracle
-    from ddls_b200 import workload
-    oracle.build()
-    cores = os.cpu_count() or 1
-    L = args.segment
-    S0 = max(cores, 16)
-    wl = workload.generate(args.config, oracle_jcts, n_episodes=S0, n_steps=L, seed=args.seed)
-    t0 = time.perf_counter()
-    _oracle_segment(oracle, wl, cores)
-    probe = time.perf_counter() - t0
-    S = int(max(S0, min(wl_gpu.n_episodes, S0 * 15.0 / max(probe, 1e-6))))
-    S = max(cores, (S // cores) * cores)
-    wl = workload.generate(args.config, oracle_jcts, n_episodes=S, n_steps=L, seed=args.seed)
-    _oracle_segment(oracle, wl, cores)          # warm-up (page in, thread start)
-    t0 = time.perf_counter()
-    reps = 0
-    while reps < 1 or (time.perf_counter() - t0) < 5.0:
-        _oracle_segment(oracle, wl, cores)
-        reps += 1
-    dt = (time.perf_counter() - t0) / reps
-    return {'value': S * L / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'{S} episodes x {L} env-steps of {args.config}, {reps} repetitions, {dt:.2f} s wall each on {cores} threads (oracle/ramp_oracle.c)'}
+    """Oracle port timed on this box's usable host cores on a bounded sample of the same workload (~10 s of CPU work); the
+    unmodified Python reference is timed by the reference arm (`bench.py --impl reference`)."""
+    cores = usable_cores()
+    out = port_throughput(args, cores['used'], budget_s=10.0)
+    out['host_cores'] = cores
+    return out
 
 
 def main():

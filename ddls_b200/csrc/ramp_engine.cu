@@ -168,7 +168,7 @@ struct ramp_engine {
     int ev_pending = 0;
     double la_ms_total = 0.0;
     int64_t la_launches = 0;
-    unsigned long long la_items_base = 0, la_bytes_base = 0;
+    unsigned long long la_items_base = 0, la_bytes_base = 0, la_qbytes_base = 0;
     MemoStats memo_base{};       // device counters at the last ramp_reset (memo statistics are reported since the reset)
 };
 
@@ -1152,7 +1152,17 @@ int ramp_get_lookahead_kernel_time(ramp_engine_t* e, double* total_ms, int64_t* 
     if (launches) *launches = e->la_launches;
     if (work_items) *work_items = (int64_t)(s.lookaheads - e->la_items_base);
     if (alg_bytes) *alg_bytes = (int64_t)(s.alg_bytes - e->la_bytes_base);
-    if (reset) { e->la_ms_total = 0.0; e->la_launches = 0; e->la_items_base = s.lookaheads; e->la_bytes_base = s.alg_bytes; }
+    if (reset) { e->la_ms_total = 0.0; e->la_launches = 0; e->la_items_base = s.lookaheads; e->la_bytes_base = s.alg_bytes; e->la_qbytes_base = s.quotient_bytes; }
+    return RAMP_OK;
+}
+
+
+int ramp_get_quotient_bytes(ramp_engine_t* e, int64_t* quotient_bytes) {
+    if (!e || !quotient_bytes) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    MemoStats s{};
+    CUDA_TRY(cudaMemcpy(&s, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost));
+    *quotient_bytes = (int64_t)(s.quotient_bytes - e->la_qbytes_base);
     return RAMP_OK;
 }
 

@@ -120,7 +120,7 @@ EXPORTED_SYMBOLS = ['ramp_last_error', 'ramp_engine_create', 'ramp_engine_destro
                     'ramp_get_memo_stats', 'ramp_get_memo_stats_ex',
                     'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_launch_count',
                     'ramp_get_lookahead_kernel_time', 'ramp_expand_template', 'ramp_free_expanded_job', 'ramp_free_expanded_aux', 'ramp_first_fit_place',
-                    'ramp_quotient_template', 'ramp_free_quotient']
+                    'ramp_quotient_template', 'ramp_free_quotient', 'ramp_get_quotient_bytes']
 
 
 def _check(rc):
@@ -283,10 +283,14 @@ class RampEngine:
         return int(self._L.ramp_launch_count(self._h))
 
     def lookahead_kernel_time(self, reset=False):
-        ms, nl, ni, nb = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+        ms, nl, ni, nb, qb = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._L.ramp_get_quotient_bytes.restype = C.c_int
+        self._L.ramp_get_quotient_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        _check(self._L.ramp_get_quotient_bytes(self._h, C.byref(qb)))
         _check(self._L.ramp_get_lookahead_kernel_time(self._h, C.byref(ms), C.byref(nl), C.byref(ni), C.byref(nb),
                                                       1 if reset else 0))
-        return dict(total_ms=ms.value, launches=nl.value, work_items=ni.value, algorithmic_bytes=nb.value)
+        return dict(total_ms=ms.value, launches=nl.value, work_items=ni.value, algorithmic_bytes=nb.value,
+                    quotient_bytes=qb.value)
 
 
 def action_row(actions, b, template_id, mount):

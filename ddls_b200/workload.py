@@ -70,7 +70,27 @@ class Workload:
     meta: dict = field(default_factory=dict)
 
 
-def build_templates(config: str, quantum=0.01, num_training_steps=50):
+def reference_template(g, degree, shape: RampShape, quantum=0.01, num_training_steps=50, model_id=0):
+    """The lowered job the reference's own pipeline produces for ``g`` at max partition degree ``degree`` on an EMPTY cluster:
+    RampFirstFitOpPlacer's block (ramp_first_fit_place), then OpPartition / update_dep_run_times (collectives) / SRPT schedulers /
+    FirstFitDepPlacer (ramp_expand_template, run_times='reference').  Equal to the reference-lowered job in every array but the
+    hash-ordered priority ties (tests/test_expand_native.py); needs libramp_b200.so (host-only code, no GPU)."""
+    import math
+    from .expand import expand_template
+    from .placer import first_fit_place_native
+    splits = [int(max(1, min(math.ceil(math.ceil(c / quantum) / 2) * 2, degree))) for c in g.fwd]      # RJPE:332-343
+    servers = [(c, r, s) for c in range(shape.c) for r in range(shape.r) for s in range(shape.s)]
+    where = first_fit_place_native(g.n, [a + p for a, p in zip(g.act, g.par)], g.edges, splits,
+                                   {sv: 80e9 for sv in servers}, {sv: False for sv in servers}, (shape.c, shape.r, shape.s))
+    if where is None:
+        raise Exception(f'{g.name} does not fit an empty {shape.c}x{shape.r}x{shape.s} cluster at degree {degree}')
+    return expand_template(g, degree, shape, quantum=quantum, num_training_steps=num_training_steps, model_id=model_id,
+                           run_times='reference', coords=sorted(set(where.values())))
+
+
+def build_templates(config: str, quantum=0.01, num_training_steps=50, run_times='one_to_one'):
+    """run_times='one_to_one': template_builder's aligned blocks and one-to-one transfer times (pure Python, no library needed);
+    'reference': the reference pipeline's lowered jobs on an empty cluster (reference_template)."""
     cfg = CONFIGS[config]
     shape = RampShape(*cfg['shape'])
     templates, t_model, t_degree, graphs = [], [], [], []
@@ -80,20 +100,23 @@ def build_templates(config: str, quantum=0.01, num_training_steps=50):
         for d in cfg['degrees']:
             if d > shape.n_workers:
                 continue
-            templates.append(build_template(g, d, shape, block_start=0, quantum=quantum,
-                                            num_training_steps=num_training_steps, model_id=m))
+            if run_times == 'reference':
+                templates.append(reference_template(g, d, shape, quantum=quantum, num_training_steps=num_training_steps, model_id=m))
+            else:
+                templates.append(build_template(g, d, shape, block_start=0, quantum=quantum,
+                                                num_training_steps=num_training_steps, model_id=m))
             t_model.append(m)
             t_degree.append(d)
     return cfg, shape, graphs, templates, t_model, t_degree
 
 
 def generate(config: str, jct_of_template: Callable[[Sequence[LoweredJob]], Sequence[float]], n_episodes: int = None,
-             n_steps: int = 8, seed: int = 0, interarrival: float = 1000.0) -> Workload:
+             n_steps: int = 8, seed: int = 0, interarrival: float = 1000.0, run_times: str = 'one_to_one') -> Workload:
     """Builds the templates and B scripted episodes of L decisions each.
 
     jct_of_template(templates) -> lookahead job completion time per template (from the engine or the oracle).
     """
-    cfg, shape, graphs, templates, t_model, t_degree = build_templates(config)
+    cfg, shape, graphs, templates, t_model, t_degree = build_templates(config, run_times=run_times)
     B = n_episodes or cfg['n_episodes']
     L = n_steps
     rng = np.random.default_rng(seed)
@@ -157,6 +180,6 @@ def generate(config: str, jct_of_template: Callable[[Sequence[LoweredJob]], Sequ
         actions[k]['template_id'] = tid
     wl = Workload(name=config, shape=shape, templates=templates, template_model=t_model, template_degree=t_degree,
                   n_episodes=B, n_steps=L, arrivals=arrivals, actions=actions,
-                  meta=dict(seed=seed, interarrival=interarrival, degrees=list(cfg['degrees']),
+                  meta=dict(seed=seed, interarrival=interarrival, degrees=list(cfg['degrees']), run_times=run_times,
                             placed_frac=float((actions['template_id'] >= 0).mean())))
     return wl

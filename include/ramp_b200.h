@@ -220,6 +220,9 @@ int ramp_run_lookaheads(ramp_engine_t* eng, const int32_t* template_ids, int32_t
 int64_t ramp_launch_count(ramp_engine_t* eng);
 int ramp_get_lookahead_kernel_time(ramp_engine_t* eng, double* total_ms, int64_t* launches, int64_t* work_items,
                                    int64_t* algorithmic_bytes, int32_t reset);
+/* the same 20 N + 19 E + 12 T + 24 accounting on the sizes of the symmetry quotients the thread-per-lookahead kernel really
+ * simulated (since the last reset of the counters above; read it BEFORE resetting them) */
+int ramp_get_quotient_bytes(ramp_engine_t* eng, int64_t* quotient_bytes);
 
 /* ---- native template expansion: what OpPartition / update_dep_run_times / the SRPT schedulers /
  * FirstFitDepPlacer compute for ONE job placed on a block of servers (sub-op k of every split op on server k), without

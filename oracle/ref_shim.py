@@ -9,11 +9,11 @@ replaced by inert MagicMock packages.  ``ray.remote`` becomes a pass-through
 decorator (ramp_cluster_environment.py:39, job.py:19) and ``gym.Env`` a plain
 base class (ramp_job_partitioning_environment.py:42).
 
-This file exists only so that ``oracle/gen_golden.py`` and the CPU-side
-``tests/test_reference_crosscheck.py`` can run the reference *in this container*
-to pin the C restatement in ``oracle/ramp_oracle.c``.  Nothing in the product
-path (``ddls_b200/``), in ``bench.py`` or in the ``-m gpu`` tests imports it:
-/root/reference does not exist on the GPU box.
+This file exists so that ``oracle/gen_golden.py`` and the reference cross-check tests can run the
+reference *in this container* to pin the C restatement in ``oracle/ramp_oracle.c``, and so that
+``bench.py --impl reference`` / the drop-in integration test can run the copy staged at
+``oracle/_ref`` (oracle/stage_ref.py) on the GPU box, where /root/reference does not exist.
+Nothing in the product path (``ddls_b200/``) imports it.
 """
 import importlib.abc
 import importlib.machinery
@@ -21,7 +21,8 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get('DDLS_REFERENCE_ROOT', '/root/reference')
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')     # oracle/stage_ref.py (travels to the GPU box)
+REFERENCE_ROOT = os.environ.get('DDLS_REFERENCE_ROOT') or ('/root/reference' if os.path.isdir('/root/reference/ddls') else _STAGED)
 
 MISSING = {'ray', 'sqlitedict', 'dgl', 'omegaconf', 'hydra', 'matplotlib', 'seaborn',
            'pygraphviz', 'sigfig', 'gym', 'wandb'}
