@@ -337,18 +337,24 @@ int bits_for_u64(uint64_t max_value) { int b = 1; while ((max_value >> b) != 0) 
 bool build_resident_blob(const ramp_lowered_job_t* j, const ramp_quotient_t& q, int32_t max_bytes, std::vector<unsigned char>& blob) {
     const int32_t N = q.n_ops, E = q.n_deps;
     if (N < 1 || q.n_workers > 0xFFFF || q.n_channels >= 0xFFFF) return false;
+    if (!q.masks_valid) return false;
     std::vector<uint64_t> in_total(N, 0);
-    uint32_t max_key = 1, max_inc = 1;
+    uint32_t max_inc = 1;
+    // keys only order entries: re-rank them densely so that the key and the group set share one 32-bit word
+    std::vector<uint32_t> distinct(q.dep_key, q.dep_key + E);
+    std::sort(distinct.begin(), distinct.end());
+    distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+    std::vector<uint32_t> dense_key(E);
     for (int32_t k = 0; k < E; ++k) {
         in_total[q.dep_dst[k]] += q.dep_inc[k];
-        max_key = std::max(max_key, q.dep_key[k]);
         max_inc = std::max(max_inc, q.dep_inc[k]);
+        dense_key[k] = (uint32_t)(std::lower_bound(distinct.begin(), distinct.end(), q.dep_key[k]) - distinct.begin()) + 1u;
     }
     for (int32_t c = 0; c < N; ++c)
         if (q.op_weight[c] > 0xFFFF || in_total[c] > 0xFFFF || q.op_threshold[c] > 0xFFFFFFFFu) return false;   // u16 counters never wrap
-    const int kbits = bits_for_u64(max_key), cbits = bits_for_u64((uint64_t)q.n_channels + 1);
+    const int kbits = bits_for_u64((uint64_t)distinct.size() + 1), cbits = std::max(q.n_channels, 1);
     const int ibits = bits_for_u64(max_inc), nbits = bits_for_u64((uint64_t)N);
-    if (kbits + cbits > 32 || 1 + ibits + nbits > 32) return false;     // dep word = two 32-bit halves
+    if (kbits + cbits > 32 || 1 + ibits + nbits > 32) return false;     // dep word = two 32-bit halves: key | group set, flow | inc | child
     std::vector<int32_t> in_deg(N, 0), src;
     for (int32_t k = 0; k < E; ++k) in_deg[q.dep_dst[k]]++;
     for (int32_t c = 0; c < N; ++c) if (in_deg[c] == 0) src.push_back(c);
@@ -380,8 +386,7 @@ bool build_resident_blob(const ramp_lowered_job_t* j, const ramp_quotient_t& q, 
         thr[c] = q.op_threshold[c];
     }
     for (int32_t k = 0; k < E; ++k) {
-        const unsigned long long chan = (q.dep_channel[k] == 0xFFFFFFFFu) ? (unsigned long long)h.cmask : (unsigned long long)q.dep_channel[k];
-        const uint32_t lo = q.dep_key[k] | (uint32_t)(chan << h.cshift);
+        const uint32_t lo = dense_key[k] | (uint32_t)(q.dep_group_mask[k] << h.cshift);
         const uint32_t hi = (q.dep_is_flow[k] ? 1u : 0u) | (q.dep_inc[k] << h.ishift) | ((uint32_t)q.dep_dst[k] << h.dshift);
         kd[k] = (unsigned long long)lo | ((unsigned long long)hi << 32);
         rt[k] = q.dep_run_time[k] + 0.0;
@@ -403,6 +408,7 @@ int identity_quotient(const ramp_lowered_job_t* j, ramp_quotient_t* q) {
     const size_t e1 = std::max(E, 1);
     q->dep_dst = (int32_t*)malloc(4 * e1); q->dep_run_time = (double*)malloc(8 * e1); q->dep_key = (uint32_t*)malloc(4 * e1);
     q->dep_channel = (uint32_t*)malloc(4 * e1); q->dep_is_flow = (uint8_t*)malloc(e1); q->dep_inc = (uint32_t*)malloc(4 * e1);
+    q->dep_group_mask = (uint64_t*)malloc(8 * e1); q->merged = 0; q->masks_valid = j->n_channels <= 64 ? 1 : 0;
     q->op_class = (int32_t*)malloc(4 * (size_t)N); q->dep_entry = (int32_t*)malloc(4 * e1);
     for (int32_t i = 0; i < N; ++i) {
         q->op_cost[i] = j->op_cost[i]; q->op_key[i] = ok[i]; q->op_worker[i] = j->op_worker[i]; q->op_weight[i] = 1;
@@ -412,6 +418,7 @@ int identity_quotient(const ramp_lowered_job_t* j, ramp_quotient_t* q) {
     for (int32_t k = 0; k < E; ++k) {
         q->dep_dst[k] = j->dep_dst[k]; q->dep_run_time[k] = j->dep_run_time[k]; q->dep_key[k] = dk[k];
         q->dep_channel[k] = (j->dep_channel[k] == RAMP_NO_CHANNEL) ? 0xFFFFFFFFu : (uint32_t)j->dep_channel[k];
+        q->dep_group_mask[k] = (j->dep_channel[k] == RAMP_NO_CHANNEL || !q->masks_valid) ? 0ull : (1ull << j->dep_channel[k]);
         q->dep_is_flow[k] = j->dep_is_flow[k] ? 1 : 0; q->dep_inc[k] = 1; q->dep_entry[k] = k;
     }
     return RAMP_OK;

@@ -39,13 +39,13 @@ namespace ramp {
 #define RAMP_T_NFCAP 8      // ready non-flow entries kept in shared memory per lane
 #endif
 #define RAMP_T_WCAP 8       // worker groups / channel groups with a per-lane winner table (more: pairwise comparison)
-#define RAMP_T_CCAP 8
+#define RAMP_T_CCAP 32
 
 // header of a resident template blob (the blob is what the bulk copy moves: 16-byte aligned, size a multiple of 16)
 struct ResHeader {
     int32_t n_ops, n_deps, n_workers, n_channels;      // classes, entries, worker groups, channel groups
     int32_t n_src, num_training_steps, orig_workers, _pad0;
-    uint32_t kmask, cmask, imask, _pad1;               // dep word lo: key | channel group << cshift (all ones: none);
+    uint32_t kmask, cmask, imask, _pad1;               // dep word lo: key | SET of channel groups << cshift (empty: no channel);
     int32_t cshift, fshift, ishift, dshift;            // dep word hi: flow | inc << 1 | child << dshift  (fshift = 0, ishift = 1)
     int32_t off_op_row, off_op_thr, off_dep_kd, off_dep_rt;   // byte offsets from the blob start (op records follow the header)
     int32_t off_src, total_bytes, _pad2, _pad3;
@@ -152,7 +152,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // Lane-interleaved per-lane lists (element k of this lane at base[k * 32 + lane]).  SPILL: entries past the shared-memory
 // capacity live in the CTA's HBM slab; !SPILL: the template's recorded frontier sizes (TemplateHints) fit the capacity.
 //   ready op class   {remaining.lo, remaining.hi, key, worker group | class size << 16} + its class index
-//   ready flow entry {remaining.lo, remaining.hi, dep word lo (key | channel group << cshift), dep word hi (flow | inc << 1 | child << dshift)}
+//   ready flow entry {remaining.lo, remaining.hi, dep word lo (key | set of channel groups << cshift), dep word hi (flow | inc << 1 | child << dshift)}
 //   ready non-flow   dep word hi
 // nothing the tick loop needs about a ready item is behind a second load
 template <bool SPILL>
@@ -219,7 +219,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
     const double* dep_rt = reinterpret_cast<const double*>(x.tm + H.off_dep_rt);
     const int32_t* src_ops = reinterpret_cast<const int32_t*>(x.tm + H.off_src);
     const int N = H.n_ops, E = H.n_deps, W = H.n_workers, C = H.n_channels;
-    const uint32_t kmask = H.kmask, cmask = H.cmask, imask = H.imask;
+    const uint32_t kmask = H.kmask, imask = H.imask;
     const int csh = H.cshift, dsh = H.dshift;
     const bool tab_w = (W <= RAMP_T_WCAP), tab_c = (C <= RAMP_T_CCAP);
     const LaneOps<SPILL> ops{x.o_sm, x.oi_sm, x.o_gl, x.oi_gl, lane};
@@ -241,6 +241,143 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
     double* tt_ptr = x.tr_tick;
 
     while (R.status == RAMP_ST_OK) {
+        if (nF <= 4 && nO <= 2) {
+            // ======== small frontiers (the usual case on a quotient): every ready item is loaded ONCE into registers and each
+            // phase runs code specialised for the exact number of ready ops (0-2) and flows (0-4): winners by pairwise
+            // comparison (no tables, any number of worker / channel groups), no loop or predication overhead ========
+            int4 fr[4], orr[2];
+            int oi[2];
+            bool ow0 = false, ow1 = false;
+            double t_op = INF;
+            int n_active = 0;
+            // ---- A, B ----
+            if (nO >= 1) {
+                orr[0] = x.o_sm[lane]; oi[0] = x.oi_sm[lane];
+                ow0 = true;
+                if (nO == 2) {
+                    orr[1] = x.o_sm[32 + lane]; oi[1] = x.oi_sm[32 + lane];
+                    ow1 = true;
+                    if (((orr[0].w ^ orr[1].w) & 0xffff) == 0) { if ((uint32_t)orr[0].z > (uint32_t)orr[1].z) ow1 = false; else ow0 = false; }
+                    if (ow1) { t_op = __hiloint2double(orr[1].y, orr[1].x); n_active = (int)((uint32_t)orr[1].w >> 16); }
+                }
+                if (ow0) { const double r0 = __hiloint2double(orr[0].y, orr[0].x); t_op = (r0 < t_op) ? r0 : t_op; n_active += (int)((uint32_t)orr[0].w >> 16); }
+            }
+            // ---- C, D ----
+            const bool any_nf = nNF > 0;
+            double t_comm = any_nf ? 0.0 : INF;
+            auto load_flows = [&](auto nf_tag) {
+                constexpr int NF = decltype(nf_tag)::value;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) fr[k] = x.f_sm[k * 32 + lane];
+            };
+            auto winners = [&](auto nf_tag) {
+                constexpr int NF = decltype(nf_tag)::value;
+                uint32_t gm[NF > 0 ? NF : 1], key[NF > 0 ? NF : 1];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { gm[k] = (uint32_t)fr[k].z >> csh; key[k] = (uint32_t)fr[k].z & kmask; }
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    // the entry wins on a channel group of its set unless a ready entry with a larger key lies on that group too
+                    // (an empty set -- no channel -- never wins, it only ticks)
+                    uint32_t open_groups = gm[k];
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) if (j != k && key[j] > key[k]) open_groups &= ~gm[j];
+                    if (open_groups) { const double rem = __hiloint2double(fr[k].y, fr[k].x); t_comm = (rem < t_comm) ? rem : t_comm; }
+                }
+            };
+            if (!any_nf) {
+                switch (nF) {
+                    case 1: load_flows(std::integral_constant<int, 1>{}); winners(std::integral_constant<int, 1>{}); break;
+                    case 2: load_flows(std::integral_constant<int, 2>{}); winners(std::integral_constant<int, 2>{}); break;
+                    case 3: load_flows(std::integral_constant<int, 3>{}); winners(std::integral_constant<int, 3>{}); break;
+                    case 4: load_flows(std::integral_constant<int, 4>{}); winners(std::integral_constant<int, 4>{}); break;
+                    default: break;
+                }
+            }
+            // ---- E, I, J ----
+            const double tick = (t_comm < t_op) ? t_comm : t_op;
+            if ((!any_nf) && (nF > 0)) R.comm = __dadd_rn(R.comm, tick);                             // RCE:434-439, 777-791
+            if (n_active > 0) R.comp = __dadd_rn(R.comp, tick);
+            R.t = __dadd_rn(R.t, tick);
+            if (R.tick_no < x.tr_cap) { *tn_ptr = n_active; *tt_ptr = tick; tn_ptr += x.tr_stride; tt_ptr += x.tr_stride; }
+            else R.status = RAMP_ST_TRACE_OVERFLOW;
+            ++R.tick_no;
+            // ---- H ----
+            int tailO = nO;
+            auto complete_dep = [&](const uint32_t hi) {                                            // JOB:525-536
+                const int child = (int)(hi >> dsh);
+                const uint32_t inc = (hi >> 1) & imask;
+                const uint32_t old = cnt[child * 32];
+                const uint32_t thr = op_thr[child];
+                const uint32_t neu = old + inc;
+                cnt[child * 32] = (uint16_t)neu;
+                if (old < thr && thr <= neu) { ops.put(tailO, op_rec[child], child); ++tailO; }     // JOB:531 for every member
+            };
+            if (any_nf) {
+                _Pragma("unroll 1")
+                for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
+                deps_completed += nNF;
+                nNF = 0;
+            } else if (nF > 0) {
+                int p = 0;
+                auto tick_flows = [&](auto nf_tag) {
+                    constexpr int NF = decltype(nf_tag)::value;
+#pragma unroll
+                    for (int k = 0; k < NF; ++k) {
+                        const double r2 = tick_down(__hiloint2double(fr[k].y, fr[k].x), tick);      // JOB:561
+                        if (r2 == 0.0) { complete_dep((uint32_t)fr[k].w); ++deps_completed; }       // JOB:562
+                        else { fr[k].x = __double2loint(r2); fr[k].y = __double2hiint(r2); x.f_sm[p * 32 + lane] = fr[k]; ++p; }
+                    }
+                };
+                switch (nF) {
+                    case 1: tick_flows(std::integral_constant<int, 1>{}); break;
+                    case 2: tick_flows(std::integral_constant<int, 2>{}); break;
+                    case 3: tick_flows(std::integral_constant<int, 3>{}); break;
+                    default: tick_flows(std::integral_constant<int, 4>{}); break;
+                }
+                nF = p;
+            }
+            // ---- G ----
+            int p = 0;
+            auto tick_op = [&](int4 r, const int op, const bool win) {
+                if (win) {                                                                          // this tick's winner
+                    const double rem = tick_down(__hiloint2double(r.y, r.x), tick);                 // JOB:555
+                    if (rem == 0.0) {                                                               // JOB:556
+                        ++ops_completed;
+                        const int2 row = op_row[op];
+                        _Pragma("unroll 1")
+                        for (int e = row.x; e < row.x + row.y; ++e) {                               // JOB:496-506
+                            const uint2 kd = dep_kd[e];
+                            if (kd.y & 1u) {
+                                const double rt = dep_rt[e];
+                                flows.put(nF, make_int4(__double2loint(rt), __double2hiint(rt), (int)kd.x, (int)kd.y));
+                                ++nF;
+                            } else { nfs.put(nNF, kd.y); ++nNF; }
+                        }
+                        return;
+                    }
+                    r.x = __double2loint(rem); r.y = __double2hiint(rem);
+                }
+                x.o_sm[p * 32 + lane] = r; x.oi_sm[p * 32 + lane] = op; ++p;
+            };
+            if (nO >= 1) {
+                tick_op(orr[0], oi[0], ow0);
+                if (nO == 2) tick_op(orr[1], oi[1], ow1);
+            }
+            if (tailO != nO) {
+                _Pragma("unroll 1")
+                for (int k = nO; k < tailO; ++k, ++p) { if (p != k) ops.put(p, ops.rec(k), ops.idx(k)); }
+            }
+            nO = p;
+            if (SPILL) {
+                R.max_o = (tailO > R.max_o) ? tailO : R.max_o;
+                R.max_f = (nF > R.max_f) ? nF : R.max_f;
+                R.max_nf = (nNF > R.max_nf) ? nNF : R.max_nf;
+            }
+            if ((ops_completed == N) && (deps_completed == E)) break;                               // JOB:549-551
+            if (isinf(tick)) { R.status = RAMP_ST_INFINITE_TICK; break; }                           // RCE:462
+            continue;
+        }
         // ---- A, B: winners per worker group: largest key; t_op = min of their remaining times ----
         double t_op = INF;
         int n_active = 0;
@@ -303,44 +440,45 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                     _Pragma("unroll 1")
                     for (int k = 0; k < nF; ++k) {
                         const int4 f = flows.get(k);
-                        if (((uint32_t)f.z >> csh) == cmask) continue;                               // no channel: ticks, never a winner
+                        if (((uint32_t)f.z >> csh) == 0u) continue;                                  // no channel: ticks, never a winner
                         const uint32_t key = (uint32_t)f.z & kmask;
                         const double rem = __hiloint2double(f.y, f.x);
                         if (key > best) { best = key; t_comm = rem; }
                         else if (key == best) t_comm = (rem < t_comm) ? rem : t_comm;
                     }
                 } else if (tab_c) {
+                    // per-group table: largest key among the ready entries whose set contains the group
                     _Pragma("unroll 1")
                     for (int q = 0; q < C; ++q) ck[q * 32] = 0u;
                     _Pragma("unroll 1")
                     for (int k = 0; k < nF; ++k) {
                         const uint32_t lo = (uint32_t)flows.get(k).z;
-                        const uint32_t q = lo >> csh;
-                        if (q != cmask) { const uint32_t key = lo & kmask; if (key > ck[q * 32]) ck[q * 32] = key; }
+                        const uint32_t key = lo & kmask;
+                        uint32_t m = lo >> csh;
+                        while (m) { const int q = __ffs((int)m) - 1; m &= m - 1u; if (key > ck[q * 32]) ck[q * 32] = key; }
                     }
                     _Pragma("unroll 1")
                     for (int k = 0; k < nF; ++k) {
                         const int4 f = flows.get(k);
-                        const uint32_t q = (uint32_t)f.z >> csh;
-                        if (q != cmask && ck[q * 32] == ((uint32_t)f.z & kmask)) {
-                            const double rem = __hiloint2double(f.y, f.x);
-                            t_comm = (rem < t_comm) ? rem : t_comm;
-                        }
+                        const uint32_t key = (uint32_t)f.z & kmask;
+                        uint32_t m = (uint32_t)f.z >> csh;
+                        bool win = false;
+                        while (m && !win) { const int q = __ffs((int)m) - 1; m &= m - 1u; win = ck[q * 32] == key; }
+                        if (win) { const double rem = __hiloint2double(f.y, f.x); t_comm = (rem < t_comm) ? rem : t_comm; }
                     }
                 } else {
                     _Pragma("unroll 1")
                     for (int k = 0; k < nF; ++k) {
                         const int4 f = flows.get(k);
-                        const uint32_t q = (uint32_t)f.z >> csh;
-                        if (q == cmask) continue;
+                        uint32_t open_groups = (uint32_t)f.z >> csh;
+                        if (open_groups == 0u) continue;
                         const uint32_t key = (uint32_t)f.z & kmask;
-                        bool win = true;
                         _Pragma("unroll 1")
-                        for (int j = 0; j < nF && win; ++j) {
+                        for (int j = 0; j < nF && open_groups; ++j) {
                             const uint32_t lo2 = (uint32_t)flows.get(j).z;
-                            if ((lo2 >> csh) == q && (lo2 & kmask) > key) win = false;
+                            if ((lo2 & kmask) > key) open_groups &= ~(lo2 >> csh);
                         }
-                        if (win) { const double rem = __hiloint2double(f.y, f.x); t_comm = (rem < t_comm) ? rem : t_comm; }
+                        if (open_groups) { const double rem = __hiloint2double(f.y, f.x); t_comm = (rem < t_comm) ? rem : t_comm; }
                     }
                 }
             }

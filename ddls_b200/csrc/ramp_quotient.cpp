@@ -14,8 +14,10 @@
 //               its channel or priority; those only feed  t_comm = min over channels of remaining(winner)  (RCE:608-663).
 //   channel group = channels that carry the same dep classes in the same priority order, where deps that leave the same
 //               op class with the same run time ("twins": always ready in the same ticks with the same remaining time)
-//               count as one.  A dep class is split into one ENTRY per channel group its members lie on; the entry's key is
-//               the rank its twins hold on the group's first channel.
+//               count as one.  When the groups' orders are restrictions of ONE order (priorities from one global ranking, no
+//               cross-twin ties) a dep class is ONE entry that carries the set of groups its members lie on and its twins'
+//               global rank; otherwise it is split into one entry per group, keyed by the twins' rank on that group.  On a
+//               group the winner is the ready entry with the largest key among those whose set contains the group.
 //   counters  = len(parent_deps_completed) of JOB:530 is kept per op CLASS, scaled by the class size: an entry adds its
 //               member count, the class is readied when the count passes through n_parents x class size -- all entries of
 //               a dep class complete in the same tick, so that is the tick in which every member's own count passes
@@ -81,7 +83,7 @@ extern "C" {
 void ramp_free_quotient(ramp_quotient_t* q) {
     if (!q) return;
     free(q->op_cost); free(q->op_key); free(q->op_worker); free(q->op_weight); free(q->op_threshold); free(q->row_ptr);
-    free(q->dep_dst); free(q->dep_run_time); free(q->dep_key); free(q->dep_channel); free(q->dep_is_flow); free(q->dep_inc);
+    free(q->dep_dst); free(q->dep_run_time); free(q->dep_key); free(q->dep_channel); free(q->dep_group_mask); free(q->dep_is_flow); free(q->dep_inc);
     free(q->op_class); free(q->dep_entry);
     memset(q, 0, sizeof(*q));
 }
@@ -289,20 +291,41 @@ int ramp_quotient_template(const ramp_lowered_job_t* j, ramp_quotient_t* out) {
     std::vector<std::unordered_map<int32_t, uint32_t>> c_key(n_cg);
     for (int32_t g = 0; g < n_cg; ++g) for (auto& p : c_seq[g]) c_key[g][p.first] = p.second;
 
-    // ---- entries: (dep class, channel group or none) ----
+    // ---- one key per twin for ALL groups?  The global rank of a twin = the largest original key among its deps.  If every
+    // group's sequence is strictly descending in it, the per-channel orders are restrictions of ONE order (they are whenever the
+    // priorities come from one global ranking by run time, srpt_dep_scheduler.py:60-81, with no cross-twin ties), and a dep class
+    // needs a single entry carrying the SET of groups its members lie on: on group g the winner is the live entry with the
+    // largest key among those whose set contains g.  Otherwise (hash-ordered ties) a class is split into one entry per group. ----
+    std::unordered_map<int32_t, uint32_t> gk;              // twin -> global key
+    for (int32_t e = 0; e < E; ++e) if (j->dep_channel[e] != RAMP_NO_CHANNEL) { uint32_t& b = gk[twin[e]]; b = std::max(b, dep_key[e]); }
+    bool merged = n_cg <= 64;
+    for (int32_t g = 0; g < n_cg && merged; ++g)
+        for (size_t k = 1; k < c_seq[g].size() && merged; ++k) merged = gk[c_seq[g][k - 1].first] > gk[c_seq[g][k].first];
+    {
+        // two twins with the same global key would compare equal: impossible (keys are unique ranks), checked for safety
+        std::vector<uint32_t> all;
+        for (auto& p : gk) all.push_back(p.second);
+        std::sort(all.begin(), all.end());
+        for (size_t k = 1; k < all.size() && merged; ++k) merged = all[k] != all[k - 1];
+    }
+    const bool masks_valid = n_cg <= 64;
+
+    // ---- entries: merged: one per dep class; split: one per (dep class, channel group or none) ----
     std::vector<int32_t> entry(E);
     std::vector<int32_t> ent_rep;         // representative dep of every entry
     std::vector<uint32_t> ent_inc;
+    std::vector<uint64_t> ent_mask;
     {
         std::unordered_map<uint64_t, int32_t> ids;
         ids.reserve((size_t)E * 2 + 16);
         for (int32_t e = 0; e < E; ++e) {
             const int32_t g = (j->dep_channel[e] == RAMP_NO_CHANNEL) ? -1 : cg[j->dep_channel[e]];
-            const uint64_t k = ((uint64_t)(uint32_t)dc[e] << 32) | (uint64_t)(uint32_t)(g + 1);
+            const uint64_t k = ((uint64_t)(uint32_t)dc[e] << 32) | (merged ? (g < 0 ? 0ull : 1ull) : (uint64_t)(uint32_t)(g + 1));
             auto it = ids.find(k);
-            if (it == ids.end()) { it = ids.emplace(k, (int32_t)ent_rep.size()).first; ent_rep.push_back(e); ent_inc.push_back(0); }
+            if (it == ids.end()) { it = ids.emplace(k, (int32_t)ent_rep.size()).first; ent_rep.push_back(e); ent_inc.push_back(0); ent_mask.push_back(0); }
             entry[e] = it->second;
             ent_inc[it->second]++;
+            if (g >= 0 && masks_valid) ent_mask[it->second] |= (1ull << g);
         }
     }
     const int32_t n_ent = (int32_t)ent_rep.size();
@@ -322,6 +345,8 @@ int ramp_quotient_template(const ramp_lowered_job_t* j, ramp_quotient_t* out) {
     out->dep_run_time = (double*)malloc(sizeof(double) * std::max(n_ent, 1));
     out->dep_key = (uint32_t*)malloc(sizeof(uint32_t) * std::max(n_ent, 1));
     out->dep_channel = (uint32_t*)malloc(sizeof(uint32_t) * std::max(n_ent, 1));
+    out->dep_group_mask = (uint64_t*)malloc(sizeof(uint64_t) * std::max(n_ent, 1));
+    out->merged = merged ? 1 : 0; out->masks_valid = masks_valid ? 1 : 0;
     out->dep_is_flow = (uint8_t*)malloc(std::max(n_ent, 1));
     out->dep_inc = (uint32_t*)malloc(sizeof(uint32_t) * std::max(n_ent, 1));
     out->op_class = (int32_t*)malloc(sizeof(int32_t) * N);
@@ -338,9 +363,13 @@ int ramp_quotient_template(const ramp_lowered_job_t* j, ramp_quotient_t* out) {
         out->dep_run_time[k] = j->dep_run_time[e] + 0.0;
         out->dep_is_flow[k] = j->dep_is_flow[e] ? 1 : 0;
         out->dep_inc[k] = ent_inc[id];
+        out->dep_group_mask[k] = ent_mask[id];
         if (j->dep_channel[e] == RAMP_NO_CHANNEL) {
             out->dep_channel[k] = 0xFFFFFFFFu;
             out->dep_key[k] = dep_key[e];
+        } else if (merged) {
+            out->dep_channel[k] = 0xFFFFFFFFu;                 // lies on the groups of dep_group_mask
+            out->dep_key[k] = gk[twin[e]];
         } else {
             const int32_t g = cg[j->dep_channel[e]];
             out->dep_channel[k] = (uint32_t)g;

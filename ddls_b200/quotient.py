@@ -18,8 +18,9 @@ class _Quotient(C.Structure):
                 ('op_weight', C.POINTER(C.c_uint32)), ('op_threshold', C.POINTER(C.c_uint32)),
                 ('row_ptr', C.POINTER(C.c_int32)), ('dep_dst', C.POINTER(C.c_int32)),
                 ('dep_run_time', C.POINTER(C.c_double)), ('dep_key', C.POINTER(C.c_uint32)),
-                ('dep_channel', C.POINTER(C.c_uint32)), ('dep_is_flow', C.POINTER(C.c_uint8)),
-                ('dep_inc', C.POINTER(C.c_uint32)), ('op_class', C.POINTER(C.c_int32)), ('dep_entry', C.POINTER(C.c_int32))]
+                ('dep_channel', C.POINTER(C.c_uint32)), ('dep_group_mask', C.POINTER(C.c_uint64)), ('dep_is_flow', C.POINTER(C.c_uint8)),
+                ('dep_inc', C.POINTER(C.c_uint32)), ('op_class', C.POINTER(C.c_int32)), ('dep_entry', C.POINTER(C.c_int32)),
+                ('merged', C.c_int32), ('masks_valid', C.c_int32)]
 
 
 @dataclass
@@ -38,11 +39,14 @@ class QuotientJob:
     dep_dst: np.ndarray
     dep_run_time: np.ndarray
     dep_key: np.ndarray
-    dep_channel: np.ndarray      # 0xFFFFFFFF = none
+    dep_channel: np.ndarray      # split entries: channel group; 0xFFFFFFFF = none or merged
     dep_is_flow: np.ndarray
     dep_inc: np.ndarray
     op_class: np.ndarray
     dep_entry: np.ndarray
+    dep_group_mask: np.ndarray = None   # uint64: bit g set = members on group g
+    merged: int = 0
+    masks_valid: int = 1
 
 
 def _arr(ptr, n, dtype):
@@ -78,6 +82,7 @@ def quotient(job: LoweredJob) -> QuotientJob:
                            dep_dst=_arr(q.dep_dst, e, np.int64), dep_run_time=_arr(q.dep_run_time, e, np.float64),
                            dep_key=_arr(q.dep_key, e, np.int64), dep_channel=_arr(q.dep_channel, e, np.int64),
                            dep_is_flow=_arr(q.dep_is_flow, e, np.uint8), dep_inc=_arr(q.dep_inc, e, np.int64),
-                           op_class=_arr(q.op_class, job.n_ops, np.int64), dep_entry=_arr(q.dep_entry, job.n_deps, np.int64))
+                           op_class=_arr(q.op_class, job.n_ops, np.int64), dep_entry=_arr(q.dep_entry, job.n_deps, np.int64),
+                           dep_group_mask=_arr(q.dep_group_mask, e, np.uint64), merged=int(q.merged), masks_valid=int(q.masks_valid))
     finally:
         L.ramp_free_quotient(C.byref(q))

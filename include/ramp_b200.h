@@ -297,11 +297,14 @@ typedef struct {
     int32_t*  dep_dst;
     double*   dep_run_time;
     uint32_t* dep_key;
-    uint32_t* dep_channel;       /* 0xFFFFFFFF = none */
+    uint32_t* dep_channel;       /* split entries: the channel group; 0xFFFFFFFF = none, or merged (see dep_group_mask) */
+    uint64_t* dep_group_mask;    /* bit g set: members of the entry lie on channels of group g (valid when masks_valid)   */
     uint8_t*  dep_is_flow;
     uint32_t* dep_inc;
     int32_t*  op_class;
     int32_t*  dep_entry;
+    int32_t   merged;            /* 1: one entry per dep class with a group set; 0: one entry per (dep class, group)        */
+    int32_t   masks_valid;       /* 0 when there are more than 64 channel groups                                            */
 } ramp_quotient_t;
 int ramp_quotient_template(const ramp_lowered_job_t* job, ramp_quotient_t* out);
 void ramp_free_quotient(ramp_quotient_t* q);

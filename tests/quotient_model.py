@@ -107,18 +107,33 @@ def quotient(job, max_rounds=256):
     for c in range(C):
         g_keys.setdefault(int(cg[c]), ckeys[c])
 
+    # one key per twin for all groups?  (see ramp_quotient.cpp)
+    gk = {}
+    for e in range(E):
+        if has_ch[e]:
+            gk[int(twin[e])] = max(gk.get(int(twin[e]), 0), int(dep_key[e]))
+    seq_of_group = {}
+    for c in range(C):
+        seq_of_group.setdefault(int(cg[c]), cseq[c])
+    merged = n_cg <= 64 and all(gk[sq[k - 1]] > gk[sq[k]] for sq in seq_of_group.values() for k in range(1, len(sq)))
+    merged = merged and len(set(gk.values())) == len(gk)
+    masks_valid = n_cg <= 64
+
     # entries
-    ids, ent_rep, ent_inc = {}, [], []
+    ids, ent_rep, ent_inc, ent_mask = {}, [], [], []
     entry = np.zeros(E, dtype=np.int64)
     for e in range(E):
         g = int(cg[int(chan[e])]) if has_ch[e] else -1
-        k = (int(dc[e]), g)
+        k = (int(dc[e]), (0 if g < 0 else 1) if merged else g + 1)
         if k not in ids:
             ids[k] = len(ent_rep)
             ent_rep.append(e)
             ent_inc.append(0)
+            ent_mask.append(0)
         entry[e] = ids[k]
         ent_inc[ids[k]] += 1
+        if g >= 0 and masks_valid:
+            ent_mask[ids[k]] |= (1 << g)
     n_ent = len(ent_rep)
     order = sorted(range(n_ent), key=lambda a: int(oc[src[ent_rep[a]]]))     # stable
     new_id = np.zeros(n_ent, dtype=np.int64)
@@ -129,6 +144,7 @@ def quotient(job, max_rounds=256):
     q_rt = np.zeros(n_ent, dtype=np.float64)
     q_key = np.zeros(n_ent, dtype=np.int64)
     q_ch = np.full(n_ent, 0xFFFFFFFF, dtype=np.int64)
+    q_mask = np.zeros(n_ent, dtype=np.uint64)
     q_flow = np.zeros(n_ent, dtype=np.uint8)
     q_inc = np.zeros(n_ent, dtype=np.int64)
     for k, a in enumerate(order):
@@ -138,12 +154,15 @@ def quotient(job, max_rounds=256):
         q_rt[k] = job.dep_run_time[e] + 0.0
         q_flow[k] = 1 if job.dep_is_flow[e] else 0
         q_inc[k] = ent_inc[a]
-        if has_ch[e]:
+        q_mask[k] = ent_mask[a]
+        if not has_ch[e]:
+            q_key[k] = dep_key[e]
+        elif merged:
+            q_key[k] = gk[int(twin[e])]
+        else:
             g = int(cg[int(chan[e])])
             q_ch[k] = g
             q_key[k] = g_keys[g][int(twin[e])]
-        else:
-            q_key[k] = dep_key[e]
     np.cumsum(q_row, out=q_row)
     return QuotientJob(n_ops=n_oc, n_deps=n_ent, n_workers=n_wg, n_channels=n_cg,
                        num_training_steps=job.num_training_steps,
@@ -151,7 +170,8 @@ def quotient(job, max_rounds=256):
                        op_weight=size_op.astype(np.int64),
                        op_threshold=job.op_n_parents[rep_op].astype(np.int64) * size_op,
                        row_ptr=q_row, dep_dst=q_dst, dep_run_time=q_rt, dep_key=q_key, dep_channel=q_ch,
-                       dep_is_flow=q_flow, dep_inc=q_inc, op_class=oc.astype(np.int64), dep_entry=new_id[entry])
+                       dep_is_flow=q_flow, dep_inc=q_inc, op_class=oc.astype(np.int64), dep_entry=new_id[entry],
+                       dep_group_mask=q_mask, merged=int(merged), masks_valid=int(masks_valid))
 
 
 def run_lookahead_quotient(q):
@@ -165,7 +185,12 @@ def run_lookahead_quotient(q):
     par_done = [0] * N
     ops = [(i, float(q.op_cost[i]) + 0.0) for i in range(N) if in_deg[i] == 0]
     flows, nf = [], []
-    ck_cur, ck_nxt = {}, {}
+
+    def groups_of(e):                       # set of channel groups of an entry as a Python int bit mask
+        if q.masks_valid:
+            return int(q.dep_group_mask[e])
+        c = int(q.dep_channel[e])
+        return 0 if c == 0xFFFFFFFF else (1 << c)
     t = comm = comp = 0.0
     trace_n, trace_tick = [], []
     ops_completed = deps_completed = 0
@@ -183,11 +208,15 @@ def run_lookahead_quotient(q):
         if any_nf:
             t_comm = 0.0
         else:
-            t_comm = min([rem for e, rem in flows
-                          if int(q.dep_channel[e]) != 0xFFFFFFFF and ck_cur.get(int(q.dep_channel[e]), 0) == int(q.dep_key[e])],
-                         default=INF)
-            ck_cur = {}
-        vote = ck_cur if any_nf else ck_nxt
+            # an entry wins on a channel group of its set unless a ready entry with a larger key lies on that group too
+            t_comm = INF
+            for e, rem in flows:
+                open_groups = groups_of(e)
+                for e2, _ in flows:
+                    if int(q.dep_key[e2]) > int(q.dep_key[e]):
+                        open_groups &= ~groups_of(e2)
+                if open_groups and rem < t_comm:
+                    t_comm = rem
         tick = t_comm if t_comm < t_op else t_op
         ticked_ops, ticked_flows = len(winners) > 0, (not any_nf) and len(flows) > 0
         if ticked_flows:
@@ -220,9 +249,6 @@ def run_lookahead_quotient(q):
                     deps_completed += 1
                 else:
                     survivors.append([e, r2])
-                    c = int(q.dep_channel[e])
-                    if c != 0xFFFFFFFF:
-                        ck_nxt[c] = max(ck_nxt.get(c, 0), int(q.dep_key[e]))
         win_set = {op for op, _ in winners}
         arrivals = []
         for op, rem in ops:
@@ -237,9 +263,6 @@ def run_lookahead_quotient(q):
         for e in arrivals:
             if int(q.dep_is_flow[e]):
                 survivors.append([e, float(q.dep_run_time[e]) + 0.0])
-                c = int(q.dep_channel[e])
-                if c != 0xFFFFFFFF:
-                    vote[c] = max(vote.get(c, 0), int(q.dep_key[e]))
             else:
                 nf.append(e)
         flows = survivors
@@ -247,8 +270,6 @@ def run_lookahead_quotient(q):
         finished = ops_completed == N and deps_completed == E
         if finished or math.isinf(tick):
             break
-        if not any_nf:
-            ck_cur, ck_nxt = ck_nxt, ck_cur
     steps = float(q.num_training_steps)
     return dict(jct=t * steps, comm=comm * steps, comp=comp * steps, n_ticks=len(trace_tick),
                 trace_n_active=np.array(trace_n, dtype=np.int32), trace_tick=np.array(trace_tick, dtype=np.float64),

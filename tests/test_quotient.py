@@ -15,12 +15,12 @@ from ddls_b200.quotient import quotient
 from ddls_b200.template_builder import RampShape, build_template, random_dag_template
 
 FIELDS = ('op_cost', 'op_key', 'op_worker', 'op_weight', 'op_threshold', 'row_ptr', 'dep_dst', 'dep_run_time', 'dep_key',
-          'dep_channel', 'dep_is_flow', 'dep_inc', 'op_class', 'dep_entry')
+          'dep_channel', 'dep_is_flow', 'dep_inc', 'op_class', 'dep_entry', 'dep_group_mask')
 MAX_WORK = 40_000_000
 
 
 def _assert_same_quotient(a, b):
-    assert (a.n_ops, a.n_deps, a.n_workers, a.n_channels) == (b.n_ops, b.n_deps, b.n_workers, b.n_channels)
+    assert (a.n_ops, a.n_deps, a.n_workers, a.n_channels, a.merged, a.masks_valid) == (b.n_ops, b.n_deps, b.n_workers, b.n_channels, b.merged, b.masks_valid)
     for f in FIELDS:
         np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
 
@@ -143,3 +143,19 @@ def test_quotient_of_replicated_random_jobs(seed, oracle_lib):
         assert N < q.n_ops <= 2 * N
     ref = oracle_lib.run_lookahead(job)
     _assert_matches_oracle(qm.run_lookahead_quotient(q), ref, oracle_lib)
+
+
+@pytest.mark.parametrize('degree', [4, 8, 16])
+def test_quotient_merges_entries_over_channel_groups(degree, oracle_lib):
+    """Reference run times (collectives whose time depends on which racks / communication groups a server pair spans): several
+    channel groups, but one global priority order -> ONE entry per dep class carrying its group set; the lookahead on it equals
+    the oracle's on the full job at BASELINE.json's size."""
+    from ddls_b200 import workload
+    job = workload.reference_template(synth.resnet_like_graph(), degree, RampShape(4, 4, 4))
+    q = quotient(job)
+    _check_structure(job, q)
+    assert q.merged == 1 and q.masks_valid == 1 and q.n_channels >= 2 and q.n_ops == 330
+    assert q.n_deps < 1500
+    assert int(np.bitwise_or.reduce(q.dep_group_mask)) == (1 << q.n_channels) - 1
+    ref = oracle_lib.run_lookahead(job)
+    _assert_lookahead(qm.run_lookahead_quotient(q), ref['trace_n_active'], ref['trace_tick'], ref['jct'], ref['comm'], ref['comp'])
