@@ -107,6 +107,7 @@ struct ramp_engine {
     // episode state
     EpisodeState ep{};
     ramp_arrival_t* d_arrivals = nullptr;
+    int32_t* d_n_jobs_ep = nullptr;
     // lookahead scratch
     unsigned char* d_scratch = nullptr;
     uint64_t scratch_stride = 0;
@@ -536,8 +537,9 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     if (alloc_result_slots(e->res, e->n_slots) != RAMP_OK) return RAMP_ERR_CUDA;
     CUDA_TRY(cudaMemset(e->res.status, 0, sizeof(int32_t) * e->n_slots));
 
-    // trace pool: exact-size allocations, default budget 48 Mi entries (576 MiB) or enough for B x 4 x 2048 ticks
-    e->pool.len = std::max<uint64_t>(48ull << 20, (uint64_t)B * 4ull * 2048ull);
+    // trace pool: exact-size allocations; 4 Mi entries at least, else enough for 8 un-memoised lookaheads of 2,048 ticks per
+    // episode between two resets (the pool is reset with the memo)
+    e->pool.len = std::max<uint64_t>(4ull << 20, (uint64_t)B * 8ull * 2048ull);      // B=1: 48 MiB; B=4096: 805 MiB
     CUDA_TRY(cudaMalloc(&e->pool.n_active, sizeof(int32_t) * e->pool.len));
     CUDA_TRY(cudaMalloc(&e->pool.tick, sizeof(double) * e->pool.len));
     CUDA_TRY(cudaMalloc(&e->pool.top, sizeof(unsigned long long)));
@@ -581,6 +583,9 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     CUDA_TRY(cudaMemset(ep.ei, 0, sizeof(int32_t) * EI_COUNT * B));
     CUDA_TRY(cudaMemset(ep.rec, 0, sizeof(ramp_job_record_t) * (size_t)cfg.max_jobs * B));
     ep.arr = e->d_arrivals;
+    CUDA_TRY(cudaMalloc(&e->d_n_jobs_ep, sizeof(int32_t) * B));
+    CUDA_TRY(cudaMemset(e->d_n_jobs_ep, 0, sizeof(int32_t) * B));
+    ep.n_jobs_ep = e->d_n_jobs_ep;
 
     for (int k = 0; k < MAX_EVENT_PAIRS; ++k) {
         CUDA_TRY(cudaEventCreate(&e->ev_a[k]));
@@ -603,7 +608,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     cudaFree(e->d_items); cudaFree(e->d_items_big); cudaStreamDestroy(e->stream2); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); cudaFree(e->d_counters); cudaFree(e->d_stats); cudaFree(e->d_actions);
     cudaFree(e->d_step_stats); cudaFree(e->d_n_cluster_steps); cudaFree(e->d_ep_export);
     cudaFree(e->ep.ef); cudaFree(e->ep.ei); cudaFree(e->ep.rf); cudaFree(e->ep.ri); cudaFree(e->ep.rec);
-    cudaFree(e->d_arrivals); cudaFree(e->d_scratch); cudaFree(e->sa_items); cudaFree(e->sa_counters); cudaFreeHost(e->h_n_work);
+    cudaFree(e->d_arrivals); cudaFree(e->d_n_jobs_ep); cudaFree(e->d_scratch); cudaFree(e->sa_items); cudaFree(e->sa_counters); cudaFreeHost(e->h_n_work);
     for (int k = 0; k < MAX_EVENT_PAIRS; ++k) { cudaEventDestroy(e->ev_a[k]); cudaEventDestroy(e->ev_b[k]); }
     cudaStreamDestroy(e->stream);
     delete e;
@@ -642,6 +647,9 @@ int ramp_register_template(ramp_engine_t* e, const ramp_lowered_job_t* j, int32_
             return set_error(RAMP_ERR_BAD_ARG, "non-flow dep %d has a non-zero run time (RCE:542-560 zeroes it)", k);
         in_deg[j->dep_dst[k]]++;
     }
+    for (int32_t i = 0; i < N; ++i)
+        if ((int32_t)j->op_n_parents[i] > in_deg[i])
+            return set_error(RAMP_ERR_BAD_ARG, "op %d has n_parents %d > in-degree %d", i, (int)j->op_n_parents[i], in_deg[i]);
     // ---- derive ----
     std::vector<uint32_t> op_key, dep_key;
     make_rank_keys(j->op_prio, N, op_key);
@@ -769,6 +777,11 @@ int ramp_reset(ramp_engine_t* e, const ramp_arrival_t* arrivals, int32_t n_jobs)
                                    cudaMemcpyHostToDevice, e->stream));
     }
     e->ep.n_jobs = n_jobs;
+    {
+        std::vector<int32_t> nj(B, n_jobs);
+        CUDA_TRY(cudaMemcpyAsync(e->d_n_jobs_ep, nj.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));     // nj goes out of scope
+    }
     // memo is per env instance per episode: cleared on reset (RCE:269-275)
     CUDA_TRY(cudaMemsetAsync(e->d_memo_keys, 0, sizeof(unsigned long long) * e->memo_cap, e->stream));
     // the batch-wide cache of RAMP_MEMO_SHARED (level-2 keys, its result slots and traces) is a pure function of the
@@ -791,6 +804,25 @@ int ramp_set_arrivals(ramp_engine_t* e, int32_t episode, int32_t first_job, cons
     CUDA_TRY(cudaMemcpyAsync(e->d_arrivals + (size_t)episode * e->cfg.max_jobs + first_job, rows, sizeof(ramp_arrival_t) * (size_t)n,
                              cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RAMP_OK;
+}
+
+int ramp_set_job_count(ramp_engine_t* e, int32_t episode, int32_t n_jobs) {
+    if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");
+    if (episode < 0 || episode >= e->cfg.n_episodes || n_jobs < 0 || n_jobs > e->cfg.max_jobs)
+        return set_error(n_jobs > e->cfg.max_jobs ? RAMP_ERR_CAPACITY : RAMP_ERR_BAD_ARG,
+                         "job count %d of episode %d out of range (max_jobs=%d)", n_jobs, episode, e->cfg.max_jobs);
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(e->d_n_jobs_ep + episode, &n_jobs, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RAMP_OK;
+}
+
+int ramp_set_limits(ramp_engine_t* e, double max_sim_time, int32_t queue_capacity) {
+    if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");
+    if (queue_capacity < 0 || !(max_sim_time > 0.0)) return set_error(RAMP_ERR_BAD_ARG, "bad limits");
+    e->cfg.max_simulation_run_time = max_sim_time; e->cfg.job_queue_capacity = queue_capacity;
+    e->ep.max_sim_time = max_sim_time; e->ep.queue_capacity = queue_capacity;
     return RAMP_OK;
 }
 
@@ -943,6 +975,7 @@ int ramp_check_status(ramp_engine_t* e, int32_t* ep_out, int32_t* st_out) {
                      : st == RAMP_ST_TRACE_OVERFLOW ? "lookahead needed more ticks than trace_cap (or the trace pool is full)"
                      : st == RAMP_ST_TABLE_FULL ? "running-job table or memo table is full"
                      : st == RAMP_ST_NO_QUEUED_JOB ? "an action was given for an episode whose job queue is empty"
+                     : st == RAMP_ST_BAD_TEMPLATE ? "an action names a template id that was never registered"
                      : "simulation error";
     return set_error(RAMP_ERR_SIM, "episode %d: %s (status %d)", b, what, st);
 }

@@ -119,6 +119,8 @@ struct EpisodeState {
     int32_t* ri;                // [RI_COUNT][max_running][B]
     ramp_job_record_t* rec;     // [B][max_jobs]
     const ramp_arrival_t* arr;  // [B][max_jobs]
+    const int32_t* n_jobs_ep;   // [B] jobs the episode's arrival stream holds so far (len(jobs_generator) > 0 <=> more than arrived,
+                                //     RCE:1019-1040); ramp_reset sets n_jobs for all, ramp_set_job_count changes one episode
 };
 
 struct MemoTable {
@@ -748,7 +750,12 @@ __global__ void ramp_plan_kernel(const PlanArgs p) {
     ei[EI_PLAN_RAN * B + b] = 0;
     const ramp_action_t act = p.actions[b];
     if ((act.flags & RAMP_ACT_SKIP) || ei[EI_DONE * B + b]) return;
-    if (act.template_id < 0 || act.template_id >= p.n_templates) return;
+    if (act.template_id < 0) return;
+    if (act.template_id >= p.n_templates) {                             // the reference would KeyError on an unknown job
+        atomicCAS(&p.counters->err_episode, 0, b + 1);
+        ei[EI_STATUS * B + b] = RAMP_ST_BAD_TEMPLATE;
+        return;
+    }
     if (ei[EI_QUEUED * B + b] < 0) return;                              // reported by the step kernel
     const TemplateDev& T = p.templates[act.template_id];
     const uint32_t cap_mask = p.memo.mask;
@@ -861,7 +868,7 @@ __device__ inline bool step_is_done(const EpisodeState& ep, int b) {   // RCE:15
     const int B = ep.B;
     const double* ef = ep.ef; const int32_t* ei = ep.ei;
     if (EF(EF_NOW) >= ep.max_sim_time) return true;
-    return (ep.n_jobs - EI(EI_NUM_ARRIVED)) == 0 && EI(EI_N_RUNNING) == 0 && EI(EI_QUEUED) < 0;
+    return (ep.n_jobs_ep[b] - EI(EI_NUM_ARRIVED)) <= 0 && EI(EI_N_RUNNING) == 0 && EI(EI_QUEUED) < 0;
 }
 
 __device__ inline void step_get_next_job(const EpisodeState& ep, int b) {   // RCE:351-377
@@ -1028,7 +1035,7 @@ __global__ void ramp_step_kernel(const StepArgs s) {
                     }
                 }
                 // RCE:1019-1040
-                if ((ep.n_jobs - EI(EI_NUM_ARRIVED)) > 0) {
+                if ((ep.n_jobs_ep[b] - EI(EI_NUM_ARRIVED)) > 0) {
                     if (__dadd_rn(now2, ep.eps) >= EF(EF_NEXT_ARRIVAL)) {
                         const int idx = EI(EI_NUM_ARRIVED);
                         step_get_next_job(ep, b);

@@ -87,6 +87,10 @@ def load_library():
     L.ramp_template_count.argtypes = [C.c_void_p]
     L.ramp_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.ramp_set_arrivals.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    L.ramp_set_job_count.restype = C.c_int
+    L.ramp_set_job_count.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    L.ramp_set_limits.restype = C.c_int
+    L.ramp_set_limits.argtypes = [C.c_void_p, C.c_double, C.c_int32]
     L.ramp_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.ramp_step_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     L.ramp_sync.argtypes = [C.c_void_p]
@@ -120,7 +124,8 @@ EXPORTED_SYMBOLS = ['ramp_last_error', 'ramp_engine_create', 'ramp_engine_destro
                     'ramp_get_memo_stats', 'ramp_get_memo_stats_ex',
                     'ramp_get_last_lookahead', 'ramp_run_lookaheads', 'ramp_launch_count',
                     'ramp_get_lookahead_kernel_time', 'ramp_expand_template', 'ramp_free_expanded_job', 'ramp_free_expanded_aux', 'ramp_first_fit_place',
-                    'ramp_quotient_template', 'ramp_free_quotient', 'ramp_get_quotient_bytes']
+                    'ramp_quotient_template', 'ramp_free_quotient', 'ramp_get_quotient_bytes', 'ramp_set_job_count',
+                    'ramp_set_limits']
 
 
 def _check(rc):
@@ -193,6 +198,13 @@ class RampEngine:
     def set_arrivals(self, episode, first_job, rows):
         rows = np.ascontiguousarray(rows, dtype=ARRIVAL_DTYPE).reshape(-1)
         _check(self._L.ramp_set_arrivals(self._h, episode, first_job, rows.ctypes.data, len(rows)))
+
+    def set_job_count(self, episode, n_jobs):
+        """len(jobs_generator) > 0 of one episode, as a count of jobs its arrival stream holds so far (RCE:1019-1040)."""
+        _check(self._L.ramp_set_job_count(self._h, episode, n_jobs))
+
+    def set_limits(self, max_simulation_run_time=float('inf'), job_queue_capacity=10):
+        _check(self._L.ramp_set_limits(self._h, float(max_simulation_run_time), int(job_queue_capacity)))
 
     def make_actions(self):
         a = np.zeros(self.n_episodes, dtype=ACTION_DTYPE)

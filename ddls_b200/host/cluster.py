@@ -26,8 +26,8 @@ import numpy as np
 
 from .. import engine as _engine
 from ..lowering import ModelRegistry, lower_job
-from .devices import A100, gen_job_dep_str
-from .job_queue import JobQueue
+from ._classes import A100, JobQueue
+from .devices import gen_job_dep_str
 from .topology import Ramp
 
 SS = _engine.SS
@@ -142,27 +142,28 @@ class RampClusterEnvironment:
         self._pending = None           # (job, gap) drawn one ahead of its arrival
         self._done = False
 
-        # engine: one episode; the memo tables are cleared by ramp_reset like RCE:269-275
-        if self._engine is not None:
-            self._engine.close()
-        self._engine = _engine.RampEngine(
-            n_episodes=1, n_cluster_workers=self.topology.graph.graph['num_workers'], max_jobs=self._max_jobs,
-            device=self.device, job_queue_capacity=job_queue_capacity, machine_epsilon=self.machine_epsilon,
-            max_simulation_run_time=float(max_simulation_run_time), memo_mode=_engine.MEMO_REFERENCE)
-        self._template_cache = {}
-        # first job (RCE:280-281)
+        # engine: ONE episode, created once per environment and re-used by every reset(); ramp_reset clears the memo tables
+        # like RCE:269-275 (registered templates are immutable and stay)
+        n_workers = self.topology.graph.graph['num_workers']
+        if self._engine is None:
+            self._engine = _engine.RampEngine(
+                n_episodes=1, n_cluster_workers=n_workers, max_jobs=self._max_jobs, device=self.device,
+                job_queue_capacity=job_queue_capacity, machine_epsilon=self.machine_epsilon,
+                max_simulation_run_time=float(max_simulation_run_time), memo_mode=_engine.MEMO_REFERENCE)
+            self._template_cache = {}
+        else:
+            self._engine.set_limits(float(max_simulation_run_time), job_queue_capacity)
+        # first job (RCE:280-281).  The arrival stream is fed one job ahead of its arrival (see step()); the engine's
+        # "len(jobs_generator) > 0" is `job count - arrived > 0`, kept exact with ramp_set_job_count, so generators that never
+        # run dry ('remove_and_repeat', 'replace') keep producing arrivals until max_simulation_run_time like the reference.
         self.time_next_job_to_arrive = 0
         job, gap = self._draw_job()
-        n_total = 1 + len(self.jobs_generator)
-        if n_total > self._max_jobs:
-            n_total = self._max_jobs           # 'remove_and_repeat' generators never run dry; bounded by max_jobs
-        self._n_total = n_total
-        rows = np.zeros((1, n_total), dtype=_engine.ARRIVAL_DTYPE)
-        rows['interarrival'] = np.inf
+        rows = np.zeros((1, 1), dtype=_engine.ARRIVAL_DTYPE)
         rows[0, 0] = self._arrival_row(job, gap)
         self._engine.reset(rows)
         self._register_arrival(job, gap)
         self.job_queue.add(job)
+        self._rec_prev = self._engine.job_records()[0].copy()
         return None
 
     def _reset_steps_log(self):
@@ -211,11 +212,15 @@ class RampClusterEnvironment:
             raise Exception('reset() must be called before step()')
         self.action = action
         eng = self._engine
-        # draw the next job one ahead (see module docstring) and stream its arrival row to the engine
-        if self._pending is None and len(self.jobs_generator) > 0 and self.num_jobs_arrived < self._n_total:
+        # draw the next job one ahead (see module docstring), stream its arrival row to the engine and tell it whether the
+        # generator still holds a job (RCE:1019-1040)
+        if self._pending is None and len(self.jobs_generator) > 0:
+            if self.num_jobs_arrived >= self._max_jobs:
+                raise Exception(f'more than max_jobs={self._max_jobs} arrivals in one episode: construct the environment with a larger max_jobs')
             job, gap = self._draw_job()
             self._pending = (job, gap)
             eng.set_arrivals(0, self.num_jobs_arrived, np.array([self._arrival_row(job, gap)], dtype=_engine.ARRIVAL_DTYPE))
+        eng.set_job_count(0, self.num_jobs_arrived + (1 if self._pending is not None else 0))
 
         job_ids = list(action.job_ids)
         if len(job_ids) > 1:
@@ -244,10 +249,11 @@ class RampClusterEnvironment:
             mounted_job = self.jobs_running[self.job_id_to_job_idx[job_id]]
             mounted_job._lowered = lj
 
-        before = eng.job_records()[0].copy()
+        before = self._rec_prev                                           # records only change inside a step
         stats = eng.step(actions)[0]
         eng.check_status()                                                # raises like RCE:462
-        after = eng.job_records()[0]
+        after = eng.job_records()[0].copy()
+        self._rec_prev = after
         self._replay(stats, before, after, mounted_job, newly_blocked_host)
         done = bool(stats[SS['done']])
         self._done = done
@@ -411,16 +417,42 @@ class RampClusterEnvironment:
         if mounted_job is not None:
             idx = mounted_job.details['job_idx']
             rec = after[idx]
-            if rec['status'] == JS.JS_BLOCKED:
+            # a record that is BLOCKED with its lookahead results filled in was accepted (RCE:826-888) and then blocked because
+            # the simulation ended in this very step with the job still running (RCE:1111-1121): handled with the events below
+            if rec['status'] == JS.JS_BLOCKED and float(rec['jct']) == 0.0:
                 self._register_blocked_job(mounted_job.original_job)
                 self._remove_job_from_cluster(mounted_job)
             else:
-                mounted_job.details['lookahead_job_completion_time'] = float(rec['jct'])
-                mounted_job.details['communication_overhead_time'] = float(rec['comm'])
-                mounted_job.details['computation_overhead_time'] = float(rec['comp'])
-                mounted_job.details['mean_mounted_worker_utilisation_frac'] = float(rec['util'])
-                mounted_job.details['job_total_flow_size'] = mounted_job._lowered.mount.flow_size
+                details = {'lookahead_job_completion_time': float(rec['jct']),
+                           'communication_overhead_time': float(rec['comm']),
+                           'computation_overhead_time': float(rec['comp']),
+                           'mounted_workers': mounted_job.details['mounted_workers'],
+                           'mounted_channels': mounted_job.details['mounted_channels'],
+                           'mean_mounted_worker_utilisation_frac': float(rec['util'])}
+                if hasattr(mounted_job, 'reset_job') and hasattr(self.op_partition, 'job_id_to_max_partition_degree'):
+                    # RCE:848-879: reset the whole job for the actual simulation, re-using (and then refreshing) the
+                    # per-(model, max partition degree) init details that OpPartition reads (op_partition.py:47-50)
+                    job_id = mounted_job.job_id
+                    mnp = self.op_partition.job_id_to_max_partition_degree[job_id]
+                    model = mounted_job.details['model']
+                    memo = self.job_model_to_max_num_partitions_to_init_details
+                    tot_mem = tot_dep = imm = None
+                    if model in memo and mnp in memo[model]:
+                        tot_mem = memo[model][mnp]['job_total_operation_memory_cost']
+                        tot_dep = memo[model][mnp]['job_total_dependency_size']
+                        imm = memo[model][mnp]['init_job_immutable_details']
+                    memo[model]
+                    mounted_job.reset_job(details=details, job_total_operation_memory_cost=tot_mem,
+                                          job_total_dependency_size=tot_dep, init_job_immutable_details=imm)
+                    memo[model][mnp]['job_total_operation_memory_cost'] = mounted_job.job_total_operation_memory_cost
+                    memo[model][mnp]['job_total_dependency_size'] = mounted_job.job_total_dependency_size
+                    memo[model][mnp]['init_job_immutable_details'] = mounted_job.init_job_immutable_details
+                    memo[model][mnp]['partitioned_computation_graph'] = self.op_partition.job_id_to_partitioned_computation_graph[job_id]
+                else:
+                    mounted_job.details.update(details)
+                mounted_job.details['job_total_flow_size'] = mounted_job._lowered.mount.flow_size          # RCE:882-888
         # 3. events of the outer loop, in event order (RCE:1004-1037)
+        n_blocked_at_sim_end = 0
         changed = [i for i in range(self.num_jobs_arrived) if after[i]['status'] != before[i]['status']
                    and after[i]['status'] in (JS.JS_COMPLETED, JS.JS_BLOCKED)]
         for i in sorted(changed, key=lambda i: int(after[i]['event_seq'])):
@@ -431,6 +463,7 @@ class RampClusterEnvironment:
             elif after[i]['status'] == JS.JS_BLOCKED and job is not None:     # still running when the simulation ended (RCE:1111-1121)
                 self._register_blocked_job(job.original_job)
                 self._remove_job_from_cluster(job)
+                n_blocked_at_sim_end += 1
         self.stopwatch._time = float(stats[SS['step_end_time']])
         if step_stats['num_jobs_arrived'] > 0:
             job, gap = self._pending
@@ -448,8 +481,10 @@ class RampClusterEnvironment:
             self.mounted_channels.update(job.details['mounted_channels'])
 
         # logs (RCE:1082-1109)
+        # the reference appends to steps_log BEFORE it blocks the jobs still running at the end of the simulation (RCE:1082-1090 vs
+        # RCE:1111-1121), so the log's last num_jobs_blocked lacks them while step_stats has them
         for key, val in step_stats.items():
-            self.steps_log[key].append(val)
+            self.steps_log[key].append(val - n_blocked_at_sim_end if key == 'num_jobs_blocked' else val)
         for metric in ('compute_info_processed', 'dep_info_processed', 'flow_info_processed', 'cluster_info_processed',
                        'demand_compute_info_processed', 'demand_dep_info_processed', 'demand_total_info_processed',
                        'mean_compute_overhead_frac', 'mean_communication_overhead_frac', 'mean_num_jobs_running',

@@ -46,6 +46,7 @@ extern "C" {
 #define RAMP_ST_TABLE_FULL 3         /* running-job table full (ramp_config_t.max_running)            */
 #define RAMP_ST_NO_QUEUED_JOB 4      /* an action was given for an episode with an empty job queue    */
 #define RAMP_ST_JOBS_EXHAUSTED 5     /* more arrivals than ramp_config_t.max_jobs                     */
+#define RAMP_ST_BAD_TEMPLATE 6       /* an action names a template id that was never registered       */
 
 /* memo modes (RCE:269-277, RCE:488-506) */
 #define RAMP_MEMO_REFERENCE 0        /* key = (episode, model, max partition degree): first seen wins, per episode */
@@ -170,6 +171,13 @@ int ramp_reset(ramp_engine_t* eng, const ramp_arrival_t* arrivals, int32_t n_job
  * drop-in RampClusterEnvironment, whose JobsGenerator samples the next job only when needed, RCE:351-377) stream
  * the arrival process instead of fixing it at reset. */
 int ramp_set_arrivals(ramp_engine_t* eng, int32_t episode, int32_t first_job, const ramp_arrival_t* rows, int32_t n);
+/* How many jobs one episode's arrival stream holds so far (<= max_jobs).  The engine treats `n_jobs - arrived > 0` as the
+ * reference's `len(self.jobs_generator) > 0` (RCE:1019-1040, RCE:1542-1557): a host that draws jobs lazily from a generator
+ * that never runs dry ('remove_and_repeat' sampling) keeps it one ahead of the arrivals instead of fixing it at reset. */
+int ramp_set_job_count(ramp_engine_t* eng, int32_t episode, int32_t n_jobs);
+/* max_simulation_run_time / job_queue_capacity of the NEXT ramp_reset (RCE:202-205), so that one engine serves every
+ * reset() of a drop-in environment */
+int ramp_set_limits(ramp_engine_t* eng, double max_simulation_run_time, int32_t job_queue_capacity);
 
 /* One RampClusterEnvironment.step for every episode.  HOST buffers; the host<->device copies are issued
  * on the engine stream inside the call:  actions [n_episodes] in,  stats [n_episodes][RAMP_STEP_STATS_LEN]

@@ -95,6 +95,10 @@ def lib():
         L.orc_env_reset.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_int32]
         L.orc_env_step.restype = C.c_int
         L.orc_env_step.argtypes = [C.c_void_p, C.POINTER(CLoweredJob), C.POINTER(CMount), C.c_void_p]
+        L.orc_env_set_arrival.restype = C.c_int
+        L.orc_env_set_arrival.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_env_set_job_count.restype = C.c_int
+        L.orc_env_set_job_count.argtypes = [C.c_void_p, C.c_int32]
         L.orc_env_queued_job.restype = C.c_int32
         L.orc_env_queued_job.argtypes = [C.c_void_p]
         L.orc_env_num_jobs_arrived.restype = C.c_int32
@@ -174,6 +178,16 @@ class OracleEnv:
         rc = lib().orc_env_reset(self._h, max_simulation_run_time, job_queue_capacity, arr.ctypes.data, len(arr))
         if rc != 0:
             raise Exception(f'orc_env_reset failed with status {rc}')
+
+    def set_arrival(self, k, row):
+        r = np.ascontiguousarray(row, dtype=ARRIVAL_DTYPE).reshape(1)
+        if lib().orc_env_set_arrival(self._h, k, r.ctypes.data) != 0:
+            raise Exception('orc_env_set_arrival failed')
+        self._n_jobs = max(self._n_jobs, k + 1)
+
+    def set_job_count(self, n):
+        if lib().orc_env_set_job_count(self._h, n) != 0:
+            raise Exception('orc_env_set_job_count failed')
 
     def step(self, job=None):
         stats = np.zeros(STEP_STATS_LEN, dtype=np.float64)

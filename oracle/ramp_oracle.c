@@ -290,6 +290,20 @@ int orc_env_reset(orc_env_t* env, double max_simulation_run_time, int32_t job_qu
     return ORC_OK;
 }
 
+/* A host that draws jobs lazily from the reference's JobsGenerator (RCE:351-377) streams the arrival rows one ahead and
+ * tells the env whether the generator still holds a job: `n_jobs - num_arrived > 0` stands for `len(jobs_generator) > 0`
+ * (RCE:1019-1040).  Mirrors ramp_set_arrivals / ramp_set_job_count of the product's C ABI. */
+int orc_env_set_arrival(orc_env_t* env, int32_t k, const orc_arrival_t* row) {
+    if (k < 0 || k >= env->max_jobs) return ORC_ERR_BAD_ARG;
+    env->arrivals_own[k] = *row;
+    return ORC_OK;
+}
+int orc_env_set_job_count(orc_env_t* env, int32_t n_jobs) {
+    if (n_jobs < 0 || n_jobs > env->max_jobs) return ORC_ERR_BAD_ARG;
+    env->n_jobs = n_jobs;
+    return ORC_OK;
+}
+
 /* RCE:1504-1540 (the counters; per-job lists are rebuilt from the records) */
 static void register_blocked(orc_env_t* env, int32_t job_idx) {
     orc_job_record_t* r = &env->records[job_idx];

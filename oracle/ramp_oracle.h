@@ -169,6 +169,10 @@ int orc_env_reset(orc_env_t* env, double max_simulation_run_time, int32_t job_qu
  * stats: double[ORC_STEP_STATS_LEN].  Returns ORC_OK or an error status. */
 int orc_env_step(orc_env_t* env, const orc_lowered_job_t* job, const orc_mount_t* mount, double* stats);
 
+/* lazily drawn arrival streams (see ramp_oracle.c) */
+int orc_env_set_arrival(orc_env_t* env, int32_t k, const orc_arrival_t* row);
+int orc_env_set_job_count(orc_env_t* env, int32_t n_jobs);
+
 /* accessors */
 int32_t orc_env_queued_job(const orc_env_t* env);   /* job idx at head of queue or -1 */
 int32_t orc_env_num_jobs_arrived(const orc_env_t* env);
