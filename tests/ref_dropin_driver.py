@@ -20,6 +20,11 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 
 
+# The reference lists its job files with an UNSORTED glob (jobs_generator.py:96), so which file is "job type 0" depends on the
+# file system's directory order.  These are the orders of the container the golden fixtures were generated in; the driver pins
+# them so that the seeded episodes are the same episodes on every machine.
+FILE_ORDER = {'mixed16': ['res2.txt', 'chain5.txt', 'tfm1.txt'], 'mixed64_busy': ['tfm1b.txt', 'chain4.txt', 'res1.txt']}
+
 EXTRA_CASES = {
     # a generator that never runs dry (the reference's default 'remove_and_repeat' sampling, heuristic_config.yaml:126): the
     # episode ends on max_simulation_run_time, arrivals keep coming until then
@@ -62,6 +67,18 @@ def main():
     d = tempfile.mkdtemp(prefix='dropin_graphs_')
     for g in spec['graphs']:
         g.write(d)
+    if case in FILE_ORDER:
+        import ddls.demands.jobs.jobs_generator as jg_mod
+        import glob as _glob
+        real_glob = _glob.glob
+
+        class _PinnedGlob:
+            @staticmethod
+            def glob(pattern, *a, **kw):
+                found = real_glob(pattern, *a, **kw)
+                rank = {n: i for i, n in enumerate(FILE_ORDER[case])}
+                return sorted(found, key=lambda pth: rank.get(os.path.basename(pth), len(rank)))
+        jg_mod.glob = _PinnedGlob
     env = gen_golden.make_env(d, spec['shape'], spec['n_jobs'], spec['max_partitions'], spec['interarrival'],
                               Uniform(spec['frac'][0], spec['frac'][1], decimals=2), max_sim_time=spec.get('max_sim_time', 1e6),
                               sampling_mode=sampling_mode)
