@@ -1,0 +1,324 @@
+"""Batched gym-like surface over ONE B-episode engine: thousands of ``RampJobPartitioningEnvironment`` rollouts in lock step.
+
+``BatchedRampJobPartitioningEnvironment.reset() -> obs`` / ``.step(actions[B]) -> (obs, reward[B], done[B], info)`` is, per
+episode, ``RampJobPartitioningEnvironment.reset / step`` (RJPE:243-274, :300-420): the action is the maximum partition
+degree of the queued job (0 = do not place); each op gets ``clamp(even(ceil(cost / quantum)), 1, action)`` sub-ops
+(RJPE:332-343); the job is placed by the reference's first-fit rule (ramp_first_fit_place: agents/placers/utils.py:68-582),
+partitioned / timed / scheduled / mounted on one-hop channels like the reference's pipeline (ramp_expand_template:
+OpPartition, update_dep_run_times, SRPT schedulers, FirstFitDepPlacer), handed to the engine, and the cluster is stepped
+until the next job is queued (RJPE:394-395, fused on the device).  Nothing of that is redone per episode:
+
+  * a placement is a pure function of (model, degree, which servers are busy): decisions are cached by that key and the
+    B episodes of a step are grouped by it with one ``np.unique`` -- a step of 4,096 episodes calls the native placer a
+    handful of times (first-fit blocks repeat), never 4,096 times;
+  * a lowered job is a pure function of (model, degree, servers of the block): templates are cached by that key; a miss
+    costs one native expansion + one symmetry quotient + one upload (milliseconds), a hit costs nothing;
+  * what the policy observes of a job is static per model (node / edge features and the per-graph statistics,
+    observation.py:503-567) except a few graph-level numbers: ``obs`` carries the model index of every episode's queued job,
+    the dynamic graph features ``[B, 11]`` (the normalised job totals, max-acceptable JCT and fraction, mounted workers and
+    running jobs over the cluster size: observation.py:358-498) and the action mask ``[B, |A|]`` (observation.py:80-131).
+
+The per-episode random streams (which model arrives, its max-acceptable-JCT fraction, the inter-arrival gaps) are drawn
+up front for ``jobs_per_episode`` arrivals, or supplied (``script=``) -- that is how the tests replay the reference's
+recorded episodes in lock step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine as _engine
+from .expand import expand_template
+from .observation import PARAM_KEYS, _block_shapes_exist
+from .placer import first_fit_place_native
+from .synth import ForwardGraph
+from .template_builder import RampShape, original_job_totals
+
+SS, EP = _engine.SS, _engine.EP
+A100_MEMORY = 80e9                       # devices/processors/gpus/A100.py:17
+
+
+class _Model:
+    """What the environment needs of one job type, computed once."""
+
+    def __init__(self, g: ForwardGraph, quantum: float, num_training_steps: int):
+        self.graph = g
+        self.n = g.n
+        self.mem = [a + p for a, p in zip(g.act, g.par)]
+        self.op_mem_total, self.dep_size_total = original_job_totals(g)
+        self.quantum = quantum
+        # the mirrored job graph's node order: forward 1..n then backward 2n..n+1 is NOT the reference's dict order; the static
+        # observation only needs multiset statistics and per-op arrays in any fixed order, so forward-then-backward is used
+        self.seq_time = float(sum(g.fwd) + sum(g.bwd)) * num_training_steps
+
+    def splits(self, degree: int) -> List[int]:
+        return [int(max(1, min(math.ceil(math.ceil(c / self.quantum) / 2) * 2, degree))) for c in self.graph.fwd]   # RJPE:336
+
+
+class BatchedRampJobPartitioningEnvironment:
+    def __init__(self, shape: Tuple[int, int, int], graphs: Sequence[ForwardGraph], n_episodes: int, jobs_per_episode: int = 8,
+                 max_partitions_per_op: int = 16, min_op_run_time_quantum: float = 0.01, num_training_steps: int = 50,
+                 interarrival=('fixed', 1000.0), frac=(0.1, 1.0, 2), max_simulation_run_time: float = float('inf'),
+                 fail_reward: float = -1, success_reward: float = 1, device: int = 0, seed: int = 0,
+                 run_times: str = 'reference', apply_action_mask: bool = True, script: Optional[dict] = None,
+                 memo_mode: int = _engine.MEMO_REFERENCE):
+        self.shape = RampShape(*shape)
+        self.W = self.shape.n_workers
+        self.B, self.J = int(n_episodes), int(jobs_per_episode)
+        self.max_partitions_per_op = int(max_partitions_per_op)
+        self.num_training_steps = num_training_steps
+        self.models = [_Model(g, min_op_run_time_quantum, num_training_steps) for g in graphs]
+        self.interarrival, self.frac_dist = interarrival, frac
+        self.max_simulation_run_time = float(max_simulation_run_time)
+        self.fail_reward, self.success_reward = fail_reward, success_reward
+        self.apply_action_mask = apply_action_mask
+        self.run_times = run_times
+        self.rng = np.random.default_rng(seed)
+        self.script = script
+        self.eng = _engine.RampEngine(n_episodes=self.B, n_cluster_workers=self.W, max_jobs=self.J, device=device,
+                                      memo_mode=memo_mode, trace_cap=8192, max_simulation_run_time=self.max_simulation_run_time)
+        self.n_words = (self.W + 63) // 64
+        self._servers = [(c, r, s) for c in range(self.shape.c) for r in range(self.shape.r) for s in range(self.shape.s)]
+        self._server_index = {sv: i for i, sv in enumerate(self._servers)}
+        # action set (observation.py:80-131): 0..max_partitions_per_op; which actions have a RAMP-symmetric block shape at all
+        self.action_set = np.arange(self.max_partitions_per_op + 1, dtype=np.int16)
+        self._shape_ok = np.array([True] + [(a == 1) or (a % 2 == 0 and _block_shapes_exist(a, shape))
+                                            for a in range(1, self.max_partitions_per_op + 1)])
+        # caches
+        self._placement_cache: Dict[tuple, tuple] = {}       # (model, degree, busy words...) -> (template id | -1, mask words)
+        self._template_cache: Dict[tuple, int] = {}          # (model, degree, coords) -> template id
+        self._t_mount: List[tuple] = []                      # per template id: (seq_time, part_op_mem, part_dep, flow, n_workers, n_channels)
+        self._t_arrays = None
+        self.stats = {'placer_calls': 0, 'expansions': 0, 'placement_hits': 0}
+        self._jobs_params = None
+
+    # ---- arrival streams ------------------------------------------------------------------------------------------
+    def _draw_streams(self):
+        B, J, M = self.B, self.J, len(self.models)
+        if self.script is not None:
+            self.model_of = np.asarray(self.script['model'], dtype=np.int64).reshape(B, J)
+            gaps = np.asarray(self.script['gap'], dtype=np.float64).reshape(B, J)
+            self.frac = np.asarray(self.script.get('frac', np.ones((B, J))), dtype=np.float64).reshape(B, J)
+            self.macc_override = (np.asarray(self.script['max_acceptable_jct'], dtype=np.float64).reshape(B, J)
+                                  if 'max_acceptable_jct' in self.script else None)
+        else:
+            self.model_of = self.rng.integers(0, M, size=(B, J))
+            kind = self.interarrival[0]
+            if kind == 'fixed':
+                gaps = np.full((B, J), float(self.interarrival[1]))
+            elif kind == 'exponential':
+                gaps = self.rng.exponential(float(self.interarrival[1]), size=(B, J))
+            else:
+                raise Exception(f'unknown inter-arrival distribution {kind}')
+            gaps[:, J - 1] = np.inf                              # no job after the last one (jobs_generator.py:270-272)
+            lo, hi, dec = self.frac_dist
+            self.frac = np.round(self.rng.uniform(lo, hi, size=(B, J)), dec)
+            self.macc_override = None
+        arr = np.zeros((B, J), dtype=_engine.ARRIVAL_DTYPE)
+        arr['interarrival'] = gaps
+        arr['orig_op_mem'] = np.array([m.op_mem_total for m in self.models])[self.model_of]
+        arr['orig_dep_size'] = np.array([m.dep_size_total for m in self.models])[self.model_of]
+        return arr
+
+    # ---- RJPE.reset ----------------------------------------------------------------------------------------------
+    def reset(self):
+        self.arrivals = self._draw_streams()
+        self.eng.reset(self.arrivals)
+        B, J = self.B, self.J
+        self.busy = np.zeros((B, self.n_words), dtype=np.uint64)
+        self.job_mask = np.zeros((B, J, self.n_words), dtype=np.uint64)
+        self.status = np.zeros((B, J), dtype=np.int32)
+        self.status[:, 0] = _engine.JS_QUEUED
+        self.queued = np.zeros(B, dtype=np.int64)                 # RCE:280-281: job 0 is queued
+        self.done = np.zeros(B, dtype=bool)
+        self.n_running = np.zeros(B, dtype=np.int64)
+        self.step_counter = 0
+        return self._observe()
+
+    # ---- placement + lowering, cached ------------------------------------------------------------------------------
+    def _free_count(self):
+        return self.W - np.bitwise_count(self.busy).sum(axis=1).astype(np.int64)
+
+    def action_mask(self):
+        """[B, |A|] validity of every action for the queued job (observation.py:80-131)."""
+        free = self._free_count()
+        a = self.action_set.astype(np.int64)[None, :]
+        ok = (a <= free[:, None]) & self._shape_ok[None, :]
+        ok[:, 0] = True
+        return ok
+
+    def _place(self, m: int, degree: int, busy_words: tuple):
+        """(template id or -1, server mask words) of model m at `degree` on a cluster whose busy servers are `busy_words`."""
+        key = (m, degree) + busy_words
+        hit = self._placement_cache.get(key)
+        if hit is not None:
+            self.stats['placement_hits'] += 1
+            return hit
+        model = self.models[m]
+        busy = {}
+        for i, sv in enumerate(self._servers):
+            busy[sv] = bool((busy_words[i >> 6] >> (i & 63)) & 1)
+        free_mem = {sv: A100_MEMORY for sv in self._servers}
+        self.stats['placer_calls'] += 1
+        where = first_fit_place_native(model.n, model.mem, model.graph.edges, model.splits(degree), free_mem, busy,
+                                       (self.shape.c, self.shape.r, self.shape.s))
+        if where is None:                                          # the reference leaves the job out of the Action: blocked (RCE:914-919)
+            out = (-1, (0,) * self.n_words)
+        else:
+            coords = tuple(sorted(set(where.values())))
+            tkey = (m, degree, coords)
+            tid = self._template_cache.get(tkey)
+            if tid is None:
+                self.stats['expansions'] += 1
+                lj = expand_template(model.graph, degree, self.shape, quantum=model.quantum,
+                                     num_training_steps=self.num_training_steps, model_id=m, run_times=self.run_times, coords=list(coords))
+                tid = self.eng.register_template(lj)
+                self._template_cache[tkey] = tid
+                mt = lj.mount
+                while len(self._t_mount) <= tid:
+                    self._t_mount.append(None)
+                self._t_mount[tid] = (lj.seq_time, mt.part_op_mem, mt.part_dep_size, mt.flow_size, mt.n_mounted_workers, mt.n_mounted_channels)
+                self._t_arrays = None
+            words = [0] * self.n_words
+            for sv in coords:
+                i = self._server_index[sv]
+                words[i >> 6] |= (1 << (i & 63))
+            out = (tid, tuple(words))
+        self._placement_cache[key] = out
+        return out
+
+    def _mount_arrays(self):
+        if self._t_arrays is None:
+            rows = [r if r is not None else (0.0,) * 6 for r in self._t_mount]
+            self._t_arrays = np.array(rows, dtype=np.float64).reshape(-1, 6) if rows else np.zeros((0, 6))
+        return self._t_arrays
+
+    # ---- RJPE.step -----------------------------------------------------------------------------------------------
+    def step(self, actions):
+        B, J = self.B, self.J
+        actions = np.asarray(actions, dtype=np.int64).reshape(B)
+        live = ~self.done
+        q = self.queued
+        if np.any(live & (q < 0)):
+            raise Exception('an episode that is not done has no queued job (RJPE:394-395 keeps stepping until there is one)')
+        mask = self.action_mask()
+        bad_set = live & ((actions < 0) | (actions > self.max_partitions_per_op))
+        if np.any(bad_set):
+            b = int(np.nonzero(bad_set)[0][0])
+            raise Exception(f'Action {int(actions[b])} not in action set {self.action_set.tolist()}.')                 # RJPE:314-316
+        invalid = live & ~mask[np.arange(B), np.clip(actions, 0, self.max_partitions_per_op)]
+        if np.any(invalid):
+            if self.apply_action_mask:
+                b = int(np.nonzero(invalid)[0][0])
+                raise Exception(f'Action {int(actions[b])} is invalid given action mask {mask[b].astype(int).tolist()}.')  # RJPE:317-319
+            actions = np.where(invalid, 0, actions)                                                                        # RJPE:320-322
+        qq = np.clip(q, 0, J - 1)
+        m_of = self.model_of[np.arange(B), qq]
+        # ---- group the episodes by (model, degree, busy servers): one placement decision per group ----
+        tid = np.full(B, -1, dtype=np.int32)
+        mask_words = np.zeros((B, self.n_words), dtype=np.uint64)
+        sel = np.nonzero(live & (actions > 0))[0]
+        if len(sel):
+            keys = np.concatenate([m_of[sel, None].astype(np.uint64), actions[sel, None].astype(np.uint64), self.busy[sel]], axis=1)
+            uniq, inv = np.unique(keys, axis=0, return_inverse=True)
+            inv = inv.reshape(-1)
+            u_tid = np.empty(len(uniq), dtype=np.int32)
+            u_words = np.zeros((len(uniq), self.n_words), dtype=np.uint64)
+            for k, row in enumerate(uniq):
+                t, words = self._place(int(row[0]), int(row[1]), tuple(int(x) for x in row[2:]))
+                u_tid[k] = t
+                u_words[k] = np.array(words, dtype=np.uint64)
+            tid[sel] = u_tid[inv]
+            mask_words[sel] = u_words[inv]
+        # ---- action rows ----
+        act = self.eng.make_actions()
+        act['flags'] = np.where(live, 0, _engine.ACT_SKIP)
+        placed = tid >= 0
+        if placed.any():
+            mt = self._mount_arrays()[tid[placed]]
+            fr = self.frac[np.arange(B), qq][placed]
+            macc = fr * mt[:, 0]
+            if self.macc_override is not None:
+                ov = self.macc_override[np.arange(B), qq][placed]
+                macc = np.where(np.isnan(ov), macc, ov)
+            act['max_acceptable_jct'][placed] = macc
+            act['part_op_mem'][placed] = mt[:, 1]
+            act['part_dep_size'][placed] = mt[:, 2]
+            act['flow_size'][placed] = mt[:, 3]
+            act['n_mounted_workers'][placed] = mt[:, 4].astype(np.int32)
+            act['n_mounted_channels'][placed] = mt[:, 5].astype(np.int32)
+        act['template_id'] = tid
+        stats, ncs = self.eng.step(act, fuse_empty_steps=True, want_cluster_steps=True)
+        self.eng.check_status()
+        rec = self.eng.job_records()
+        ep = self.eng.episode_state()
+        status = rec['status']
+        # ---- reward (rewards/job_acceptance.py): the job counts as placed unless it was blocked by the end of the FIRST cluster
+        #      step (RJPE:379-391); a lookahead-blocked job has no lookahead results in its record ----
+        rq = rec[np.arange(B), qq]
+        accepted = placed & (rq['jct'] != 0.0)
+        blocked_in_action_step = accepted & (rq['status'] == _engine.JS_BLOCKED) & (ncs == 1)
+        reward = np.where(accepted & ~blocked_in_action_step, self.success_reward, self.fail_reward).astype(np.float64)
+        reward[~live] = 0.0
+        # ---- occupancy: servers of the jobs that are running now ----
+        acc = np.nonzero(accepted)[0]
+        self.job_mask[acc, qq[acc]] = mask_words[acc]
+        running = (status == _engine.JS_RUNNING)
+        self.busy = np.bitwise_or.reduce(np.where(running[:, :, None], self.job_mask, np.uint64(0)), axis=1)
+        self.n_running = running.sum(axis=1)
+        self.status = status
+        self.queued = ep[:, EP['queued_job']].astype(np.int64)
+        self.done = ep[:, EP['done']] != 0
+        self.last_stats, self.last_cluster_steps = stats, ncs
+        self.step_counter += 1
+        info = {'template_id': tid, 'cluster_steps': ncs, 'accepted': accepted}
+        return self._observe(), reward, self.done.copy(), info
+
+    # ---- observations ---------------------------------------------------------------------------------------------
+    def jobs_params(self):
+        """(min, max) per PARAM_KEYS over the job types, as JobsGenerator.jobs_params holds them (jobs_generator.py:278-333)."""
+        if self._jobs_params is None:
+            lo, hi, _ = self.frac_dist
+            vals = {
+                'job_total_num_ops': [2 * m.n for m in self.models],
+                'job_total_num_deps': [2 * len(m.graph.edges) + 1 for m in self.models],
+                'job_sequential_completion_times': [m.seq_time for m in self.models],
+                'max_acceptable_job_completion_times': [f * m.seq_time for m in self.models for f in (lo, hi)],
+                'max_acceptable_job_completion_time_fracs': [lo, hi],
+                'job_total_op_memory_costs': [m.op_mem_total for m in self.models],
+                'job_total_dep_sizes': [m.dep_size_total for m in self.models],
+                'job_num_training_steps': [self.num_training_steps],
+            }
+            self._jobs_params = [(min(vals[k]), max(vals[k])) for k in PARAM_KEYS]
+        return self._jobs_params
+
+    def _observe(self):
+        B = self.B
+        qq = np.clip(self.queued, 0, self.J - 1)
+        m_of = self.model_of[np.arange(B), qq]
+        fr = self.frac[np.arange(B), qq]
+        P = self.jobs_params()
+
+        def norm(x, k):
+            lo, hi = P[PARAM_KEYS.index(k)]
+            return (x - lo) / (hi - lo) if hi - lo != 0 else np.ones_like(x, dtype=np.float64)
+        seq = np.array([m.seq_time for m in self.models])[m_of]
+        n_ops = np.array([2.0 * m.n for m in self.models])[m_of]
+        n_deps = np.array([2.0 * len(m.graph.edges) + 1 for m in self.models])[m_of]
+        opm = np.array([m.op_mem_total for m in self.models])[m_of]
+        dps = np.array([m.dep_size_total for m in self.models])[m_of]
+        mounted = self.W - self._free_count()
+        dyn = np.stack([norm(n_ops, 'job_total_num_ops'), norm(n_deps, 'job_total_num_deps'),
+                        norm(seq, 'job_sequential_completion_times'), norm(fr * seq, 'max_acceptable_job_completion_times'),
+                        norm(fr, 'max_acceptable_job_completion_time_fracs'), fr, norm(opm, 'job_total_op_memory_costs'),
+                        norm(dps, 'job_total_dep_sizes'),
+                        norm(np.full(B, float(self.num_training_steps)), 'job_num_training_steps'),
+                        mounted / self.W, self.n_running / self.W], axis=1).astype(np.float32)
+        mask = self.action_mask()
+        return {'model': m_of.astype(np.int32), 'graph_features_dynamic': dyn, 'action_set': self.action_set,
+                'action_mask': mask.astype(np.int16), 'queued_job': self.queued.copy(), 'done': self.done.copy()}
+
+    def close(self):
+        self.eng.close()
