@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument('--ref-budget', type=float, default=90.0, help='--impl reference: seconds of timed env-steps per process')
     ap.add_argument('--ref-procs', type=int, default=0, help='--impl reference: processes (0 = min(usable cores, 32))')
     ap.add_argument('--ref-kind', default='auto', choices=['auto', 'reference', 'port'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --episodes (or the config batch) per GPU; strong: the config batch divided over the GPUs')
+    ap.add_argument('--no-batched-env', action='store_true', help='skip the BatchedRampJobPartitioningEnvironment secondary figure')
     return ap.parse_args()
 
 
@@ -312,6 +315,8 @@ def run_b200_arm(args, rank, world, local_rank):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     cfg = workload.CONFIGS[args.config]
     B = args.episodes or cfg['n_episodes']
+    if args.scaling == 'strong':
+        B = max(1, B // world)                 # total work fixed: the config's batch divided over the GPUs
     L = args.segment
 
     # ---- build templates, get their JCTs from the CUDA path, script the episodes ----
@@ -343,25 +348,38 @@ def run_b200_arm(args, rank, world, local_rank):
     stats_dev = torch.empty((B, engine.STEP_STATS_LEN), dtype=torch.float64, device='cuda')
     ncs_dev = torch.empty(B, dtype=torch.int32, device='cuda')
     stats_pinned = torch.empty((B, engine.STEP_STATS_LEN), dtype=torch.float64).pin_memory()
-    ep_dev = torch.empty((B, engine.EP_LEN), dtype=torch.float64, device='cuda')
-    gathered = torch.empty((world * B, engine.EP_LEN), dtype=torch.float64, device='cuda') if world > 1 else None
+    # episode metrics: exported on the engine stream into one of two buffers, all-gathered over NCCL on a SIDE stream so that the
+    # collective of step s overlaps the lookaheads of step s + 1 (episodes shard with no other exchange)
+    ep_dev = [torch.empty((B, engine.EP_LEN), dtype=torch.float64, device='cuda') for _ in range(2)]
+    gathered = [torch.empty((world * B, engine.EP_LEN), dtype=torch.float64, device='cuda') for _ in range(2)] if world > 1 else None
     ext = torch.cuda.ExternalStream(eng.stream, device=torch.device('cuda', local_rank))
+    side = torch.cuda.Stream(device=torch.device('cuda', local_rank)) if world > 1 else None
+    gather_events = [None, None]
+    n_gathers = [0]
     torch.cuda.synchronize()
 
     def barrier():
+        if side is not None:
+            side.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def gather_metrics():
-        # one all-gather of the per-episode metric rows per batch step; episodes shard with no
-        # other exchange
-        eng.export_episode_state_to(ep_dev.data_ptr())
+        k = n_gathers[0] & 1
+        n_gathers[0] += 1
+        if world > 1 and gather_events[k] is not None:
+            ext.wait_event(gather_events[k])          # the collective that last read this buffer has finished
+        eng.export_episode_state_to(ep_dev[k].data_ptr())
         if world > 1:
             ev = torch.cuda.Event()
             ev.record(ext)
-            torch.cuda.current_stream().wait_event(ev)
-            dist.all_gather_into_tensor(gathered, ep_dev)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                dist.all_gather_into_tensor(gathered[k], ep_dev[k])
+                done_ev = torch.cuda.Event()
+                done_ev.record(side)
+            gather_events[k] = done_ev
 
     memo_acc = {'lookups': 0, 'hits': 0, 'lookaheads': 0}
     memo_base = {'lookups': 0, 'hits': 0, 'lookaheads': 0}     # part of the current segment that belongs to the warm-up
@@ -484,6 +502,55 @@ def run_b200_arm(args, rank, world, local_rank):
     except Exception as ex:          # secondary measurement only
         shared = {'error': str(ex)[:200]}
 
+    # ---- secondary: the batched gym-like surface (ddls_b200/batched.py): RJPE.step for every episode through host arrays, with
+    #      placement (native first-fit, cached by cluster occupancy), lowering (native expansion, cached by block) and the action
+    #      mask / graph features computed on the host inside the timed region; policy stand-in: random valid degree ----
+    batched = None
+    if not args.no_batched_env:
+        try:
+            from ddls_b200.batched import BatchedRampJobPartitioningEnvironment
+            graphs_b = [workload.make_graph(kind, **kw) for kind, kw in cfg['graphs']]
+            benv = BatchedRampJobPartitioningEnvironment(tuple(cfg['shape']), graphs_b, n_episodes=B, jobs_per_episode=L, device=local_rank,
+                                                         seed=args.seed + 7 * rank, run_times=args.run_times,
+                                                         interarrival=('exponential', 1000.0) if cfg.get('exponential') else ('fixed', 1000.0))
+            degs = np.array([d for d in cfg['degrees'] if d <= benv.W])
+            prng = np.random.default_rng(args.seed + 99 + rank)
+
+            def policy(obs):
+                ok = obs['action_mask'][:, degs].astype(bool)
+                r = prng.random(ok.shape) * ok
+                return np.where(ok.any(axis=1), degs[r.argmax(axis=1)], 0)
+            obs_b = benv.reset()
+            for s_ in range(W):
+                if s_ % L == 0 and s_ > 0:
+                    obs_b = benv.reset()
+                obs_b, _, _, _ = benv.step(policy(obs_b))
+            barrier()
+            tb = time.perf_counter()
+            n_env_steps_b = 0
+            for s_ in range(W, W + K):
+                if s_ % L == 0:
+                    obs_b = benv.reset()
+                live_before = int((~benv.done).sum())
+                obs_b, _, _, _ = benv.step(policy(obs_b))
+                n_env_steps_b += live_before
+            barrier()
+            tb = time.perf_counter() - tb
+            tb_t = torch.tensor([tb], dtype=torch.float64, device='cuda')
+            nb_t = torch.tensor([float(n_env_steps_b)], dtype=torch.float64, device='cuda')
+            if world > 1:
+                dist.all_reduce(tb_t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(nb_t, op=dist.ReduceOp.SUM)
+            batched = {'value': float(nb_t[0]) / float(tb_t[0]), 'unit': UNIT, 'ms_per_step': float(tb_t[0]) / K * 1e3,
+                       'native_placer_calls': benv.stats['placer_calls'], 'native_expansions': benv.stats['expansions'],
+                       'placement_cache_hits': benv.stats['placement_hits'],
+                       'what': 'BatchedRampJobPartitioningEnvironment.step(actions[B]) with host arrays: action mask + first-fit placement + '
+                               'template lookup on the host (cached), ramp_step_host, job-record read-back; env-steps of episodes that are not '
+                               'done are counted'}
+            benv.close()
+        except Exception as ex:
+            batched = {'error': repr(ex)[:300]}
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         la_ms = kt['total_ms']
@@ -513,7 +580,7 @@ def run_b200_arm(args, rank, world, local_rank):
             roofline['issue_slots']['frac'] = roofline['issue_slots']['achieved_warp_inst_per_s'] / roofline['issue_slots']['peak_warp_inst_per_s']
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': dict(workload_config(args, cfg, wl.templates, world, B),
                            l2='inputs larger than L2 are not needed: the lookahead kernel keeps its working set (template blob + per-lane '
@@ -531,6 +598,7 @@ def run_b200_arm(args, rank, world, local_rank):
             'cluster_steps': {'per_env_step': cluster_steps_per_env_step, 'value': value * cluster_steps_per_env_step,
                               'e2e': e2e_value * cluster_steps_per_env_step, 'unit': 'RampClusterEnvironment.step calls/s'},
             'memo_shared': shared,
+            'batched_env': batched,
         }
         if args.config == 'cfg3-resnet50-64w':
             line['python_reference'] = python_reference_note()

@@ -32,7 +32,6 @@ import numpy as np
 from . import engine as _engine
 from .expand import expand_template
 from .observation import PARAM_KEYS, _block_shapes_exist
-from .placer import first_fit_place_native
 from .synth import ForwardGraph
 from .template_builder import RampShape, original_job_totals
 
@@ -88,7 +87,7 @@ class BatchedRampJobPartitioningEnvironment:
                                             for a in range(1, self.max_partitions_per_op + 1)])
         # caches
         self._placement_cache: Dict[tuple, tuple] = {}       # (model, degree, busy words...) -> (template id | -1, mask words)
-        self._template_cache: Dict[tuple, int] = {}          # (model, degree, coords) -> template id
+        self._template_cache: Dict[tuple, int] = {}          # (model, degree, block geometry) -> template id
         self._t_mount: List[tuple] = []                      # per template id: (seq_time, part_op_mem, part_dep, flow, n_workers, n_channels)
         self._t_arrays = None
         self.stats = {'placer_calls': 0, 'expansions': 0, 'placement_hits': 0}
@@ -149,31 +148,56 @@ class BatchedRampJobPartitioningEnvironment:
         ok[:, 0] = True
         return ok
 
-    def _place(self, m: int, degree: int, busy_words: tuple):
-        """(template id or -1, server mask words) of model m at `degree` on a cluster whose busy servers are `busy_words`."""
-        key = (m, degree) + busy_words
-        hit = self._placement_cache.get(key)
-        if hit is not None:
-            self.stats['placement_hits'] += 1
-            return hit
+    def _c_graph(self, m: int):
+        """ramp_forward_graph_t of model m (built once; only the memory costs and the edges matter to the placer)."""
+        import ctypes as C
+        from .expand import _FwdGraph
         model = self.models[m]
-        busy = {}
-        for i, sv in enumerate(self._servers):
-            busy[sv] = bool((busy_words[i >> 6] >> (i & 63)) & 1)
-        free_mem = {sv: A100_MEMORY for sv in self._servers}
-        self.stats['placer_calls'] += 1
-        where = first_fit_place_native(model.n, model.mem, model.graph.edges, model.splits(degree), free_mem, busy,
-                                       (self.shape.c, self.shape.r, self.shape.s))
-        if where is None:                                          # the reference leaves the job out of the Action: blocked (RCE:914-919)
-            out = (-1, (0,) * self.n_words)
-        else:
-            coords = tuple(sorted(set(where.values())))
-            tkey = (m, degree, coords)
+        if not hasattr(model, '_cg'):
+            mem = np.ascontiguousarray(model.mem, dtype=np.float64)
+            zero = np.zeros(model.n, dtype=np.float64)
+            es = np.ascontiguousarray([u for (u, _) in model.graph.edges], dtype=np.int32)
+            ed = np.ascontiguousarray([v for (_, v) in model.graph.edges], dtype=np.int32)
+            model._cg_keep = (mem, zero, es, ed)
+            model._cg = _FwdGraph(model.n, len(model.graph.edges), zero.ctypes.data, zero.ctypes.data, mem.ctypes.data, zero.ctypes.data,
+                                  es.ctypes.data, ed.ctypes.data)
+        return model._cg
+
+    def _place_many(self, m: int, degree: int, busy_rows: np.ndarray):
+        """First-fit placement of model m at `degree` on every cluster state of busy_rows [n, n_words] (one native call), then the
+        template of each resulting block (cached).  Fills the placement cache."""
+        import ctypes as C
+        L = _engine.load_library()
+        L.ramp_first_fit_place_many.restype = C.c_int
+        L.ramp_first_fit_place_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        model = self.models[m]
+        n = len(busy_rows)
+        busy_rows = np.ascontiguousarray(busy_rows, dtype=np.uint64)
+        splits = np.ascontiguousarray(model.splits(degree), dtype=np.int32)
+        shape = (C.c_int32 * 3)(self.shape.c, self.shape.r, self.shape.s)
+        masks = np.zeros((n, self.n_words), dtype=np.uint64)
+        ok = np.zeros(n, dtype=np.uint8)
+        g = self._c_graph(m)
+        _engine._check(L.ramp_first_fit_place_many(C.byref(g), splits.ctypes.data, shape, A100_MEMORY, n, self.n_words,
+                                                  busy_rows.ctypes.data, masks.ctypes.data, ok.ctypes.data))
+        self.stats['placer_calls'] += n
+        for k in range(n):
+            key = (m, degree) + tuple(int(x) for x in busy_rows[k])
+            if not ok[k]:                                          # the reference leaves the job out of the Action: blocked (RCE:914-919)
+                self._placement_cache[key] = (-1, (0,) * self.n_words)
+                continue
+            words = tuple(int(x) for x in masks[k])
+            coords = [self._servers[i] for i in range(self.W) if (words[i >> 6] >> (i & 63)) & 1]
+            # the lowered job depends on the block only through which servers share a communication group / rack / server index
+            # (collective times, actions/utils.py:168-245; one-to-one transfers only test equality): blocks that are equal after an
+            # order-preserving relabelling of each coordinate axis give byte-identical jobs (tests/test_expand_native.py)
+            ranks = [{v: i for i, v in enumerate(sorted({c[ax] for c in coords}))} for ax in range(3)]
+            tkey = (m, degree, tuple((ranks[0][c[0]], ranks[1][c[1]], ranks[2][c[2]]) for c in coords))
             tid = self._template_cache.get(tkey)
             if tid is None:
                 self.stats['expansions'] += 1
                 lj = expand_template(model.graph, degree, self.shape, quantum=model.quantum,
-                                     num_training_steps=self.num_training_steps, model_id=m, run_times=self.run_times, coords=list(coords))
+                                     num_training_steps=self.num_training_steps, model_id=m, run_times=self.run_times, coords=coords)
                 tid = self.eng.register_template(lj)
                 self._template_cache[tkey] = tid
                 mt = lj.mount
@@ -181,13 +205,7 @@ class BatchedRampJobPartitioningEnvironment:
                     self._t_mount.append(None)
                 self._t_mount[tid] = (lj.seq_time, mt.part_op_mem, mt.part_dep_size, mt.flow_size, mt.n_mounted_workers, mt.n_mounted_channels)
                 self._t_arrays = None
-            words = [0] * self.n_words
-            for sv in coords:
-                i = self._server_index[sv]
-                words[i >> 6] |= (1 << (i & 63))
-            out = (tid, tuple(words))
-        self._placement_cache[key] = out
-        return out
+            self._placement_cache[key] = (tid, words)
 
     def _mount_arrays(self):
         if self._t_arrays is None:
@@ -226,8 +244,16 @@ class BatchedRampJobPartitioningEnvironment:
             inv = inv.reshape(-1)
             u_tid = np.empty(len(uniq), dtype=np.int32)
             u_words = np.zeros((len(uniq), self.n_words), dtype=np.uint64)
-            for k, row in enumerate(uniq):
-                t, words = self._place(int(row[0]), int(row[1]), tuple(int(x) for x in row[2:]))
+            rows = [tuple(int(x) for x in row) for row in uniq]
+            miss = [k for k, row in enumerate(rows) if row not in self._placement_cache]
+            self.stats['placement_hits'] += len(rows) - len(miss)
+            by_md = {}
+            for k in miss:
+                by_md.setdefault(rows[k][:2], []).append(k)
+            for (m_, d_), ks in by_md.items():
+                self._place_many(m_, d_, uniq[ks][:, 2:])
+            for k, row in enumerate(rows):
+                t, words = self._placement_cache[row]
                 u_tid[k] = t
                 u_words[k] = np.array(words, dtype=np.uint64)
             tid[sel] = u_tid[inv]

@@ -440,4 +440,35 @@ int ramp_first_fit_place(const ramp_forward_graph_t* g, const int32_t* splits, c
     return RAMP_OK;
 }
 
+
+// The same decision for MANY cluster states at once (the batched environment groups its episodes by occupancy pattern and asks
+// once per distinct pattern): busy_words[k] is a bit set over the servers (bit i = server i is busy; free servers hold no job, so
+// their worker's memory is empty: memory_capacity bytes free).  server_mask_out[k] receives the set of servers the job is put
+// on, ok_out[k] = 1, or ok_out[k] = 0 when the job cannot be placed there.
+int ramp_first_fit_place_many(const ramp_forward_graph_t* g, const int32_t* splits, const int32_t shape[3], double memory_capacity,
+                              int32_t n_states, int32_t n_words, const uint64_t* busy_words, uint64_t* server_mask_out, uint8_t* ok_out) {
+    if (!g || !splits || !shape || !busy_words || !server_mask_out || !ok_out || n_states < 0 || n_words < 1) return RAMP_ERR_BAD_ARG;
+    const int n_servers = shape[0] * shape[1] * shape[2];
+    if (n_servers > 64 * n_words) return RAMP_ERR_BAD_ARG;
+    int total = 0;
+    for (int i = 0; i < g->n_fwd; ++i) total += std::max(splits[i], 1);
+    std::vector<double> free_mem(n_servers, memory_capacity);
+    std::vector<uint8_t> busy(n_servers);
+    std::vector<int32_t> server_out(total), offset_out(g->n_fwd + 1);
+    ramp_cluster_state_t st{};
+    st.shape[0] = shape[0]; st.shape[1] = shape[1]; st.shape[2] = shape[2];
+    st.free_mem = free_mem.data(); st.busy = busy.data();
+    for (int32_t k = 0; k < n_states; ++k) {
+        const uint64_t* bw = busy_words + (size_t)k * n_words;
+        for (int i = 0; i < n_servers; ++i) busy[i] = (uint8_t)((bw[i >> 6] >> (i & 63)) & 1ull);
+        uint64_t* out = server_mask_out + (size_t)k * n_words;
+        for (int w = 0; w < n_words; ++w) out[w] = 0ull;
+        const int rc = ramp_first_fit_place(g, splits, &st, server_out.data(), offset_out.data());
+        if (rc < 0) return rc;
+        ok_out[k] = rc == RAMP_OK ? 1 : 0;
+        if (rc == RAMP_OK) for (int i = 0; i < total; ++i) out[server_out[i] >> 6] |= 1ull << (server_out[i] & 63);
+    }
+    return RAMP_OK;
+}
+
 }  // extern "C"

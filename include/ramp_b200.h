@@ -285,6 +285,11 @@ typedef struct {
 int ramp_first_fit_place(const ramp_forward_graph_t* graph, const int32_t* splits, const ramp_cluster_state_t* state,
                          int32_t* server_out, int32_t* offset_out);
 void ramp_free_expanded_job(ramp_lowered_job_t* job);
+/* ramp_first_fit_place for many cluster states in one call: busy_words[k] / server_mask_out[k] are bit sets over the servers
+ * (n_words x 64 bits each); ok_out[k] = 0 when the job cannot be placed on state k.  Free servers have memory_capacity bytes free
+ * (one job per worker, ramp_rules.py:6-39). */
+int ramp_first_fit_place_many(const ramp_forward_graph_t* graph, const int32_t* splits, const int32_t shape[3], double memory_capacity,
+                              int32_t n_states, int32_t n_words, const uint64_t* busy_words, uint64_t* server_mask_out, uint8_t* ok_out);
 
 /* ---- symmetry quotient of a lowered job (host-only; ddls_b200/csrc/ramp_quotient.cpp).  ramp_register_template applies it
  * by itself; it is exported so that tests can check it without a GPU.  The quotient job is what _run_lookahead

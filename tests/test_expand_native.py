@@ -104,3 +104,23 @@ def test_placer_plus_native_expansion_reproduce_reference_jobs_on_busy_clusters(
                 np.testing.assert_array_equal(np.asarray(getattr(mine, f)), np.asarray(getattr(ref, f)), err_msg=f'{name} tid {tid} {f}')
             checked += 1
     assert checked == 67
+
+
+def test_native_expansion_depends_on_the_block_only_through_its_geometry():
+    """Blocks that are equal after an order-preserving relabelling of each coordinate axis (communication group, rack, server)
+    give byte-identical lowered jobs -- what the batched environment's template cache keys on."""
+    g = synth.resnet_like_graph(n_blocks=2, stem=2, name='res2', seed=7, body_per_block=3)
+    shape = RampShape(4, 4, 4)
+    groups = [[[(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0)], [(2, 2, 1), (3, 2, 1), (2, 3, 1), (3, 3, 1)], [(0, 1, 3), (2, 1, 3), (0, 3, 3), (2, 3, 3)]],
+              [[(0, 0, 0), (0, 0, 1), (0, 0, 2), (0, 0, 3)], [(1, 2, 0), (1, 2, 1), (1, 2, 2), (1, 2, 3)]],
+              [[(0, 0, 0), (1, 1, 0)], [(2, 0, 3), (3, 2, 3)]]]
+    for blocks in groups:
+        first = None
+        for b in blocks:
+            t = expand_template(g, len(b), shape, run_times='reference', coords=b)
+            if first is None:
+                first = t
+                continue
+            for f in ARRAYS:
+                np.testing.assert_array_equal(np.asarray(getattr(t, f)), np.asarray(getattr(first, f)), err_msg=f)
+            assert t.mount == first.mount
