@@ -25,9 +25,18 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 must print ONE JSON line on stdout: NCCL's log (whatever NCCL_DEBUG level the caller asked for) goes to stderr
+# rank 0 must print ONE JSON line on stdout.  NCCL's log (whatever NCCL_DEBUG level the caller asked for) goes to stderr, and so
+# does anything a library printf()s to file descriptor 1 (NCCL prints its version banner there when NCCL_DEBUG is unset): the
+# real stdout is kept aside and only emit() writes to it.
 if not os.environ.get('NCCL_DEBUG_FILE'):
     os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = os.fdopen(os.dup(2), 'w', buffering=1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
 
 METRIC = 'env_steps_per_sec'
 UNIT = 'env-steps/s'
@@ -215,7 +224,7 @@ def run_reference_arm(args, rank, world):
                     cpu_baseline={'value': value, 'unit': UNIT, 'cores': cores['used'], 'kind': 'port', 'sample': port['sample'],
                                   'per_core': value / cores['used']},
                     e2e={'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     P = args.ref_procs or max(1, min(cores['used'], 32))
     warm = 1 if args.warmup > 0 else 0
@@ -247,7 +256,7 @@ def run_reference_arm(args, rank, world):
                                         f'imports and one warm-up step); unmodified reference from {results[0]["reference_root"]}',
                               'failed_processes': len(errors)},
                 e2e={'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def port_throughput(args, n_threads, budget_s=10.0):
@@ -605,7 +614,7 @@ def run_b200_arm(args, rank, world, local_rank):
             line['template_expansion'] = template_expansion_note()
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(args, wl)
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
