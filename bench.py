@@ -63,6 +63,8 @@ def parse_args():
     ap.add_argument('--ref-kind', default='auto', choices=['auto', 'reference', 'port'])
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --episodes (or the config batch) per GPU; strong: the config batch divided over the GPUs')
+    ap.add_argument('--gather-every', type=int, default=0,
+                    help='all-gather the episode metrics every this many steps (0 = once per scripted segment, i.e. per batch of rollouts)')
     ap.add_argument('--no-batched-env', action='store_true', help='skip the BatchedRampJobPartitioningEnvironment secondary figure')
     return ap.parse_args()
 
@@ -390,6 +392,7 @@ def run_b200_arm(args, rank, world, local_rank):
                 done_ev.record(side)
             gather_events[k] = done_ev
 
+    gather_every = args.gather_every or L       # one NCCL all-gather of episode metrics per batch of rollouts (north_star)
     memo_acc = {'lookups': 0, 'hits': 0, 'lookaheads': 0}
     memo_base = {'lookups': 0, 'hits': 0, 'lookaheads': 0}     # part of the current segment that belongs to the warm-up
 
@@ -406,7 +409,8 @@ def run_b200_arm(args, rank, world, local_rank):
                 fold_memo()
             eng.reset(arrivals)
         eng.step_device(on_dev[p].data_ptr(), True, stats_dev.data_ptr(), ncs_dev.data_ptr())
-        gather_metrics()
+        if (s + 1) % gather_every == 0:
+            gather_metrics()
 
     def host_step(s):
         p = s % L
@@ -416,7 +420,8 @@ def run_b200_arm(args, rank, world, local_rank):
         rc = eng._L.ramp_step_host(eng._h, pinned[p].data_ptr(), 1, stats_pinned.data_ptr(), None)
         if rc != 0:
             engine._check(rc)
-        gather_metrics()
+        if (s + 1) % gather_every == 0:
+            gather_metrics()
         return float(stats_pinned[0, engine.SS['step_end_time']])
 
     W, K = args.warmup, args.steps
@@ -594,7 +599,7 @@ def run_b200_arm(args, rank, world, local_rank):
             'config': dict(workload_config(args, cfg, wl.templates, world, B),
                            l2='inputs larger than L2 are not needed: the lookahead kernel keeps its working set (template blob + per-lane '
                               'lists) in shared memory; per step it writes %.1f MB of tick traces to HBM; no explicit flush' % _trace_mb(kt),
-                           parallelism=f'episodes sharded x{world}, one NCCL all-gather of episode metrics per step' if world > 1
+                           parallelism=f'episodes sharded x{world}, one NCCL all-gather of episode metrics every {gather_every} steps (per batch of rollouts), on a side stream' if world > 1
                                        else 'single GPU'),
             'e2e': {'value': e2e_value, 'unit': UNIT,
                     'h2d_bytes_per_step': int(B * engine.ACTION_DTYPE.itemsize + (arrivals.nbytes / L)),
