@@ -1,6 +1,9 @@
-"""Summarises an `ncu --set full` report of bench.py's lookahead launches into profiles/ncu_lookahead_summary.json
-(run HERE, on the report copied back in gpurun_out/):  python scripts/ncu_summary.py gpurun_out/prof_bench.ncu-rep "<what>"
-"""
+"""Summarises an `ncu --set full` report of bench.py's lookahead launches (run HERE, on the report copied back in gpurun_out/):
+
+    python scripts/ncu_summary.py gpurun_out/prof_bench.ncu-rep "<what>" [out.json] [lookaheads per launch]
+
+Writes profiles/ncu_lookahead_summary.json by default; round 2 writes profiles/r2_ncu_thread_summary.json, which bench.py reads for
+the STATIC `roofline.traffic` / `roofline.issue_slots` figures (labelled with this file as their source)."""
 import csv, json, subprocess, sys, os
 
 rep = sys.argv[1]
@@ -45,6 +48,13 @@ total_bytes = sum((l['dram_read_MB'] + l['dram_write_MB']) * 1e6 for l in launch
 n_steps = sum(1 for l in launches if 'cta' not in l['kernel']) or len(launches)
 out = {'_what': what, 'dram_bytes_per_launch': total_bytes / max(n_steps, 1), 'n_launches': len(launches), 'n_steps': n_steps,
        'launches': launches}
-path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'ncu_lookahead_summary.json')
+path = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'ncu_lookahead_summary.json')
+if len(sys.argv) > 4 and launches:
+    per = float(sys.argv[4])
+    thr = [l for l in launches if 'thread' in l['kernel']]
+    if thr:
+        # one warp carries 32 lookaheads: warp instructions x 32 / lookaheads = instructions per lookahead (thread-level stream)
+        out['warp_inst_per_lookahead'] = sum(l['inst'] for l in thr) * 32.0 / (per * len(thr))
+        out['lookaheads_per_launch'] = per
 json.dump(out, open(path, 'w'), indent=1)
 print('wrote', path, 'dram bytes per step', out['dram_bytes_per_launch'], 'over', n_steps, 'steps')
