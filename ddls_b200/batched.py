@@ -348,3 +348,196 @@ class BatchedRampJobPartitioningEnvironment:
 
     def close(self):
         self.eng.close()
+
+
+class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment):
+    """The same environment with the per-step decision and bookkeeping ON THE DEVICE (include/ramp_b200.h: ramp_env_*): first-fit
+    placement over host-enumerated candidate blocks, template lookup by (model, degree, block geometry), action
+    rows, reward, occupancy, dynamic observation features and action mask (8f-2) are kernels with one thread per episode; a step
+    is ``ramp_env_decide`` -> ``ramp_env_advance`` and, through ``step``, one read-back of the outputs.  ``device_buffers()`` gives
+    the raw device pointers for a policy that lives on the GPU (then nothing crosses PCIe).  The host is asked only for what the
+    tables cannot decide: jobs whose ops take different numbers of sub-ops, and the first use of a block geometry (it lowers the
+    job natively, registers it and fills the table)."""
+
+    def __init__(self, *args, **kw):
+        import ctypes as C
+        super().__init__(*args, **kw)
+        from .placer import _block_shapes, _factor_pairs, _get_block
+        D, nw, shape = self.max_partitions_per_op, self.n_words, (self.shape.c, self.shape.r, self.shape.s)
+        self._geom_index: Dict[tuple, int] = {}
+        cand_ptr, cand_mask, cand_geom = [0, 0], [], []
+        for d in range(1, D + 1):
+            if d == 1 or d % 2 == 0:
+                shapes = _block_shapes(_factor_pairs(d), shape) + [(d, d, -1), (d, 1, 1)]          # utils.py:333-383, 491-530
+                for bs in shapes:                                                                   # utils.py:394-443
+                    I, J_, K = (shape[0] - bs[0]) + 1, (shape[1] - bs[1]) + 1, (shape[2] - bs[2]) + 1
+                    if I <= 0 or J_ <= 0 or K <= 0:
+                        continue
+                    for i in range(I):
+                        for j in range(J_):
+                            for k in range(K):
+                                block = _get_block(bs[0], bs[1], bs[2], shape, (i, j, k))
+                                if any(sv not in self._server_index for sv in block) or len(set(block)) != d:
+                                    continue                                                         # check_block fails on it
+                                words = [0] * nw
+                                for sv in block:
+                                    ix = self._server_index[sv]
+                                    words[ix >> 6] |= (1 << (ix & 63))
+                                cand_mask.append(words)
+                                cand_geom.append(self._geometry(sorted(block)))
+            cand_ptr.append(len(cand_mask))
+        self._n_geoms = max(len(self._geom_index), 1)
+        M = len(self.models)
+        uniform = np.zeros((M, D + 1), dtype=np.uint8)
+        for m, model in enumerate(self.models):
+            sources = set(range(1, model.n + 1)) - {v for (_, v) in model.graph.edges}
+            for d in range(1, D + 1):
+                if (d == 1 or d % 2 == 0) and all(s == d for s in model.splits(d)) and len(sources) == 1 \
+                        and sum(model.mem) <= d * A100_MEMORY:
+                    uniform[m, d] = 1
+        self._uniform = uniform
+        P = self.jobs_params()
+        mp = np.array([[mo.seq_time, 2.0 * mo.n, 2.0 * len(mo.graph.edges) + 1, mo.op_mem_total, mo.dep_size_total] for mo in self.models],
+                      dtype=np.float64)
+        keep = dict(cand_ptr=np.ascontiguousarray(cand_ptr, dtype=np.int32),
+                    cand_mask=np.ascontiguousarray(cand_mask, dtype=np.uint64).reshape(-1, nw),
+                    cand_geom=np.ascontiguousarray(cand_geom, dtype=np.int32), uniform=np.ascontiguousarray(uniform),
+                    shape_ok=np.ascontiguousarray(self._shape_ok, dtype=np.uint8), mp=np.ascontiguousarray(mp),
+                    jp=np.ascontiguousarray(P, dtype=np.float64).reshape(8, 2))
+
+        class _Cfg(C.Structure):
+            _fields_ = [('shape', C.c_int32 * 3), ('n_models', C.c_int32), ('max_degree', C.c_int32), ('n_geoms', C.c_int32),
+                        ('jobs_per_episode', C.c_int32), ('n_words', C.c_int32), ('apply_action_mask', C.c_int32),
+                        ('num_training_steps', C.c_int32), ('fail_reward', C.c_double), ('success_reward', C.c_double),
+                        ('cand_ptr', C.c_void_p), ('cand_mask', C.c_void_p), ('cand_geom', C.c_void_p), ('uniform', C.c_void_p),
+                        ('shape_ok', C.c_void_p), ('model_params', C.c_void_p), ('jobs_params', C.c_void_p)]
+        cfg = _Cfg((C.c_int32 * 3)(*shape), M, D, self._n_geoms, self.J, nw, 1 if self.apply_action_mask else 0, self.num_training_steps,
+                   float(self.fail_reward), float(self.success_reward), keep['cand_ptr'].ctypes.data, keep['cand_mask'].ctypes.data,
+                   keep['cand_geom'].ctypes.data, keep['uniform'].ctypes.data, keep['shape_ok'].ctypes.data, keep['mp'].ctypes.data,
+                   keep['jp'].ctypes.data)
+        L = self.eng._L
+        for name in ('ramp_env_create', 'ramp_env_set_template', 'ramp_env_reset', 'ramp_env_buffers', 'ramp_env_decide', 'ramp_env_patch',
+                     'ramp_env_advance', 'ramp_env_read'):
+            getattr(L, name).restype = C.c_int
+        L.ramp_env_create.argtypes = [C.c_void_p, C.c_void_p]
+        L.ramp_env_set_template.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.ramp_env_reset.argtypes = [C.c_void_p] * 5
+        L.ramp_env_buffers.argtypes = [C.c_void_p, C.c_void_p]
+        L.ramp_env_decide.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ramp_env_patch.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ramp_env_advance.argtypes = [C.c_void_p]
+        L.ramp_env_read.argtypes = [C.c_void_p] * 6
+        _engine._check(L.ramp_env_create(self.eng._h, C.byref(cfg)))
+        self._table_set = set()
+        B, A = self.B, D + 1
+        self._reward = np.zeros(B, dtype=np.float64)
+        self._done = np.zeros(B, dtype=np.uint8)
+        self._qmodel = np.zeros(B, dtype=np.int32)
+        self._obs_dyn = np.zeros((B, 11), dtype=np.float32)
+        self._mask = np.zeros((B, A), dtype=np.uint8)
+        self._need = np.zeros(B, dtype=np.int32)
+
+    def _geometry(self, coords):
+        ranks = [{v: i for i, v in enumerate(sorted({c[ax] for c in coords}))} for ax in range(3)]
+        key = tuple((ranks[0][c[0]], ranks[1][c[1]], ranks[2][c[2]]) for c in coords)
+        return self._geom_index.setdefault(key, len(self._geom_index))
+
+    def device_buffers(self):
+        import ctypes as C
+
+        class _Buf(C.Structure):
+            _fields_ = [(n, C.c_void_p) for n in ('actions', 'reward', 'done', 'queued_model', 'obs_dynamic', 'action_mask', 'busy', 'template_id')]
+        b = _Buf()
+        _engine._check(self.eng._L.ramp_env_buffers(self.eng._h, C.byref(b)))
+        return {n: getattr(b, n) for n, _ in _Buf._fields_}
+
+    @property
+    def queued(self):
+        return self.eng.episode_state()[:, EP['queued_job']].astype(np.int64)
+
+    @property
+    def last_stats(self):
+        import ctypes as C
+        out = np.zeros((self.B, _engine.STEP_STATS_LEN), dtype=np.float64)
+        self.eng._L.ramp_get_last_step_stats.restype = C.c_int
+        self.eng._L.ramp_get_last_step_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _engine._check(self.eng._L.ramp_get_last_step_stats(self.eng._h, out.ctypes.data, None))
+        return out
+
+    def _read(self):
+        _engine._check(self.eng._L.ramp_env_read(self.eng._h, self._reward.ctypes.data, self._done.ctypes.data, self._qmodel.ctypes.data,
+                                                 self._obs_dyn.ctypes.data, self._mask.ctypes.data))
+        self.done = self._done.astype(bool)
+        return {'model': self._qmodel.copy(), 'graph_features_dynamic': self._obs_dyn.copy(), 'action_set': self.action_set,
+                'action_mask': self._mask.astype(np.int16), 'done': self.done.copy()}
+
+    def reset(self):
+        self.arrivals = self._draw_streams()
+        macc = self.macc_override if self.macc_override is not None else np.full((self.B, self.J), np.nan)
+        model_of = np.ascontiguousarray(self.model_of, dtype=np.int32)
+        frac = np.ascontiguousarray(self.frac, dtype=np.float64)
+        macc = np.ascontiguousarray(macc, dtype=np.float64)
+        arr = np.ascontiguousarray(self.arrivals, dtype=_engine.ARRIVAL_DTYPE)
+        self._keep_reset = (model_of, frac, macc, arr)
+        _engine._check(self.eng._L.ramp_env_reset(self.eng._h, model_of.ctypes.data, frac.ctypes.data, macc.ctypes.data, arr.ctypes.data))
+        self.eng.n_jobs = self.J
+        self.step_counter = 0
+        return self._read()
+
+    def step(self, actions=None):
+        """actions: int array [B] on the host, or None when a device-resident policy already wrote ramp_env_buffers_t.actions."""
+        import ctypes as C
+        L, h = self.eng._L, self.eng._h
+        n_need = C.c_int32(0)
+        a_ptr = None
+        if actions is not None:
+            actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.B)
+            a_ptr = actions.ctypes.data
+        _engine._check(L.ramp_env_decide(h, a_ptr, C.byref(n_need), self._need.ctypes.data))
+        if n_need.value > 0:
+            self._decide_on_host(self._need[:n_need.value].copy(), actions)
+        _engine._check(L.ramp_env_advance(h))
+        obs = self._read()
+        self.eng.check_status()
+        self.step_counter += 1
+        return obs, self._reward.copy(), self.done.copy(), {}
+
+    def _decide_on_host(self, episodes, actions):
+        """Episodes the device tables could not decide: full native placer + expansion, then patch the rows (and remember the
+        template of the geometry so that the device decides it next time)."""
+        import ctypes as C
+        L, h = self.eng._L, self.eng._h
+        nw = self.n_words
+        busy = np.zeros((self.B, nw), dtype=np.uint64)
+        dev_actions = np.zeros(self.B, dtype=np.int32)
+        L.ramp_env_read_state.restype = C.c_int
+        L.ramp_env_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _engine._check(L.ramp_env_read_state(h, busy.ctypes.data, dev_actions.ctypes.data))
+        if actions is None:
+            actions = dev_actions
+        ep = self.eng.episode_state()
+        q = ep[:, EP['queued_job']].astype(np.int64)
+        keys = {}
+        for b in episodes:
+            keys.setdefault((int(self.model_of[b, q[b]]), int(actions[b])) + tuple(int(x) for x in busy[b]), []).append(int(b))
+        by_md = {}
+        for key in keys:
+            if key not in self._placement_cache:
+                by_md.setdefault(key[:2], []).append(key)
+        for (m, d), ks in by_md.items():
+            self._place_many(m, d, np.array([k[2:] for k in ks], dtype=np.uint64).reshape(-1, nw))
+        mounts = self._t_mount
+        for key, bs in keys.items():
+            tid, words = self._placement_cache[key]
+            mask = np.array(words, dtype=np.uint64)
+            mt = np.array(mounts[tid] if tid >= 0 else (0.0,) * 6, dtype=np.float64)
+            m, d = key[0], key[1]
+            if tid >= 0 and self._uniform[m, d]:
+                coords = [self._servers[i] for i in range(self.W) if (words[i >> 6] >> (i & 63)) & 1]
+                gkey = self._geometry(coords)
+                if gkey < self._n_geoms and (m, d, gkey) not in self._table_set:
+                    _engine._check(L.ramp_env_set_template(h, m, d, gkey, tid, mt.ctypes.data))
+                    self._table_set.add((m, d, gkey))
+            for b in bs:
+                _engine._check(L.ramp_env_patch(h, b, tid, mask.ctypes.data, mt.ctypes.data))
+

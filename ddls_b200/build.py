@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, 'libramp_b200.so')
 SOURCES = [os.path.join(HERE, 'csrc', 'ramp_engine.cu'), os.path.join(HERE, 'csrc', 'ramp_expand.cpp'),
            os.path.join(HERE, 'csrc', 'ramp_quotient.cpp')]
 DEPS = SOURCES + [os.path.join(HERE, 'csrc', 'ramp_kernels.cuh'), os.path.join(HERE, 'csrc', 'ramp_lookahead_cta.cuh'),
+                  os.path.join(HERE, 'csrc', 'ramp_lookahead_thread.cuh'), os.path.join(HERE, 'csrc', 'ramp_env.cuh'),
                   os.path.join(os.path.dirname(HERE), 'include', 'ramp_b200.h')]
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',

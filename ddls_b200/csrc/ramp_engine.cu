@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ramp_kernels.cuh"
+#include "ramp_env.cuh"
 
 using namespace ramp;
 
@@ -156,6 +157,11 @@ struct ramp_engine {
     int32_t* d_tbase = nullptr;
     int32_t* d_rank = nullptr;           // [B]
     TemplateHints* d_hints = nullptr;    // [max_templates]
+    // device-resident rollouts (ramp_env_*)
+    bool has_env = false;
+    EnvDev env{};
+    std::vector<void*> env_allocs;
+    int32_t* env_h_need = nullptr;       // pinned: [0] = count
     // standalone lookahead buffers
     WorkItem* sa_chunk_items = nullptr;
     ChunkDesc* sa_chunks = nullptr;
@@ -600,6 +606,8 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     for (auto& t : e->templates) { cudaFree(t.blob); cudaFree(t.res_blob); }
+    for (void* pa : e->env_allocs) cudaFree(pa);
+    if (e->env_h_need) cudaFreeHost(e->env_h_need);
     cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank); cudaFree(e->d_hints);
     cudaFree(e->d_res_scratch); cudaFree(e->sa_chunk_items); cudaFree(e->sa_chunks);
     cudaFree(e->d_templates); cudaFree(e->d_memo_keys); cudaFree(e->d_memo_vals); cudaFree(e->d_memo_keys2);
@@ -1204,6 +1212,204 @@ int ramp_get_quotient_bytes(ramp_engine_t* e, int64_t* quotient_bytes) {
     CUDA_TRY(cudaMemcpy(&s, e->d_stats, sizeof(MemoStats), cudaMemcpyDeviceToHost));
     *quotient_bytes = (int64_t)(s.quotient_bytes - e->la_qbytes_base);
     return RAMP_OK;
+}
+
+
+// ---- device-resident rollouts ---------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+template <class T> int env_upload(ramp_engine* e, T** dst, const T* src, size_t n) {
+    CUDA_TRY(cudaMalloc(dst, sizeof(T) * std::max<size_t>(n, 1)));
+    e->env_allocs.push_back(*dst);
+    if (src && n) CUDA_TRY(cudaMemcpy(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    else CUDA_TRY(cudaMemset(*dst, 0, sizeof(T) * std::max<size_t>(n, 1)));
+    return RAMP_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int ramp_env_create(ramp_engine_t* e, const ramp_env_config_t* c) {
+    if (!e || !c) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    if (e->has_env) return set_error(RAMP_ERR_BAD_ARG, "the engine already has an environment");
+    const int B = e->cfg.n_episodes, J = c->jobs_per_episode, M = c->n_models, D = c->max_degree, G = c->n_geoms, nw = c->n_words;
+    const int n_workers = c->shape[0] * c->shape[1] * c->shape[2];
+    if (J != e->cfg.max_jobs) return set_error(RAMP_ERR_BAD_ARG, "jobs_per_episode %d != the engine's max_jobs %d", J, e->cfg.max_jobs);
+    if (n_workers != e->cfg.n_cluster_workers || nw * 64 < n_workers || M < 1 || D < 1 || G < 1)
+        return set_error(RAMP_ERR_BAD_ARG, "bad environment shape");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    EnvDev& v = e->env;
+    v.B = B; v.J = J; v.n_words = nw; v.n_models = M; v.max_degree = D; v.n_geoms = G; v.n_workers = n_workers;
+    v.apply_mask = c->apply_action_mask; v.fail_reward = c->fail_reward; v.success_reward = c->success_reward;
+    v.num_training_steps = (double)c->num_training_steps;
+    const int n_cand = c->cand_ptr[D + 1];
+    int rc;
+    int32_t* cand_ptr; unsigned long long* cand_mask; int32_t* cand_geom; uint8_t* uniform; uint8_t* shape_ok; double* mp; double* jp;
+    if ((rc = env_upload(e, &cand_ptr, c->cand_ptr, (size_t)D + 2))) return rc;
+    if ((rc = env_upload(e, &cand_mask, (const unsigned long long*)c->cand_mask, (size_t)n_cand * nw))) return rc;
+    if ((rc = env_upload(e, &cand_geom, c->cand_geom, (size_t)n_cand))) return rc;
+    if ((rc = env_upload(e, &uniform, c->uniform, (size_t)M * (D + 1)))) return rc;
+    if ((rc = env_upload(e, &shape_ok, c->shape_ok, (size_t)D + 1))) return rc;
+    if ((rc = env_upload(e, &mp, c->model_params, (size_t)M * 5))) return rc;
+    if ((rc = env_upload(e, &jp, c->jobs_params, (size_t)16))) return rc;
+    v.cand_ptr = cand_ptr; v.cand_mask = cand_mask; v.cand_geom = cand_geom; v.uniform = uniform; v.shape_ok = shape_ok;
+    v.model_params = mp; v.jobs_params = jp;
+    std::vector<int32_t> minus1((size_t)M * (D + 1) * G, -1);
+    if ((rc = env_upload(e, &v.tmpl_of, minus1.data(), minus1.size()))) return rc;
+    if ((rc = env_upload<double>(e, &v.tmpl_mount, nullptr, (size_t)e->cfg.max_templates * 6))) return rc;
+    int32_t* model_of; double* frac; double* macc;
+    if ((rc = env_upload<int32_t>(e, &model_of, nullptr, (size_t)B * J))) return rc;
+    if ((rc = env_upload<double>(e, &frac, nullptr, (size_t)B * J))) return rc;
+    if ((rc = env_upload<double>(e, &macc, nullptr, (size_t)B * J))) return rc;
+    v.model_of = model_of; v.frac = frac; v.macc = macc;
+    if ((rc = env_upload<unsigned long long>(e, &v.busy, nullptr, (size_t)B * nw))) return rc;
+    if ((rc = env_upload<unsigned long long>(e, &v.job_mask, nullptr, (size_t)B * J * nw))) return rc;
+    if ((rc = env_upload<unsigned long long>(e, &v.placed, nullptr, (size_t)B * nw))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.tid, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.decided_job, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.actions, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<double>(e, &v.reward, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<uint8_t>(e, &v.done, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.queued_model, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<float>(e, &v.obs_dyn, nullptr, (size_t)B * 11))) return rc;
+    if ((rc = env_upload<uint8_t>(e, &v.action_mask, nullptr, (size_t)B * (D + 1)))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.need_host, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.n_need_host, nullptr, 1))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.err, nullptr, 1))) return rc;
+    CUDA_TRY(cudaMallocHost(&e->env_h_need, sizeof(int32_t) * 2));
+    e->has_env = true;
+    return RAMP_OK;
+}
+
+int ramp_env_set_template(ramp_engine_t* e, int32_t model, int32_t degree, int32_t geom, int32_t template_id, const double mount[6]) {
+    if (!e || !e->has_env || !mount) return set_error(RAMP_ERR_BAD_ARG, "no environment");
+    const EnvDev& v = e->env;
+    if (model < 0 || model >= v.n_models || degree < 0 || degree > v.max_degree || geom < 0 || geom >= v.n_geoms ||
+        template_id < 0 || template_id >= (int32_t)e->templates.size())
+        return set_error(RAMP_ERR_BAD_ARG, "bad template table entry (model %d degree %d geometry %d template %d)", model, degree, geom, template_id);
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMemcpy(v.tmpl_of + ((size_t)model * (v.max_degree + 1) + degree) * v.n_geoms + geom, &template_id, sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(v.tmpl_mount + (size_t)template_id * 6, mount, sizeof(double) * 6, cudaMemcpyHostToDevice));
+    return RAMP_OK;
+}
+
+int ramp_env_reset(ramp_engine_t* e, const int32_t* model_of, const double* frac, const double* macc, const ramp_arrival_t* arrivals) {
+    if (!e || !e->has_env || !model_of || !frac || !macc || !arrivals) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    EnvDev& v = e->env;
+    const size_t n = (size_t)v.B * v.J;
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync((void*)v.model_of, model_of, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync((void*)v.frac, frac, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync((void*)v.macc, macc, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemsetAsync(v.job_mask, 0, sizeof(unsigned long long) * n * v.n_words, e->stream));
+    CUDA_TRY(cudaMemsetAsync(v.done, 0, (size_t)v.B, e->stream));
+    CUDA_TRY(cudaMemsetAsync(v.err, 0, sizeof(int32_t), e->stream));
+    int rc = ramp_reset(e, arrivals, v.J);
+    if (rc != RAMP_OK) return rc;
+    ramp_env_update_kernel<<<(v.B + 127) / 128, 128, 0, e->stream>>>(v, e->ep, nullptr, 1);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RAMP_OK;
+}
+
+int ramp_env_buffers(ramp_engine_t* e, ramp_env_buffers_t* out) {
+    if (!e || !e->has_env || !out) return set_error(RAMP_ERR_BAD_ARG, "no environment");
+    const EnvDev& v = e->env;
+    out->actions = v.actions; out->reward = v.reward; out->done = v.done; out->queued_model = v.queued_model;
+    out->obs_dynamic = v.obs_dyn; out->action_mask = v.action_mask; out->busy = (uint64_t*)v.busy; out->template_id = v.tid;
+    return RAMP_OK;
+}
+
+int ramp_env_decide(ramp_engine_t* e, const int32_t* actions, int32_t* n_need_host_out, int32_t* need_host_out) {
+    if (!e || !e->has_env) return set_error(RAMP_ERR_BAD_ARG, "no environment");
+    EnvDev& v = e->env;
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = e->stream;
+    if (actions) CUDA_TRY(cudaMemcpyAsync(v.actions, actions, sizeof(int32_t) * v.B, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(v.n_need_host, 0, sizeof(int32_t), st));
+    ramp_env_decide_kernel<<<(v.B + 127) / 128, 128, 0, st>>>(v, e->ep, e->d_actions);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (n_need_host_out) {
+        CUDA_TRY(cudaMemcpyAsync(e->env_h_need, v.n_need_host, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(e->env_h_need + 1, v.err, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (e->env_h_need[1] != 0) {
+            CUDA_TRY(cudaMemset(v.err, 0, sizeof(int32_t)));
+            return set_error(RAMP_ERR_BAD_ARG, "episode %d: the action is invalid given its action mask (RJPE:314-319)", e->env_h_need[1] - 1);
+        }
+        *n_need_host_out = e->env_h_need[0];
+        if (need_host_out && e->env_h_need[0] > 0)
+            CUDA_TRY(cudaMemcpy(need_host_out, v.need_host, sizeof(int32_t) * e->env_h_need[0], cudaMemcpyDeviceToHost));
+    }
+    return RAMP_OK;
+}
+
+int ramp_env_patch(ramp_engine_t* e, int32_t episode, int32_t template_id, const uint64_t* server_mask, const double mount[6]) {
+    if (!e || !e->has_env || !server_mask || !mount) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    EnvDev& v = e->env;
+    if (episode < 0 || episode >= v.B || template_id >= (int32_t)e->templates.size()) return set_error(RAMP_ERR_BAD_ARG, "bad patch");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    int32_t q = -1;
+    CUDA_TRY(cudaMemcpy(&q, v.decided_job + episode, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    ramp_action_t row{};
+    row.template_id = template_id;
+    if (template_id >= 0 && q >= 0) {
+        double fr = 0.0, ov = 0.0;
+        CUDA_TRY(cudaMemcpy(&fr, v.frac + (size_t)episode * v.J + q, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&ov, v.macc + (size_t)episode * v.J + q, sizeof(double), cudaMemcpyDeviceToHost));
+        row.max_acceptable_jct = std::isnan(ov) ? fr * mount[0] : ov;
+        row.part_op_mem = mount[1]; row.part_dep_size = mount[2]; row.flow_size = mount[3];
+        row.n_mounted_workers = (int32_t)mount[4]; row.n_mounted_channels = (int32_t)mount[5];
+    } else {
+        row.template_id = -1;
+    }
+    CUDA_TRY(cudaMemcpy(e->d_actions + episode, &row, sizeof(row), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(v.tid + episode, &row.template_id, sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(v.placed + (size_t)episode * v.n_words, server_mask, sizeof(uint64_t) * v.n_words, cudaMemcpyHostToDevice));
+    return RAMP_OK;
+}
+
+int ramp_env_advance(ramp_engine_t* e) {
+    if (!e || !e->has_env) return set_error(RAMP_ERR_BAD_ARG, "no environment");
+    EnvDev& v = e->env;
+    int rc = ramp_step_device(e, e->d_actions, 1, e->d_step_stats, e->d_n_cluster_steps);
+    if (rc != RAMP_OK) return rc;
+    ramp_env_update_kernel<<<(v.B + 127) / 128, 128, 0, e->stream>>>(v, e->ep, e->d_n_cluster_steps, 0);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return RAMP_OK;
+}
+
+int ramp_env_read(ramp_engine_t* e, double* reward, uint8_t* done, int32_t* queued_model, float* obs_dynamic, uint8_t* action_mask) {
+    if (!e || !e->has_env) return set_error(RAMP_ERR_BAD_ARG, "no environment");
+    const EnvDev& v = e->env;
+    cudaStream_t st = e->stream;
+    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, v.reward, sizeof(double) * v.B, cudaMemcpyDeviceToHost, st));
+    if (done) CUDA_TRY(cudaMemcpyAsync(done, v.done, (size_t)v.B, cudaMemcpyDeviceToHost, st));
+    if (queued_model) CUDA_TRY(cudaMemcpyAsync(queued_model, v.queued_model, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, st));
+    if (obs_dynamic) CUDA_TRY(cudaMemcpyAsync(obs_dynamic, v.obs_dyn, sizeof(float) * 11 * v.B, cudaMemcpyDeviceToHost, st));
+    if (action_mask) CUDA_TRY(cudaMemcpyAsync(action_mask, v.action_mask, (size_t)v.B * (v.max_degree + 1), cudaMemcpyDeviceToHost, st));
+    return ramp_sync(e);
+}
+
+
+int ramp_get_last_step_stats(ramp_engine_t* e, double* stats_out, int32_t* n_cluster_steps_out) {
+    if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");
+    const int B = e->cfg.n_episodes;
+    if (stats_out) CUDA_TRY(cudaMemcpyAsync(stats_out, e->d_step_stats, sizeof(double) * RAMP_STEP_STATS_LEN * B, cudaMemcpyDeviceToHost, e->stream));
+    if (n_cluster_steps_out) CUDA_TRY(cudaMemcpyAsync(n_cluster_steps_out, e->d_n_cluster_steps, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, e->stream));
+    return ramp_sync(e);
+}
+
+
+int ramp_env_read_state(ramp_engine_t* e, uint64_t* busy_out, int32_t* actions_out) {
+    if (!e || !e->has_env) return set_error(RAMP_ERR_BAD_ARG, "no environment");
+    const EnvDev& v = e->env;
+    if (busy_out) CUDA_TRY(cudaMemcpyAsync(busy_out, v.busy, sizeof(uint64_t) * (size_t)v.B * v.n_words, cudaMemcpyDeviceToHost, e->stream));
+    if (actions_out) CUDA_TRY(cudaMemcpyAsync(actions_out, v.actions, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, e->stream));
+    return ramp_sync(e);
 }
 
 }  // extern "C"

@@ -322,6 +322,62 @@ typedef struct {
 int ramp_quotient_template(const ramp_lowered_job_t* job, ramp_quotient_t* out);
 void ramp_free_quotient(ramp_quotient_t* q);
 
+
+/* ---- device-resident rollouts (SURVEY.md 8f-2 / 8f-4 on the device, 8g): one RampJobPartitioningEnvironment.step for every
+ * episode without the host in the loop.  Per episode the action is the maximum partition degree of the queued job
+ * (RJPE:300-343).  ramp_env_decide places the job with the reference's first-fit rule (agents/placers/utils.py:394-443, 532-582:
+ * the first free block in the (block shape, origin) order the host enumerated into `cand_*`), looks the lowered job up by
+ * (model, degree, block geometry) and writes the engine's action rows; ramp_env_advance runs the batched cluster step with the
+ * RJPE:394-395 loop fused and then, per episode, the reward (rewards/job_acceptance.py), the occupancy of the cluster, and the
+ * dynamic observation features + action mask of the next queued job (observations/...observation.py:80-131, 358-498).
+ * Episodes the tables cannot decide (ops of one job split different numbers of times, a block geometry whose template is not
+ * registered yet) are listed for the host, which patches their rows before ramp_env_advance. ---- */
+typedef struct {
+    int32_t shape[3];             /* communication groups, racks per group, servers per rack                       */
+    int32_t n_models, max_degree, n_geoms, jobs_per_episode, n_words;   /* n_words = ceil(servers / 64)             */
+    int32_t apply_action_mask;    /* 1: an invalid action is an error (RJPE:317-319); 0: it becomes action 0       */
+    int32_t num_training_steps;
+    double  fail_reward, success_reward;
+    const int32_t*  cand_ptr;     /* [max_degree + 2] candidates of degree d are [cand_ptr[d], cand_ptr[d + 1])    */
+    const uint64_t* cand_mask;    /* [n_cand][n_words] servers of the block (bit set)                              */
+    const int32_t*  cand_geom;    /* [n_cand] geometry index of the block (what the lowered job depends on)        */
+    const uint8_t*  uniform;      /* [n_models][max_degree + 1] 1: every op of the model takes `degree` sub-ops and the job fits
+                                     the block's memory, so placing it is one first-fit search                    */
+    const uint8_t*  shape_ok;     /* [max_degree + 1] a RAMP-symmetric block shape exists (action mask)            */
+    const double*   model_params; /* [n_models][5] sequential completion time, #ops, #deps, op memory, dep size    */
+    const double*   jobs_params;  /* [8][2] (min, max) of JobsGenerator.jobs_params in observation.PARAM_KEYS order */
+} ramp_env_config_t;
+
+/* device buffers of the environment (valid until the engine is destroyed): what a device-resident policy reads and writes */
+typedef struct {
+    int32_t*  actions;            /* [B] in: max partition degree chosen for the queued job (0 = do not place)      */
+    double*   reward;             /* [B] out                                                                        */
+    uint8_t*  done;               /* [B] out                                                                        */
+    int32_t*  queued_model;       /* [B] out: model of the queued job (-1 none)                                     */
+    float*    obs_dynamic;        /* [B][11] out: graph features that change per job / cluster state                */
+    uint8_t*  action_mask;        /* [B][max_degree + 1] out                                                        */
+    uint64_t* busy;               /* [B][n_words] occupancy of the cluster                                          */
+    int32_t*  template_id;        /* [B] template the decision mounted (-1 none)                                    */
+} ramp_env_buffers_t;
+
+int ramp_env_create(ramp_engine_t* eng, const ramp_env_config_t* cfg);
+int ramp_env_set_template(ramp_engine_t* eng, int32_t model, int32_t degree, int32_t geom, int32_t template_id, const double mount[6]);
+/* model_of / frac / max_acceptable_jct (NaN = frac x sequential time): HOST [n_episodes][jobs_per_episode]; arrivals as ramp_reset */
+int ramp_env_reset(ramp_engine_t* eng, const int32_t* model_of, const double* frac, const double* max_acceptable_jct,
+                   const ramp_arrival_t* arrivals);
+int ramp_env_buffers(ramp_engine_t* eng, ramp_env_buffers_t* out);
+/* actions: HOST [n_episodes] (copied) or NULL (already in ramp_env_buffers_t.actions).  need_host_out: HOST [n_episodes] list of
+ * episodes the tables could not decide, n_need_host_out their number (pass NULL for both when `uniform` covers every model). */
+int ramp_env_decide(ramp_engine_t* eng, const int32_t* actions, int32_t* n_need_host_out, int32_t* need_host_out);
+int ramp_env_patch(ramp_engine_t* eng, int32_t episode, int32_t template_id, const uint64_t* server_mask, const double mount[6]);
+int ramp_env_advance(ramp_engine_t* eng);
+/* HOST copies of the outputs (any may be NULL) */
+/* step statistics / cluster-step counts of the last ramp_env_advance (the engine's own buffers): HOST [n_episodes][RAMP_STEP_STATS_LEN], [n_episodes] */
+int ramp_get_last_step_stats(ramp_engine_t* eng, double* stats_out, int32_t* n_cluster_steps_out);
+/* HOST copies of the occupancy [n_episodes][n_words] and of the actions the device holds (either may be NULL) */
+int ramp_env_read_state(ramp_engine_t* eng, uint64_t* busy_out, int32_t* actions_out);
+int ramp_env_read(ramp_engine_t* eng, double* reward, uint8_t* done, int32_t* queued_model, float* obs_dynamic, uint8_t* action_mask);
+
 #ifdef __cplusplus
 }
 #endif
