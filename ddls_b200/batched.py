@@ -359,12 +359,13 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
     tables cannot decide: jobs whose ops take different numbers of sub-ops, and the first use of a block geometry (it lowers the
     job natively, registers it and fills the table)."""
 
-    def __init__(self, *args, **kw):
+    def __init__(self, *args, prewarm: bool = False, **kw):
         import ctypes as C
         super().__init__(*args, **kw)
         from .placer import _block_shapes, _factor_pairs, _get_block
         D, nw, shape = self.max_partitions_per_op, self.n_words, (self.shape.c, self.shape.r, self.shape.s)
         self._geom_index: Dict[tuple, int] = {}
+        self._geom_example: Dict[tuple, list] = {}          # (degree, geometry index) -> one block with that geometry
         cand_ptr, cand_mask, cand_geom = [0, 0], [], []
         for d in range(1, D + 1):
             if d == 1 or d % 2 == 0:
@@ -384,7 +385,9 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
                                     ix = self._server_index[sv]
                                     words[ix >> 6] |= (1 << (ix & 63))
                                 cand_mask.append(words)
-                                cand_geom.append(self._geometry(sorted(block)))
+                                gi = self._geometry(sorted(block))
+                                cand_geom.append(gi)
+                                self._geom_example.setdefault((d, gi), sorted(block))
             cand_ptr.append(len(cand_mask))
         self._n_geoms = max(len(self._geom_index), 1)
         M = len(self.models)
@@ -436,6 +439,34 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         self._obs_dyn = np.zeros((B, 11), dtype=np.float32)
         self._mask = np.zeros((B, A), dtype=np.uint8)
         self._need = np.zeros(B, dtype=np.int32)
+        if prewarm:
+            self.prewarm()
+
+    def prewarm(self):
+        """Lowers and registers the job of every (model, degree, block geometry) the device can choose, so that no step waits
+        for a native expansion (each costs 1-60 ms once)."""
+        import ctypes as C
+        for (d, gi), block in sorted(self._geom_example.items()):
+            for m, model in enumerate(self.models):
+                if not self._uniform[m, d] or (m, d, gi) in self._table_set:
+                    continue
+                ranks = [{v: i for i, v in enumerate(sorted({c[ax] for c in block}))} for ax in range(3)]
+                tkey = (m, d, tuple((ranks[0][c[0]], ranks[1][c[1]], ranks[2][c[2]]) for c in block))
+                tid = self._template_cache.get(tkey)
+                if tid is None:
+                    self.stats['expansions'] += 1
+                    lj = expand_template(model.graph, d, self.shape, quantum=model.quantum, num_training_steps=self.num_training_steps,
+                                         model_id=m, run_times=self.run_times, coords=block)
+                    tid = self.eng.register_template(lj)
+                    self._template_cache[tkey] = tid
+                    mt = lj.mount
+                    while len(self._t_mount) <= tid:
+                        self._t_mount.append(None)
+                    self._t_mount[tid] = (lj.seq_time, mt.part_op_mem, mt.part_dep_size, mt.flow_size, mt.n_mounted_workers, mt.n_mounted_channels)
+                    self._t_arrays = None
+                mt = np.array(self._t_mount[tid], dtype=np.float64)
+                _engine._check(self.eng._L.ramp_env_set_template(self.eng._h, m, d, gi, tid, mt.ctypes.data))
+                self._table_set.add((m, d, gi))
 
     def _geometry(self, coords):
         ranks = [{v: i for i, v in enumerate(sorted({c[ax] for c in coords}))} for ax in range(3)]
