@@ -477,7 +477,8 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         import ctypes as C
 
         class _Buf(C.Structure):
-            _fields_ = [(n, C.c_void_p) for n in ('actions', 'reward', 'done', 'queued_model', 'obs_dynamic', 'action_mask', 'busy', 'template_id')]
+            _fields_ = ([(n, C.c_void_p) for n in ('actions', 'reward', 'done', 'queued_model', 'obs_dynamic', 'action_mask', 'busy', 'template_id')]
+                        + [(n, C.c_int32) for n in ('n_episodes', 'n_actions', 'n_models')])
         b = _Buf()
         _engine._check(self.eng._L.ramp_env_buffers(self.eng._h, C.byref(b)))
         return {n: getattr(b, n) for n, _ in _Buf._fields_}

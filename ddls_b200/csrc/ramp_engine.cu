@@ -471,6 +471,12 @@ ThreadArgs make_thread_args(ramp_engine* e, const ChunkDesc* chunks, const int32
 
 }  // namespace
 
+// hooks for the other translation units of the library (ramp_policy.cu); not part of the C ABI
+int ramp_internal_set_error(int code, const char* msg) { g_last_error = msg; return code; }
+cudaStream_t ramp_internal_stream(ramp_engine_t* e) { return e->stream; }
+int ramp_internal_device(ramp_engine_t* e) { return e->cfg.device; }
+void ramp_internal_count_launches(ramp_engine_t* e, int n) { e->launches += n; }
+
 extern "C" {
 
 const char* ramp_last_error(void) { return g_last_error.c_str(); }
@@ -1317,6 +1323,7 @@ int ramp_env_buffers(ramp_engine_t* e, ramp_env_buffers_t* out) {
     const EnvDev& v = e->env;
     out->actions = v.actions; out->reward = v.reward; out->done = v.done; out->queued_model = v.queued_model;
     out->obs_dynamic = v.obs_dyn; out->action_mask = v.action_mask; out->busy = (uint64_t*)v.busy; out->template_id = v.tid;
+    out->n_episodes = v.B; out->n_actions = v.max_degree + 1; out->n_models = v.n_models;
     return RAMP_OK;
 }
 

@@ -105,3 +105,98 @@ def encode_observation(op_compute, op_memory, op_depth, edge_src, edge_dst, edge
             'node_features': node_features, 'edge_features': edge_features, 'graph_features': graph_features,
             'edges_src': src, 'edges_dst': dst, 'node_split': np.array([N], dtype=np.float32),
             'edge_split': np.array([E], dtype=np.float32)}
+
+
+def job_arrays(g, num_training_steps: int = 1):
+    """The flat arrays ``encode_observation`` reads, derived from a forward-pass profile alone (``synth.ForwardGraph``) in the
+    node / edge iteration order of the job graph the reference builds from it:
+
+      * nodes (utils.py:342-398 mirror_graph / combine_graphs): forward 1..n in file order, then the backward mirrors in the
+        order their forward ops were visited, i.e. 2n, 2n-1, ..., n+1;
+      * edges: by source node in that order, then insertion order -- the forward edges by file order, the backward edges
+        (2n-(v-1), 2n-(u-1)) in forward-edge iteration order, and the join n -> n+1 last in n's adjacency; an edge carries
+        its source op's activation size (utils.py:394-396);
+      * depth (job.py:23-29): number of nodes on the shortest path from the first source node, 0 if unreachable;
+      * max memory op / max dep (job.py:306-325): the FIRST strict maximum in iteration order.
+
+    Returns a dict of the positional and keyword arguments of ``encode_observation`` that depend on the job type only."""
+    n = g.n
+    order = list(range(1, n + 1)) + [2 * n - (i - 1) for i in range(1, n + 1)]
+    idx = {v: k for k, v in enumerate(order)}
+    N = 2 * n
+    comp = np.zeros(N); mem = np.zeros(N)
+    for i in range(1, n + 1):
+        comp[idx[i]] = g.fwd[i - 1]; comp[idx[2 * n - (i - 1)]] = g.bwd[i - 1]
+        mem[idx[i]] = mem[idx[2 * n - (i - 1)]] = g.act[i - 1] + g.par[i - 1]
+    adj = {v: [] for v in order}                                   # insertion-ordered adjacency, as networkx keeps it
+    for (u, v) in g.edges:
+        if v not in adj[u]:
+            adj[u].append(v)
+    fwd_iter = [(u, v) for u in range(1, n + 1) for v in adj[u]]   # forward_graph.edges()
+    for (u, v) in fwd_iter:
+        bu, bv = 2 * n - (v - 1), 2 * n - (u - 1)
+        if bv not in adj[bu]:
+            adj[bu].append(bv)
+    if (n + 1) not in adj[n]:
+        adj[n].append(n + 1)
+    act = {}
+    for i in range(1, n + 1):
+        act[i] = act[2 * n - (i - 1)] = g.act[i - 1]
+    edges = [(u, v) for u in order for v in adj[u]]
+    src = np.array([idx[u] for u, _ in edges], dtype=np.int64)
+    dst = np.array([idx[v] for _, v in edges], dtype=np.int64)
+    size = np.array([act[u] for u, _ in edges], dtype=np.float64)
+    # breadth-first depth from the source (the first node without parents)
+    has_parent = set(v for _, v in edges)
+    source = next(v for v in order if v not in has_parent)
+    depth = {source: 1}
+    frontier = [source]
+    while frontier:
+        nxt = []
+        for u in frontier:
+            for v in adj[u]:
+                if v not in depth:
+                    depth[v] = depth[u] + 1
+                    nxt.append(v)
+        frontier = nxt
+    dep = np.array([depth.get(v, 0) for v in order], dtype=np.float64)
+    max_mem, max_mem_op = 0.0, -1
+    for k in range(N):
+        if mem[k] > max_mem:
+            max_mem, max_mem_op = mem[k], k
+    max_dep, max_dep_idx = 0.0, -1
+    for k in range(len(edges)):
+        if size[k] > max_dep:
+            max_dep, max_dep_idx = size[k], k
+    total_mem = 0.0
+    for k in range(N):
+        total_mem += mem[k]
+    total_dep = 0.0
+    for k in range(len(edges)):
+        total_dep += size[k]
+    seq = 0.0
+    for k in range(N):
+        seq += comp[k]
+    return {'op_compute': comp, 'op_memory': mem, 'op_depth': dep, 'edge_src': src, 'edge_dst': dst, 'edge_size': size,
+            'max_compute_cost': float(comp.max()), 'max_compute_op': -1, 'max_memory_cost': float(max_mem), 'max_memory_op': max_mem_op,
+            'max_dep_size': float(max_dep), 'max_dep_index': max_dep_idx, 'max_depth': float(dep.max()),
+            'sequential_completion_time': seq * num_training_steps, 'total_op_memory': total_mem, 'total_dep_size': total_dep}
+
+
+def static_observation(g, machine_epsilon: float = 1e-7):
+    """What the policy observes of a job type whatever the cluster holds: node features [N, 5], edge features [E, 2], edge
+    endpoints and the six per-graph statistics (mean / median of the normalised op compute, op memory and dep size:
+    observation.py:425-469) -- ``encode_observation``'s arrays without padding."""
+    a = job_arrays(g)
+    cc, mc = a['op_compute'] / a['max_compute_cost'], a['op_memory'] / a['max_memory_cost']
+    nf = np.zeros((len(cc), 5)); nf[:, 0] = cc; nf[:, 2] = mc; nf[:, 4] = a['op_depth'] / a['max_depth']
+    if a['max_memory_op'] >= 0:
+        nf[a['max_memory_op'], 3] = 1.0
+    ef = np.zeros((len(a['edge_size']), 2)); ef[:, 0] = a['edge_size'] / a['max_dep_size']
+    if a['max_dep_index'] >= 0:
+        ef[a['max_dep_index'], 1] = 1.0
+    stats = [np.mean(cc), np.median(cc), np.mean(mc), np.median(mc), np.mean(a['edge_size']) / a['max_dep_size'],
+             np.median(a['edge_size']) / a['max_dep_size']]
+    return {'node_features': nf.astype(np.float32), 'edge_features': ef.astype(np.float32),
+            'edges_src': a['edge_src'].astype(np.int32), 'edges_dst': a['edge_dst'].astype(np.int32),
+            'graph_static': np.array(stats, dtype=np.float32)}

@@ -358,6 +358,7 @@ typedef struct {
     uint8_t*  action_mask;        /* [B][max_degree + 1] out                                                        */
     uint64_t* busy;               /* [B][n_words] occupancy of the cluster                                          */
     int32_t*  template_id;        /* [B] template the decision mounted (-1 none)                                    */
+    int32_t   n_episodes, n_actions, n_models;   /* B, max_degree + 1, job types                                    */
 } ramp_env_buffers_t;
 
 int ramp_env_create(ramp_engine_t* eng, const ramp_env_config_t* cfg);
@@ -377,6 +378,54 @@ int ramp_get_last_step_stats(ramp_engine_t* eng, double* stats_out, int32_t* n_c
 /* HOST copies of the occupancy [n_episodes][n_words] and of the actions the device holds (either may be NULL) */
 int ramp_env_read_state(ramp_engine_t* eng, uint64_t* busy_out, int32_t* actions_out);
 int ramp_env_read(ramp_engine_t* eng, double* reward, uint8_t* done, int32_t* queued_model, float* obs_dynamic, uint8_t* action_mask);
+
+
+/* ---- the GNN policy forward on the device: GNNPolicy.forward (ml_models/policies/gnn_policy.py:137-296) =
+ * num_rounds MeanPool message-passing rounds over the queued job's graph (ml_models/models/mean_pool.py:107-150, gnn.py:84-92),
+ * the mean of the node embeddings, a graph module over [graph features | action mask] (gnn_policy.py:96-109), and an RLlib
+ * FullyConnectedNetwork read-out (fcnet_hiddens, separate value branch) with the log-mask added to the logits
+ * (gnn_policy.py:283-290).  What the policy sees of a job's ops and deps is fixed per job TYPE (node / edge features:
+ * observation.py:503-567), so the message passing is run once per model and weight set (ramp_policy_embed: one CTA per model);
+ * per decision only the graph module + read-out run (one warp per episode, weights staged in shared memory), reading the
+ * environment's device buffers and writing its `actions` -- a rollout step never leaves the device.  fp32 throughout.
+ * DGL semantics restated: a node without incoming edges keeps a zero embedding after a round (dgl update_all fills
+ * zero-in-degree nodes with zeros); every other node averages reduce_module over [its own (node | zeros) state, messages]. ---- */
+typedef struct {
+    int32_t in_features_node, in_features_edge, in_features_graph;   /* 5, 2, 17 (gnn.yaml)                          */
+    int32_t n_actions;                                               /* action_space.n = max_partitions_per_op + 1    */
+    int32_t out_features_msg, out_features_hidden, out_features_node, out_features_graph;   /* 32, 64, 16, 8          */
+    int32_t num_rounds;                                              /* >= 2 (gnn.py:40-41)                           */
+    int32_t fcnet_hidden;                                            /* one hidden layer of the read-out (256)        */
+    int32_t aggregator_activation;                                   /* 0 relu, 1 leaky_relu(0.01)                    */
+    int32_t fcnet_activation;                                        /* 0 relu, 2 tanh                                */
+    int32_t apply_action_mask;
+    int32_t n_models;
+} ramp_policy_config_t;
+typedef struct ramp_policy ramp_policy_t;
+/* number of fp32 words of the weight blob for `cfg`, in torch state_dict order of GNNPolicy: per round [node LN w,b | node
+ * Linear W,b | edge LN w,b | edge Linear W,b | reduce LN w,b | reduce Linear W,b]; graph LN w,b | graph Linear W,b; read-out hidden
+ * W,b | logits W,b | value hidden W,b | value W,b.  Every W is [out][in] row-major as torch.nn.Linear keeps it. */
+int64_t ramp_policy_weight_count(const ramp_policy_config_t* cfg);
+int ramp_policy_create(int device, const ramp_policy_config_t* cfg, ramp_policy_t** out);
+void ramp_policy_destroy(ramp_policy_t* p);
+/* weights: HOST [ramp_policy_weight_count]; the per-model embeddings become stale until the next ramp_policy_embed */
+int ramp_policy_set_weights(ramp_policy_t* p, const float* weights, int64_t n);
+/* one job type: HOST node features [n_nodes][in_node], edge features [n_edges][in_edge], edge endpoints (node indices), and the
+ * per-graph statistics that sit between the dynamic graph features ([6]: observation.py:425-469) */
+int ramp_policy_set_model(ramp_policy_t* p, int32_t model, int32_t n_nodes, int32_t n_edges, const float* node_features,
+                          const float* edge_features, const int32_t* edges_src, const int32_t* edges_dst, const float* graph_static);
+/* message passing + node mean of every registered model; embeddings_out: HOST [n_models][out_features_node] or NULL */
+int ramp_policy_embed(ramp_policy_t* p, float* embeddings_out);
+/* read-out on HOST inputs (tests, host-side policies): model [n], graph_features [n][in_features_graph], action_mask
+ * [n][n_actions] -> logits [n][n_actions], value [n] (either may be NULL) */
+int ramp_policy_forward(ramp_policy_t* p, int32_t n, const int32_t* model, const float* graph_features, const uint8_t* action_mask,
+                        float* logits_out, float* value_out);
+/* one decision for every episode of `eng`'s environment on the engine's stream: reads queued_model / obs_dynamic / action_mask,
+ * writes ramp_env_buffers_t.actions (greedy: the first maximal logit; sample: categorical over softmax(logits) from a counter-based
+ * generator keyed by (seed, episode)); finished episodes get action 0.  No host transfer. */
+int ramp_policy_act(ramp_policy_t* p, ramp_engine_t* eng, int32_t sample, uint64_t seed);
+/* HOST copies of the last ramp_policy_act: logits [B][n_actions], value [B], log-probability of the chosen action [B], actions [B] (any may be NULL) */
+int ramp_policy_read(ramp_policy_t* p, ramp_engine_t* eng, float* logits_out, float* value_out, float* logp_out, int32_t* actions_out);
 
 #ifdef __cplusplus
 }
