@@ -3,7 +3,7 @@
 on the seeded golden episodes -- the per-step log and the episode statistics must equal what the reference recorded for
 itself (tests/golden/*.npz, written by oracle/gen_golden.py).
 
-Needs the reference: /root/reference in the build container, or the copy staged at oracle/_ref (oracle/stage_ref.py) on the
+Needs the reference: the checkout in the build container, or the copy staged at oracle/_ref (oracle/stage_ref.py) on the
 GPU box.  The CPU variant answers the engine calls with the oracle (tests/fake_engine.py): it checks the HOST logic
 (mount bookkeeping, lowering of the reference's real Action objects, arrival streaming, replay into episode_stats, the
 init-details memo).  The ``-m gpu`` variant is the same run on the CUDA engine."""
