@@ -564,10 +564,53 @@ def run_b200_arm(args, rank, world, local_rank):
                 benv.close()
             except Exception as ex:
                 batched[label] = {'error': repr(ex)[:300]}
+        # ---- the same rollouts with the reference's GNN policy deciding on the device (ddls_b200/policy.py): sampled actions written
+        #      straight into the environment's action buffer, no observation / reward / action crosses PCIe inside a segment ----
+        try:
+            from ddls_b200 import policy as policy_mod
+            graphs_b = [workload.make_graph(kind, **kw) for kind, kw in cfg['graphs']]
+            benv = batched_mod.DeviceRampJobPartitioningEnvironment(
+                tuple(cfg['shape']), graphs_b, n_episodes=B, jobs_per_episode=L, device=local_rank, seed=args.seed + 7 * rank,
+                run_times=args.run_times, interarrival=('exponential', 1000.0) if cfg.get('exponential') else ('fixed', 1000.0), prewarm=True)
+            pol = policy_mod.DeviceGNNPolicy(graphs_b, benv.max_partitions_per_op + 1, device=local_rank, seed=args.seed)
+            pol.embed()
+            for s_ in range(max(W, L)):
+                if s_ % L == 0:
+                    benv.reset()
+                pol.act(benv, sample=True, seed=args.seed + s_)
+                benv.step_device()
+            benv.read()
+            barrier()
+            tb = time.perf_counter()
+            n_env_steps_b = 0
+            for s_ in range(K):
+                if s_ % L == 0:
+                    if s_ > 0:
+                        n_env_steps_b += int(benv.decisions().sum())
+                    benv.reset()
+                pol.act(benv, sample=True, seed=args.seed + 1000 + s_)
+                benv.step_device()
+            n_env_steps_b += int(benv.decisions().sum())
+            _, rew_b, _ = benv.read()
+            barrier()
+            tb = time.perf_counter() - tb
+            tb_t = torch.tensor([tb], dtype=torch.float64, device='cuda')
+            nb_t = torch.tensor([float(n_env_steps_b)], dtype=torch.float64, device='cuda')
+            if world > 1:
+                dist.all_reduce(tb_t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(nb_t, op=dist.ReduceOp.SUM)
+            batched['device_gnn_policy'] = {
+                'value': float(nb_t[0]) / float(tb_t[0]), 'unit': UNIT, 'ms_per_step': float(tb_t[0]) / K * 1e3,
+                'policy': 'GNNPolicy (gnn.yaml: 2 MeanPool rounds, msg 32, hidden 64, read-out [256]), random weights, categorical sampling',
+                'host_decisions': not benv._device_decides_everything}
+            pol.close(); benv.close()
+        except Exception as ex:
+            batched['device_gnn_policy'] = {'error': repr(ex)[:300]}
         batched['what'] = ('RampJobPartitioningEnvironment.step for every episode through the batched gym-like surface (ddls_b200/batched.py), '
                            'host policy (random valid degree from the action mask), actions in and reward / done / observation out as host '
                            'arrays every step; env-steps of episodes that are not done are counted.  device: decision and bookkeeping as '
-                           'ramp_env_* kernels; host: the same in numpy + native C++ with caches')
+                           'ramp_env_* kernels; host: the same in numpy + native C++ with caches; device_gnn_policy: the device environment driven by the '
+                           'GNN policy kernels (ramp_policy_act), wall clock over whole segments including resets')
 
     if rank == 0:
         peak, peak_src = measured_peaks()

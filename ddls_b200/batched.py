@@ -439,6 +439,7 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         self._obs_dyn = np.zeros((B, 11), dtype=np.float32)
         self._mask = np.zeros((B, A), dtype=np.uint8)
         self._need = np.zeros(B, dtype=np.int32)
+        self._prewarmed = False
         if prewarm:
             self.prewarm()
 
@@ -467,6 +468,12 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
                 mt = np.array(self._t_mount[tid], dtype=np.float64)
                 _engine._check(self.eng._L.ramp_env_set_template(self.eng._h, m, d, gi, tid, mt.ctypes.data))
                 self._table_set.add((m, d, gi))
+        self._prewarmed = True
+
+    @property
+    def _device_decides_everything(self):
+        valid = [d for d in range(1, self.max_partitions_per_op + 1) if self._shape_ok[d] and d <= self.W]
+        return self._prewarmed and all(self._uniform[m, d] for m in range(len(self.models)) for d in valid)
 
     def _geometry(self, coords):
         ranks = [{v: i for i, v in enumerate(sorted({c[ax] for c in coords}))} for ax in range(3)]
@@ -534,6 +541,40 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         self.step_counter += 1
         return obs, self._reward.copy(), self.done.copy(), {}
 
+    def step_device(self):
+        """One RampJobPartitioningEnvironment.step per episode with the actions a device-resident policy left in
+        ``ramp_env_buffers_t.actions`` -- and nothing else: no observation, reward or done flag crosses PCIe (``read()`` fetches them
+        when wanted, ``decisions()`` the env-steps every episode has taken).  When every (model, degree) the action set allows is
+        decided by the device tables (``prewarm()`` registered every block geometry, no model splits its ops unevenly) the call does
+        not even synchronise."""
+        import ctypes as C
+        L, h = self.eng._L, self.eng._h
+        if self._device_decides_everything:
+            _engine._check(L.ramp_env_decide(h, None, None, None))
+        else:
+            n_need = C.c_int32(0)
+            _engine._check(L.ramp_env_decide(h, None, C.byref(n_need), self._need.ctypes.data))
+            if n_need.value > 0:
+                self._decide_on_host(self._need[:n_need.value].copy(), None)
+        _engine._check(L.ramp_env_advance(h))
+        self.step_counter += 1
+
+    def read(self):
+        """Host copies of what the last step left on the device: (obs, reward, done)."""
+        obs = self._read()
+        self.eng.check_status()
+        return obs, self._reward.copy(), self.done.copy()
+
+    def decisions(self):
+        """[B] env-steps every episode has taken since reset()."""
+        import ctypes as C
+        out = np.zeros(self.B, dtype=np.int32)
+        L = self.eng._L
+        L.ramp_env_read_state.restype = C.c_int
+        L.ramp_env_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _engine._check(L.ramp_env_read_state(self.eng._h, None, None, out.ctypes.data))
+        return out
+
     def _decide_on_host(self, episodes, actions):
         """Episodes the device tables could not decide: full native placer + expansion, then patch the rows (and remember the
         template of the geometry so that the device decides it next time)."""
@@ -543,8 +584,8 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         busy = np.zeros((self.B, nw), dtype=np.uint64)
         dev_actions = np.zeros(self.B, dtype=np.int32)
         L.ramp_env_read_state.restype = C.c_int
-        L.ramp_env_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        _engine._check(L.ramp_env_read_state(h, busy.ctypes.data, dev_actions.ctypes.data))
+        L.ramp_env_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _engine._check(L.ramp_env_read_state(h, busy.ctypes.data, dev_actions.ctypes.data, None))
         if actions is None:
             actions = dev_actions
         ep = self.eng.episode_state()

@@ -161,7 +161,8 @@ struct ramp_engine {
     bool has_env = false;
     EnvDev env{};
     std::vector<void*> env_allocs;
-    int32_t* env_h_need = nullptr;       // pinned: [0] = count
+    int32_t* env_h_need = nullptr;       // pinned: [0] = count, [1] = error flag; [2], [3]: the same, read by ramp_env_read
+    bool env_unchecked_decide = false;   // a ramp_env_decide without need_host_out has not been looked at yet
     // standalone lookahead buffers
     WorkItem* sa_chunk_items = nullptr;
     ChunkDesc* sa_chunks = nullptr;
@@ -1272,6 +1273,7 @@ int ramp_env_create(ramp_engine_t* e, const ramp_env_config_t* c) {
     if ((rc = env_upload<unsigned long long>(e, &v.placed, nullptr, (size_t)B * nw))) return rc;
     if ((rc = env_upload<int32_t>(e, &v.tid, nullptr, (size_t)B))) return rc;
     if ((rc = env_upload<int32_t>(e, &v.decided_job, nullptr, (size_t)B))) return rc;
+    if ((rc = env_upload<int32_t>(e, &v.n_decided, nullptr, (size_t)B))) return rc;
     if ((rc = env_upload<int32_t>(e, &v.actions, nullptr, (size_t)B))) return rc;
     if ((rc = env_upload<double>(e, &v.reward, nullptr, (size_t)B))) return rc;
     if ((rc = env_upload<uint8_t>(e, &v.done, nullptr, (size_t)B))) return rc;
@@ -1281,7 +1283,7 @@ int ramp_env_create(ramp_engine_t* e, const ramp_env_config_t* c) {
     if ((rc = env_upload<int32_t>(e, &v.need_host, nullptr, (size_t)B))) return rc;
     if ((rc = env_upload<int32_t>(e, &v.n_need_host, nullptr, 1))) return rc;
     if ((rc = env_upload<int32_t>(e, &v.err, nullptr, 1))) return rc;
-    CUDA_TRY(cudaMallocHost(&e->env_h_need, sizeof(int32_t) * 2));
+    CUDA_TRY(cudaMallocHost(&e->env_h_need, sizeof(int32_t) * 4));
     e->has_env = true;
     return RAMP_OK;
 }
@@ -1308,6 +1310,7 @@ int ramp_env_reset(ramp_engine_t* e, const int32_t* model_of, const double* frac
     CUDA_TRY(cudaMemcpyAsync((void*)v.macc, macc, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaMemsetAsync(v.job_mask, 0, sizeof(unsigned long long) * n * v.n_words, e->stream));
     CUDA_TRY(cudaMemsetAsync(v.done, 0, (size_t)v.B, e->stream));
+    CUDA_TRY(cudaMemsetAsync(v.n_decided, 0, sizeof(int32_t) * (size_t)v.B, e->stream));
     CUDA_TRY(cudaMemsetAsync(v.err, 0, sizeof(int32_t), e->stream));
     int rc = ramp_reset(e, arrivals, v.J);
     if (rc != RAMP_OK) return rc;
@@ -1348,6 +1351,8 @@ int ramp_env_decide(ramp_engine_t* e, const int32_t* actions, int32_t* n_need_ho
         *n_need_host_out = e->env_h_need[0];
         if (need_host_out && e->env_h_need[0] > 0)
             CUDA_TRY(cudaMemcpy(need_host_out, v.need_host, sizeof(int32_t) * e->env_h_need[0], cudaMemcpyDeviceToHost));
+    } else {
+        e->env_unchecked_decide = true;      // looked at by the next ramp_env_read
     }
     return RAMP_OK;
 }
@@ -1398,6 +1403,22 @@ int ramp_env_read(ramp_engine_t* e, double* reward, uint8_t* done, int32_t* queu
     if (queued_model) CUDA_TRY(cudaMemcpyAsync(queued_model, v.queued_model, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, st));
     if (obs_dynamic) CUDA_TRY(cudaMemcpyAsync(obs_dynamic, v.obs_dyn, sizeof(float) * 11 * v.B, cudaMemcpyDeviceToHost, st));
     if (action_mask) CUDA_TRY(cudaMemcpyAsync(action_mask, v.action_mask, (size_t)v.B * (v.max_degree + 1), cudaMemcpyDeviceToHost, st));
+    if (e->env_unchecked_decide) {
+        // decisions taken without the host looking (a device-resident policy): an invalid action under apply_action_mask is sticky
+        // in `err`; episodes the tables could not decide were left unplaced, which only the LAST decide's count can show
+        CUDA_TRY(cudaMemcpyAsync(e->env_h_need + 2, v.n_need_host, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(e->env_h_need + 3, v.err, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        int rc = ramp_sync(e);
+        if (rc != RAMP_OK) return rc;
+        e->env_unchecked_decide = false;
+        if (e->env_h_need[3] != 0) {
+            CUDA_TRY(cudaMemset(v.err, 0, sizeof(int32_t)));
+            return set_error(RAMP_ERR_BAD_ARG, "episode %d: the action is invalid given its action mask (RJPE:314-319)", e->env_h_need[3] - 1);
+        }
+        if (e->env_h_need[2] != 0)
+            return set_error(RAMP_ERR_BAD_ARG, "%d episodes needed the host's placer but ramp_env_decide was called without need_host_out", e->env_h_need[2]);
+        return RAMP_OK;
+    }
     return ramp_sync(e);
 }
 
@@ -1411,11 +1432,12 @@ int ramp_get_last_step_stats(ramp_engine_t* e, double* stats_out, int32_t* n_clu
 }
 
 
-int ramp_env_read_state(ramp_engine_t* e, uint64_t* busy_out, int32_t* actions_out) {
+int ramp_env_read_state(ramp_engine_t* e, uint64_t* busy_out, int32_t* actions_out, int32_t* n_decided_out) {
     if (!e || !e->has_env) return set_error(RAMP_ERR_BAD_ARG, "no environment");
     const EnvDev& v = e->env;
     if (busy_out) CUDA_TRY(cudaMemcpyAsync(busy_out, v.busy, sizeof(uint64_t) * (size_t)v.B * v.n_words, cudaMemcpyDeviceToHost, e->stream));
     if (actions_out) CUDA_TRY(cudaMemcpyAsync(actions_out, v.actions, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, e->stream));
+    if (n_decided_out) CUDA_TRY(cudaMemcpyAsync(n_decided_out, v.n_decided, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, e->stream));
     return ramp_sync(e);
 }
 

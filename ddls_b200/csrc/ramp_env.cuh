@@ -29,6 +29,7 @@ struct EnvDev {
     unsigned long long* placed;     // [B][n_words] block chosen this step
     int32_t* tid;                   // [B]
     int32_t* decided_job;           // [B] job idx the decision was for
+    int32_t* n_decided;             // [B] decisions taken since the reset (env-steps of the episode)
     // i/o
     int32_t* actions; double* reward; uint8_t* done; int32_t* queued_model; float* obs_dyn; uint8_t* action_mask;
     int32_t* need_host; int32_t* n_need_host;
@@ -61,6 +62,7 @@ __global__ void ramp_env_decide_kernel(const EnvDev v, const EpisodeState ep, ra
     v.decided_job[b] = q;
     if (ep.ei[EI_DONE * B + b]) { row.flags = RAMP_ACT_SKIP; rows[b] = row; return; }
     int a = v.actions[b];
+    v.n_decided[b] += 1;
     if (q < 0) { rows[b] = row; return; }                                        // cannot happen after ramp_env_advance (RJPE:394-395)
     const int free_workers = env_free_workers(v, b);
     if (!env_action_valid(v, b, a, free_workers)) {

@@ -23,6 +23,8 @@
 
 #include "../../include/ramp_b200.h"
 
+int ramp_internal_set_error(int code, const char* msg);   // ramp_engine.cu: what ramp_last_error() returns
+
 namespace {
 
 struct Node {
@@ -110,8 +112,8 @@ void ramp_free_expanded_job(ramp_lowered_job_t* j) {
 
 int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double quantum, const ramp_block_t* blk,
                          int32_t run_time_mode, int32_t num_training_steps, ramp_lowered_job_t* out, ramp_expanded_aux_t* aux) {
-    if (!g || !blk || !out || g->n_fwd < 1 || degree < 1 || (degree != 1 && degree % 2 != 0) || blk->n_servers < degree)
-        return RAMP_ERR_BAD_ARG;
+    if (!g || !blk || !out || g->n_fwd < 1 || degree < 1 || (degree != 1 && degree % 2 != 0) || blk->n_servers < 1)
+        return ramp_internal_set_error(RAMP_ERR_BAD_ARG, "ramp_expand_template: null argument, empty graph or block, or a degree that is neither 1 nor even (op_partition.py:26-27)");
     const int n = g->n_fwd;
     Graph G;
     {   // every forward edge fans out to at most degree^2 edges per direction, every split backward op adds degree^2 sync edges
@@ -128,7 +130,7 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
     }
     for (int e = 0; e < g->n_edges; ++e) {
         const int u = g->edge_src[e], v = g->edge_dst[e];
-        if (u < 1 || u > n || v < 1 || v > n) return RAMP_ERR_BAD_ARG;
+        if (u < 1 || u > n || v < 1 || v > n) return ramp_internal_set_error(RAMP_ERR_BAD_ARG, "ramp_expand_template: an edge names an op outside 1..n_fwd");
         G.add_edge(fwd_node[u], fwd_node[v], G.nodes[fwd_node[u]].mem);
     }
     for (int e = 0; e < g->n_edges; ++e) {                       // mirrored backward edge 2n-(v-1) -> 2n-(u-1)
@@ -143,6 +145,9 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
         const double c = g->fwd_cost[i - 1];
         const double k = std::max(1.0, std::min(std::ceil(std::ceil(c / quantum) / 2.0) * 2.0, (double)degree));   // RJPE:336
         splits[i] = (int)k;
+        if (splits[i] > blk->n_servers)
+            return ramp_internal_set_error(RAMP_ERR_BAD_ARG, "ramp_expand_template: an op splits into more sub-ops than the block has servers");
+        // the block holds one server per sub-op of the most-split op (which may be < degree)
     }
     std::unordered_map<uint64_t, double> in_feat, out_feat;
     in_feat.reserve(G.size.bucket_count()); out_feat.reserve(G.size.bucket_count());
@@ -341,7 +346,7 @@ int ramp_expand_template(const ramp_forward_graph_t* g, int32_t degree, double q
 // a cluster whose servers are described by free memory and a busy flag; the Python twin is ddls_b200/placer.py.
 int ramp_first_fit_place(const ramp_forward_graph_t* g, const int32_t* splits, const ramp_cluster_state_t* st,
                          int32_t* server_out, int32_t* offset_out) {
-    if (!g || !splits || !st || !server_out || !offset_out || g->n_fwd < 1) return RAMP_ERR_BAD_ARG;
+    if (!g || !splits || !st || !server_out || !offset_out || g->n_fwd < 1) return ramp_internal_set_error(RAMP_ERR_BAD_ARG, "ramp_first_fit_place: null argument or empty graph");
     const int n = g->n_fwd, C = st->shape[0], R = st->shape[1], S = st->shape[2];
     const int n_servers = C * R * S;
     auto sid = [&](int c, int r, int s) { return (c * R + r) * S + s; };
@@ -349,7 +354,7 @@ int ramp_first_fit_place(const ramp_forward_graph_t* g, const int32_t* splits, c
     std::vector<std::vector<int>> parents(n + 1), children(n + 1);
     for (int e = 0; e < g->n_edges; ++e) {
         const int u = g->edge_src[e], v = g->edge_dst[e];
-        if (u < 1 || u > n || v < 1 || v > n) return RAMP_ERR_BAD_ARG;
+        if (u < 1 || u > n || v < 1 || v > n) return ramp_internal_set_error(RAMP_ERR_BAD_ARG, "ramp_first_fit_place: an edge names an op outside 1..n_fwd");
         parents[v].push_back(u); children[u].push_back(v);
     }
     // topo_sort (utils.py:100-115)
@@ -447,9 +452,10 @@ int ramp_first_fit_place(const ramp_forward_graph_t* g, const int32_t* splits, c
 // on, ok_out[k] = 1, or ok_out[k] = 0 when the job cannot be placed there.
 int ramp_first_fit_place_many(const ramp_forward_graph_t* g, const int32_t* splits, const int32_t shape[3], double memory_capacity,
                               int32_t n_states, int32_t n_words, const uint64_t* busy_words, uint64_t* server_mask_out, uint8_t* ok_out) {
-    if (!g || !splits || !shape || !busy_words || !server_mask_out || !ok_out || n_states < 0 || n_words < 1) return RAMP_ERR_BAD_ARG;
+    if (!g || !splits || !shape || !busy_words || !server_mask_out || !ok_out || n_states < 0 || n_words < 1)
+        return ramp_internal_set_error(RAMP_ERR_BAD_ARG, "ramp_first_fit_place_many: null argument");
     const int n_servers = shape[0] * shape[1] * shape[2];
-    if (n_servers > 64 * n_words) return RAMP_ERR_BAD_ARG;
+    if (n_servers > 64 * n_words) return ramp_internal_set_error(RAMP_ERR_BAD_ARG, "ramp_first_fit_place_many: n_words too small for the cluster");
     int total = 0;
     for (int i = 0; i < g->n_fwd; ++i) total += std::max(splits[i], 1);
     std::vector<double> free_mem(n_servers, memory_capacity);

@@ -375,8 +375,9 @@ int ramp_env_advance(ramp_engine_t* eng);
 /* HOST copies of the outputs (any may be NULL) */
 /* step statistics / cluster-step counts of the last ramp_env_advance (the engine's own buffers): HOST [n_episodes][RAMP_STEP_STATS_LEN], [n_episodes] */
 int ramp_get_last_step_stats(ramp_engine_t* eng, double* stats_out, int32_t* n_cluster_steps_out);
-/* HOST copies of the occupancy [n_episodes][n_words] and of the actions the device holds (either may be NULL) */
-int ramp_env_read_state(ramp_engine_t* eng, uint64_t* busy_out, int32_t* actions_out);
+/* HOST copies of the occupancy [n_episodes][n_words], of the actions the device holds, and of the number of decisions every episode
+ * has taken since ramp_env_reset (= its env-steps; a finished episode takes none) -- any may be NULL */
+int ramp_env_read_state(ramp_engine_t* eng, uint64_t* busy_out, int32_t* actions_out, int32_t* n_decided_out);
 int ramp_env_read(ramp_engine_t* eng, double* reward, uint8_t* done, int32_t* queued_model, float* obs_dynamic, uint8_t* action_mask);
 
 

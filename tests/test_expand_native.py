@@ -60,6 +60,23 @@ def test_native_expansion_rejects_bad_arguments():
         expand_template(synth.chain_graph(4, 'c4'), 3, RampShape(2, 2, 2))           # odd degree (op_partition.py:26-27)
     with pytest.raises(Exception):
         expand_template(synth.chain_graph(4, 'c4'), 16, RampShape(2, 2, 2))          # block larger than the cluster
+    with pytest.raises(Exception, match='more sub-ops than the block has servers'):
+        expand_template(synth.chain_graph(6, 'chain6'), 16, RampShape(4, 4, 2), quantum=2.0, coords=[(0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1)])
+
+
+def test_block_may_be_smaller_than_the_action_when_no_op_splits_that_far():
+    """RJPE:332-343 gives every op clamp(even(ceil(cost / quantum)), 1, action) sub-ops: with a coarse quantum the most-split op may
+    take fewer sub-ops than the action allows, the placer then hands out that many servers, and the lowered job is the one of the
+    smaller action."""
+    g = synth.chain_graph(6, 'chain6')
+    coords = [(0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 0, 1)]
+    for mode in ('one_to_one', 'reference'):
+        a = expand_template(g, 16, RampShape(4, 4, 2), quantum=2.0, coords=coords, run_times=mode)      # splits 2, 2, 4, 4, 4, 6
+        b = expand_template(g, 6, RampShape(4, 4, 2), quantum=2.0, coords=coords, run_times=mode)
+        assert a.n_workers == 6 and a.n_ops == b.n_ops == 44
+        for f in ARRAYS:
+            np.testing.assert_array_equal(np.asarray(getattr(a, f)), np.asarray(getattr(b, f)), err_msg=f)
+        assert a.mount == b.mount
 
 
 # graphs / topologies of the seeded reference episodes behind tests/fixtures/placer_cases.json (oracle/gen_golden.py CASES,
