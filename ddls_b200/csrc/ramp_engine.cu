@@ -614,6 +614,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     cudaStreamSynchronize(e->stream);
     for (auto& t : e->templates) { cudaFree(t.blob); cudaFree(t.res_blob); }
     for (void* pa : e->env_allocs) cudaFree(pa);
+    cudaFree(e->ep.tick_util); cudaFree(e->ep.tick_util_n);
     if (e->env_h_need) cudaFreeHost(e->env_h_need);
     cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank); cudaFree(e->d_hints);
     cudaFree(e->d_res_scratch); cudaFree(e->sa_chunk_items); cudaFree(e->sa_chunks);
@@ -1422,6 +1423,39 @@ int ramp_env_read(ramp_engine_t* e, double* reward, uint8_t* done, int32_t* queu
     return ramp_sync(e);
 }
 
+
+int ramp_enable_tick_lists(ramp_engine_t* e, int32_t cap) {
+    if (!e || cap < 1) return set_error(RAMP_ERR_BAD_ARG, "ramp_enable_tick_lists: cap must be >= 1");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->ep.tick_util) { cudaFree(e->ep.tick_util); cudaFree(e->ep.tick_util_n); e->ep.tick_util = nullptr; e->ep.tick_util_n = nullptr; }
+    const size_t B = (size_t)e->cfg.n_episodes;
+    CUDA_TRY(cudaMalloc(&e->ep.tick_util, sizeof(double) * B * (size_t)cap * 2));
+    CUDA_TRY(cudaMalloc(&e->ep.tick_util_n, sizeof(int32_t) * B));
+    CUDA_TRY(cudaMemset(e->ep.tick_util_n, 0, sizeof(int32_t) * B));
+    e->ep.tick_util_cap = cap;
+    return RAMP_OK;
+}
+
+int ramp_get_tick_lists(ramp_engine_t* e, int32_t episode, double* mounted_out, double* cluster_out, int32_t cap, int32_t* n_out) {
+    if (!e || !n_out) return set_error(RAMP_ERR_BAD_ARG, "null argument");
+    if (!e->ep.tick_util) return set_error(RAMP_ERR_BAD_ARG, "per-tick lists are not recorded (ramp_enable_tick_lists)");
+    if (episode < 0 || episode >= e->cfg.n_episodes) return set_error(RAMP_ERR_BAD_ARG, "bad episode %d", episode);
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    int32_t n = 0;
+    CUDA_TRY(cudaMemcpy(&n, e->ep.tick_util_n + episode, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    if (n > e->ep.tick_util_cap)
+        return set_error(RAMP_ERR_CAPACITY, "episode %d: the step had %d outer-loop iterations, the per-tick lists hold %d", episode, n, e->ep.tick_util_cap);
+    const int m = std::min(n, cap);
+    if (m > 0 && mounted_out && cluster_out) {
+        std::vector<double> rows((size_t)m * 2);
+        CUDA_TRY(cudaMemcpy(rows.data(), e->ep.tick_util + (size_t)episode * e->ep.tick_util_cap * 2, sizeof(double) * rows.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < m; ++k) { mounted_out[k] = rows[2 * k]; cluster_out[k] = rows[2 * k + 1]; }
+    }
+    return RAMP_OK;
+}
 
 int ramp_get_last_step_stats(ramp_engine_t* e, double* stats_out, int32_t* n_cluster_steps_out) {
     if (!e) return set_error(RAMP_ERR_BAD_ARG, "null engine");

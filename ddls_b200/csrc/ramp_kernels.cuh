@@ -119,6 +119,9 @@ struct EpisodeState {
     int32_t* ri;                // [RI_COUNT][max_running][B]
     ramp_job_record_t* rec;     // [B][max_jobs]
     const ramp_arrival_t* arr;  // [B][max_jobs]
+    double* tick_util;          // [B][tick_util_cap][2] or null: the step's per-tick utilisation lists (RCE:989-994), ramp_enable_tick_lists
+    int32_t* tick_util_n;       // [B] their length in the last cluster step
+    int32_t tick_util_cap;
     const int32_t* n_jobs_ep;   // [B] jobs the episode's arrival stream holds so far (len(jobs_generator) > 0 <=> more than arrived,
                                 //     RCE:1019-1040); ramp_reset sets n_jobs for all, ramp_set_job_count changes one episode
 };
@@ -1008,11 +1011,16 @@ __global__ void ramp_step_kernel(const StepArgs s) {
                 sum_jobs = __dadd_rn(sum_jobs, (double)nr);                                   // RCE:984
                 sum_workers = __dadd_rn(sum_workers, (double)mounted_workers);               // RCE:986
                 sum_channels = __dadd_rn(sum_channels, (double)mounted_channels);            // RCE:987
+                double tick_mounted = 0.0, tick_cluster = 0.0;
                 if (nr > 0) {                                                                // RCE:989-994
-                    const double mean_util = __ddiv_rn(util_sum, (double)nr);
-                    util_mounted_sum = __dadd_rn(util_mounted_sum, mean_util);
-                    util_cluster_sum = __dadd_rn(util_cluster_sum,
-                                                 __dmul_rn(__ddiv_rn((double)mounted_workers, (double)ep.n_cluster_workers), mean_util));
+                    tick_mounted = __ddiv_rn(util_sum, (double)nr);
+                    tick_cluster = __dmul_rn(__ddiv_rn((double)mounted_workers, (double)ep.n_cluster_workers), tick_mounted);
+                    util_mounted_sum = __dadd_rn(util_mounted_sum, tick_mounted);
+                    util_cluster_sum = __dadd_rn(util_cluster_sum, tick_cluster);
+                }
+                if (ep.tick_util && n_iter < ep.tick_util_cap) {
+                    double* tu = ep.tick_util + ((size_t)b * ep.tick_util_cap + n_iter) * 2;
+                    tu[0] = tick_mounted; tu[1] = tick_cluster;
                 }
                 ++n_iter;
                 EF(EF_NOW) = __dadd_rn(now, tick);                                            // RCE:998
@@ -1073,6 +1081,7 @@ __global__ void ramp_step_kernel(const StepArgs s) {
             st[RAMP_SS_UTIL_MOUNTED_SUM] = util_mounted_sum;
             st[RAMP_SS_UTIL_CLUSTER_SUM] = util_cluster_sum;
             st[RAMP_SS_NUM_TICKS] = (double)n_iter;
+            if (ep.tick_util) ep.tick_util_n[b] = n_iter;
             st[RAMP_SS_JOB_QUEUE_LENGTH] = EI(EI_QUEUED) >= 0 ? 1.0 : 0.0;                       // RCE:1082
             EI(EI_STEP_COUNTER)++;                                                                // RCE:1109
             const bool done = step_is_done(ep, b);

@@ -127,7 +127,7 @@ EXPORTED_SYMBOLS = ['ramp_last_error', 'ramp_engine_create', 'ramp_engine_destro
                     'ramp_quotient_template', 'ramp_free_quotient', 'ramp_get_quotient_bytes', 'ramp_set_job_count',
                     'ramp_set_limits', 'ramp_first_fit_place_many', 'ramp_env_create', 'ramp_env_set_template',
                     'ramp_env_reset', 'ramp_env_buffers', 'ramp_env_decide', 'ramp_env_patch', 'ramp_env_advance', 'ramp_env_read', 'ramp_get_last_step_stats', 'ramp_env_read_state',
-                    'ramp_policy_weight_count', 'ramp_policy_create', 'ramp_policy_destroy', 'ramp_policy_set_weights', 'ramp_policy_set_model',
+                    'ramp_enable_tick_lists', 'ramp_get_tick_lists', 'ramp_policy_weight_count', 'ramp_policy_create', 'ramp_policy_destroy', 'ramp_policy_set_weights', 'ramp_policy_set_model',
                     'ramp_policy_embed', 'ramp_policy_forward', 'ramp_policy_act', 'ramp_policy_read']
 
 
@@ -230,6 +230,21 @@ class RampEngine:
 
     def sync(self):
         _check(self._L.ramp_sync(self._h))
+
+    def enable_tick_lists(self, cap=256):
+        self._L.ramp_enable_tick_lists.restype = C.c_int
+        self._L.ramp_enable_tick_lists.argtypes = [C.c_void_p, C.c_int32]
+        _check(self._L.ramp_enable_tick_lists(self._h, int(cap)))
+        self._tick_cap = int(cap)
+
+    def tick_lists(self, episode=0):
+        """The last cluster step's per-tick lists (RCE:989-994) of one episode: (mounted utilisation, cluster utilisation)."""
+        self._L.ramp_get_tick_lists.restype = C.c_int
+        self._L.ramp_get_tick_lists.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
+        cap = self._tick_cap
+        a, b, n = np.zeros(cap), np.zeros(cap), C.c_int32(0)
+        _check(self._L.ramp_get_tick_lists(self._h, int(episode), a.ctypes.data, b.ctypes.data, cap, C.byref(n)))
+        return a[:n.value], b[:n.value]
 
     def check_status(self):
         ep, st = C.c_int32(), C.c_int32()

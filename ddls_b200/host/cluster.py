@@ -150,6 +150,8 @@ class RampClusterEnvironment:
                 n_episodes=1, n_cluster_workers=n_workers, max_jobs=self._max_jobs, device=self.device,
                 job_queue_capacity=job_queue_capacity, machine_epsilon=self.machine_epsilon,
                 max_simulation_run_time=float(max_simulation_run_time), memo_mode=_engine.MEMO_REFERENCE)
+            # a step's outer loop runs once per job completion (<= one running job per worker) plus the arrival / the end of time
+            self._engine.enable_tick_lists(n_workers + 16)
             self._template_cache = {}
         else:
             self._engine.set_limits(float(max_simulation_run_time), job_queue_capacity)
@@ -403,11 +405,11 @@ class RampClusterEnvironment:
             step_stats[k] = float(stats[SS[k]])
         for k in ('step_counter', 'num_jobs_completed', 'num_jobs_arrived', 'num_jobs_blocked', 'job_queue_length'):
             step_stats[k] = int(step_stats[k])
-        n_ticks = int(stats[SS['num_ticks']])
-        # the reference leaves these two as per-tick lists (RCE:990-991); keep a list whose sum and length match
-        for k_list, k_sum in (('mean_mounted_worker_utilisation_frac', 'util_mounted_sum'),
-                              ('mean_cluster_worker_utilisation_frac', 'util_cluster_sum')):
-            step_stats[k_list] = [float(stats[SS[k_sum]]) / n_ticks] * n_ticks if n_ticks else []
+        # the reference leaves these two as per-tick lists (RCE:989-994): the engine kept every entry of the step
+        tick_mounted, tick_cluster = self._engine.tick_lists(0)
+        assert len(tick_mounted) == int(stats[SS['num_ticks']])
+        step_stats['mean_mounted_worker_utilisation_frac'] = [float(x) for x in tick_mounted]
+        step_stats['mean_cluster_worker_utilisation_frac'] = [float(x) for x in tick_cluster]
         self.step_stats = step_stats
 
         # 1. queued jobs the action did not handle (RCE:914-919)

@@ -373,6 +373,13 @@ int ramp_env_decide(ramp_engine_t* eng, const int32_t* actions, int32_t* n_need_
 int ramp_env_patch(ramp_engine_t* eng, int32_t episode, int32_t template_id, const uint64_t* server_mask, const double mount[6]);
 int ramp_env_advance(ramp_engine_t* eng);
 /* HOST copies of the outputs (any may be NULL) */
+/* The reference leaves step_stats['mean_mounted_worker_utilisation_frac'] / ['mean_cluster_worker_utilisation_frac'] as LISTS with
+ * one entry per outer-loop iteration of the step (RCE:989-994); RAMP_SS_UTIL_*_SUM / RAMP_SS_NUM_TICKS carry their sum and length.
+ * ramp_enable_tick_lists makes the step kernel also keep the entries of the last cluster step (up to `cap` per episode);
+ * ramp_get_tick_lists copies one episode's to HOST arrays [cap] and returns the length in n_out (RAMP_ERR_CAPACITY when the
+ * step had more iterations than `cap` given to ramp_enable_tick_lists). */
+int ramp_enable_tick_lists(ramp_engine_t* eng, int32_t cap);
+int ramp_get_tick_lists(ramp_engine_t* eng, int32_t episode, double* mounted_out, double* cluster_out, int32_t cap, int32_t* n_out);
 /* step statistics / cluster-step counts of the last ramp_env_advance (the engine's own buffers): HOST [n_episodes][RAMP_STEP_STATS_LEN], [n_episodes] */
 int ramp_get_last_step_stats(ramp_engine_t* eng, double* stats_out, int32_t* n_cluster_steps_out);
 /* HOST copies of the occupancy [n_episodes][n_words], of the actions the device holds, and of the number of decisions every episode

@@ -99,6 +99,8 @@ def lib():
         L.orc_env_set_arrival.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.orc_env_set_job_count.restype = C.c_int
         L.orc_env_set_job_count.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_env_tick_lists.restype = C.c_int32
+        L.orc_env_tick_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_env_queued_job.restype = C.c_int32
         L.orc_env_queued_job.argtypes = [C.c_void_p]
         L.orc_env_num_jobs_arrived.restype = C.c_int32
@@ -188,6 +190,13 @@ class OracleEnv:
     def set_job_count(self, n):
         if lib().orc_env_set_job_count(self._h, n) != 0:
             raise Exception('orc_env_set_job_count failed')
+
+    def tick_lists(self):
+        """The last step's step_stats['mean_mounted_worker_utilisation_frac'] / ['mean_cluster_worker_utilisation_frac'] (RCE:989-994)."""
+        n = lib().orc_env_tick_lists(self._h, None, None, 0)
+        a, b = np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        lib().orc_env_tick_lists(self._h, a.ctypes.data, b.ctypes.data, n)
+        return a[:n], b[:n]
 
     def step(self, job=None):
         stats = np.zeros(STEP_STATS_LEN, dtype=np.float64)

@@ -220,6 +220,9 @@ struct orc_env {
     orc_memo_t* memo;
     const orc_memo_t* last_memo;
     double* stats; /* current step stats */
+    /* the two per-tick lists of the last step (RCE:989-994): step_stats['mean_mounted_worker_utilisation_frac'] and
+       ['mean_cluster_worker_utilisation_frac'] hold one entry per outer-loop iteration */
+    double* tick_util_mounted; double* tick_util_cluster; int32_t n_tick_util, tick_util_cap;
 };
 
 orc_env_t* orc_env_create(int32_t n_cluster_workers, int32_t max_running_jobs, int32_t max_jobs,
@@ -251,6 +254,7 @@ void orc_env_destroy(orc_env_t* env) {
     if (!env) return;
     memo_clear(env);
     free(env->running); free(env->records); free(env->memo); free(env->arrivals_own);
+    free(env->tick_util_mounted); free(env->tick_util_cluster);
     free(env);
 }
 
@@ -413,12 +417,22 @@ int orc_env_step(orc_env_t* env, const orc_lowered_job_t* job, const orc_mount_t
         }
         sum_jobs_running += (double)env->n_running;                           /* RCE:984 */
         sum_workers += (double)mounted_workers; sum_channels += (double)mounted_channels; /* RCE:986-987 */
+        double tick_mounted = 0.0, tick_cluster = 0.0;
         if (env->n_running > 0) {                                             /* RCE:989-994 */
             double mean_util = util_sum / (double)env->n_running;
-            util_mounted_sum += mean_util;
-            util_cluster_sum += ((double)mounted_workers / (double)env->n_cluster_workers) * mean_util;
+            tick_mounted = mean_util;
+            tick_cluster = ((double)mounted_workers / (double)env->n_cluster_workers) * mean_util;
+            util_mounted_sum += tick_mounted;
+            util_cluster_sum += tick_cluster;
         }
+        if (n_iter >= env->tick_util_cap) {
+            env->tick_util_cap = env->tick_util_cap ? 2 * env->tick_util_cap : 64;
+            env->tick_util_mounted = (double*)realloc(env->tick_util_mounted, sizeof(double) * (size_t)env->tick_util_cap);
+            env->tick_util_cluster = (double*)realloc(env->tick_util_cluster, sizeof(double) * (size_t)env->tick_util_cap);
+        }
+        env->tick_util_mounted[n_iter] = tick_mounted; env->tick_util_cluster[n_iter] = tick_cluster;
         n_iter++;
+        env->n_tick_util = n_iter;
 
         env->now += tick;                                                     /* RCE:998 */
 
@@ -500,6 +514,11 @@ int orc_env_step(orc_env_t* env, const orc_lowered_job_t* job, const orc_mount_t
 int32_t orc_env_queued_job(const orc_env_t* env) { return env->queued_job; }
 int32_t orc_env_num_jobs_arrived(const orc_env_t* env) { return env->num_arrived; }
 double orc_env_time(const orc_env_t* env) { return env->now; }
+/* the last step's per-tick utilisation lists (RCE:989-994); returns their length, copies at most cap entries of each */
+int32_t orc_env_tick_lists(const orc_env_t* env, double* mounted_out, double* cluster_out, int32_t cap) {
+    for (int32_t k = 0; k < env->n_tick_util && k < cap; ++k) { mounted_out[k] = env->tick_util_mounted[k]; cluster_out[k] = env->tick_util_cluster[k]; }
+    return env->n_tick_util;
+}
 double orc_env_mean_load_rate(const orc_env_t* env) { return env->load_rate_n > 0 ? env->load_rate_sum / (double)env->load_rate_n : 0.0; }
 const orc_job_record_t* orc_env_job_records(const orc_env_t* env) { return env->records; }
 int32_t orc_env_last_trace(const orc_env_t* env, const int32_t** n_active, const double** tick) {

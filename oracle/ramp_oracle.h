@@ -177,6 +177,8 @@ int orc_env_set_job_count(orc_env_t* env, int32_t n_jobs);
 int32_t orc_env_queued_job(const orc_env_t* env);   /* job idx at head of queue or -1 */
 int32_t orc_env_num_jobs_arrived(const orc_env_t* env);
 double  orc_env_time(const orc_env_t* env);
+/* the last step's per-tick utilisation lists (RCE:989-994): returns their length, copies at most cap entries of each */
+int32_t orc_env_tick_lists(const orc_env_t* env, double* mounted_out, double* cluster_out, int32_t cap);
 double  orc_env_mean_load_rate(const orc_env_t* env);
 const orc_job_record_t* orc_env_job_records(const orc_env_t* env);
 /* last lookahead trace run or looked up by the env (for parity checks) */

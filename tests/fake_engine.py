@@ -58,6 +58,12 @@ class FakeEngine:
                                      float(a['flow_size']), int(a['n_mounted_workers']), int(a['n_mounted_channels']))
         return self._env.step(job).reshape(1, -1)
 
+    def enable_tick_lists(self, cap=256):
+        pass                      # the oracle always keeps them
+
+    def tick_lists(self, episode=0):
+        return self._env.tick_lists()
+
     def check_status(self):
         pass                      # OracleEnv.step raises on the same conditions
 

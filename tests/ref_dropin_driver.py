@@ -103,7 +103,10 @@ def main():
            'steps_log': {k: [float(x) for x in cluster.steps_log[k]] for k in
                          ('step_start_time', 'step_end_time', 'num_jobs_completed', 'num_jobs_arrived', 'num_jobs_blocked',
                           'mean_num_jobs_running', 'mean_compute_overhead_frac', 'mean_communication_overhead_frac',
-                          'compute_info_processed', 'mean_cluster_throughput')}}
+                          'compute_info_processed', 'mean_cluster_throughput')},
+           # the two step statistics the reference leaves as per-tick lists (RCE:989-994)
+           'tick_lists': {k: [[float(x) for x in step] for step in cluster.steps_log[k]] for k in
+                          ('mean_mounted_worker_utilisation_frac', 'mean_cluster_worker_utilisation_frac')}}
     for k in ('num_jobs_arrived', 'num_jobs_completed', 'num_jobs_blocked'):
         out[k] = int(es[k])
     for k in ('episode_end_time', 'mean_load_rate', 'blocking_rate', 'acceptance_rate', 'compute_info_processed', 'dep_info_processed',
