@@ -35,6 +35,9 @@ namespace ramp {
 #ifndef RAMP_T_FCAP
 #define RAMP_T_FCAP 16      // ready flow entries kept in shared memory per lane
 #endif
+#ifndef RAMP_T_FASTF
+#define RAMP_T_FASTF 6      // frontiers of up to this many flow entries (and 2 op classes) run the register-resident path
+#endif
 #ifndef RAMP_T_NFCAP
 #define RAMP_T_NFCAP 8      // ready non-flow entries kept in shared memory per lane
 #endif
@@ -194,6 +197,15 @@ struct LaneNF {
     }
 };
 
+// Remaining times are non-negative doubles (validated and canonicalised to +0 at registration): their u64 bit patterns order like
+// the values, so every comparison of the tick loop -- winners' minimum, tick = min(t_comm, t_op), "did it complete" -- is a 64-bit
+// INTEGER comparison (two ISETP) instead of an FP64 one.  On sm_100a DSETP / DADD results come back through the long scoreboard
+// (profiles/r2_ncu_thread_source.md: 20 % of all stall samples sat on four DSETP after tick_down); only the subtraction of the
+// survivors and the three accumulators stay FP64, off the control path.
+//   x -= min(tick, x) == 0  (JOB:555-556, 561-562)  <=>  x <= tick   (x > tick >= 0 gives x - tick > 0: no underflow to zero)
+typedef unsigned long long u64_t;
+__device__ __forceinline__ u64_t rem_bits(const int4& r) { return ((u64_t)(uint32_t)r.y << 32) | (u64_t)(uint32_t)r.x; }
+
 struct LaneCtx {                      // what one lane's lookahead works on
     const unsigned char* tm;         // template blob in shared memory
     int4* f_sm; int4* o_sm; uint32_t* nf_sm; int32_t* oi_sm; uint32_t* wk_sm; uint32_t* ck_sm; uint16_t* cnt_sm;
@@ -241,14 +253,14 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
     double* tt_ptr = x.tr_tick;
 
     while (R.status == RAMP_ST_OK) {
-        if (nF <= 4 && nO <= 2) {
+        if (nF <= RAMP_T_FASTF && nO <= 2) {
             // ======== small frontiers (the usual case on a quotient): every ready item is loaded ONCE into registers and each
             // phase runs code specialised for the exact number of ready ops (0-2) and flows (0-4): winners by pairwise
             // comparison (no tables, any number of worker / channel groups), no loop or predication overhead ========
-            int4 fr[4], orr[2];
+            int4 fr[RAMP_T_FASTF], orr[2];
             int oi[2];
             bool ow0 = false, ow1 = false;
-            double t_op = INF;
+            u64_t t_op = RAMP_INF_BITS;
             int n_active = 0;
             // ---- A, B ----
             if (nO >= 1) {
@@ -258,13 +270,13 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                     orr[1] = x.o_sm[32 + lane]; oi[1] = x.oi_sm[32 + lane];
                     ow1 = true;
                     if (((orr[0].w ^ orr[1].w) & 0xffff) == 0) { if ((uint32_t)orr[0].z > (uint32_t)orr[1].z) ow1 = false; else ow0 = false; }
-                    if (ow1) { t_op = __hiloint2double(orr[1].y, orr[1].x); n_active = (int)((uint32_t)orr[1].w >> 16); }
+                    if (ow1) { t_op = rem_bits(orr[1]); n_active = (int)((uint32_t)orr[1].w >> 16); }
                 }
-                if (ow0) { const double r0 = __hiloint2double(orr[0].y, orr[0].x); t_op = (r0 < t_op) ? r0 : t_op; n_active += (int)((uint32_t)orr[0].w >> 16); }
+                if (ow0) { const u64_t r0 = rem_bits(orr[0]); t_op = (r0 < t_op) ? r0 : t_op; n_active += (int)((uint32_t)orr[0].w >> 16); }
             }
             // ---- C, D ----
             const bool any_nf = nNF > 0;
-            double t_comm = any_nf ? 0.0 : INF;
+            u64_t t_comm = any_nf ? 0ull : (u64_t)RAMP_INF_BITS;
             auto load_flows = [&](auto nf_tag) {
                 constexpr int NF = decltype(nf_tag)::value;
 #pragma unroll
@@ -282,7 +294,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                     uint32_t open_groups = gm[k];
 #pragma unroll
                     for (int j = 0; j < NF; ++j) if (j != k && key[j] > key[k]) open_groups &= ~gm[j];
-                    if (open_groups) { const double rem = __hiloint2double(fr[k].y, fr[k].x); t_comm = (rem < t_comm) ? rem : t_comm; }
+                    if (open_groups) { const u64_t rem = rem_bits(fr[k]); t_comm = (rem < t_comm) ? rem : t_comm; }
                 }
             };
             if (!any_nf) {
@@ -291,11 +303,14 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                     case 2: load_flows(std::integral_constant<int, 2>{}); winners(std::integral_constant<int, 2>{}); break;
                     case 3: load_flows(std::integral_constant<int, 3>{}); winners(std::integral_constant<int, 3>{}); break;
                     case 4: load_flows(std::integral_constant<int, 4>{}); winners(std::integral_constant<int, 4>{}); break;
+                    case 5: load_flows(std::integral_constant<int, 5>{}); winners(std::integral_constant<int, 5>{}); break;
+                    case 6: load_flows(std::integral_constant<int, 6>{}); winners(std::integral_constant<int, 6>{}); break;
                     default: break;
                 }
             }
             // ---- E, I, J ----
-            const double tick = (t_comm < t_op) ? t_comm : t_op;
+            const u64_t tick_b = (t_comm < t_op) ? t_comm : t_op;
+            const double tick = __longlong_as_double((long long)tick_b);
             if ((!any_nf) && (nF > 0)) R.comm = __dadd_rn(R.comm, tick);                             // RCE:434-439, 777-791
             if (n_active > 0) R.comp = __dadd_rn(R.comp, tick);
             R.t = __dadd_rn(R.t, tick);
@@ -324,16 +339,21 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                     constexpr int NF = decltype(nf_tag)::value;
 #pragma unroll
                     for (int k = 0; k < NF; ++k) {
-                        const double r2 = tick_down(__hiloint2double(fr[k].y, fr[k].x), tick);      // JOB:561
-                        if (r2 == 0.0) { complete_dep((uint32_t)fr[k].w); ++deps_completed; }       // JOB:562
-                        else { fr[k].x = __double2loint(r2); fr[k].y = __double2hiint(r2); x.f_sm[p * 32 + lane] = fr[k]; ++p; }
+                        const u64_t rb = rem_bits(fr[k]);
+                        if (rb <= tick_b) { complete_dep((uint32_t)fr[k].w); ++deps_completed; }    // JOB:561-562
+                        else {
+                            const double r2 = __dsub_rn(__longlong_as_double((long long)rb), tick);
+                            fr[k].x = __double2loint(r2); fr[k].y = __double2hiint(r2); x.f_sm[p * 32 + lane] = fr[k]; ++p;
+                        }
                     }
                 };
                 switch (nF) {
                     case 1: tick_flows(std::integral_constant<int, 1>{}); break;
                     case 2: tick_flows(std::integral_constant<int, 2>{}); break;
                     case 3: tick_flows(std::integral_constant<int, 3>{}); break;
-                    default: tick_flows(std::integral_constant<int, 4>{}); break;
+                    case 4: tick_flows(std::integral_constant<int, 4>{}); break;
+                    case 5: tick_flows(std::integral_constant<int, 5>{}); break;
+                    default: tick_flows(std::integral_constant<int, 6>{}); break;
                 }
                 nF = p;
             }
@@ -341,8 +361,8 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             int p = 0;
             auto tick_op = [&](int4 r, const int op, const bool win) {
                 if (win) {                                                                          // this tick's winner
-                    const double rem = tick_down(__hiloint2double(r.y, r.x), tick);                 // JOB:555
-                    if (rem == 0.0) {                                                               // JOB:556
+                    const u64_t rb = rem_bits(r);
+                    if (rb <= tick_b) {                                                             // JOB:555-556
                         ++ops_completed;
                         const int2 row = op_row[op];
                         _Pragma("unroll 1")
@@ -356,6 +376,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                         }
                         return;
                     }
+                    const double rem = __dsub_rn(__longlong_as_double((long long)rb), tick);
                     r.x = __double2loint(rem); r.y = __double2hiint(rem);
                 }
                 x.o_sm[p * 32 + lane] = r; x.oi_sm[p * 32 + lane] = op; ++p;
@@ -375,11 +396,11 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 R.max_nf = (nNF > R.max_nf) ? nNF : R.max_nf;
             }
             if ((ops_completed == N) && (deps_completed == E)) break;                               // JOB:549-551
-            if (isinf(tick)) { R.status = RAMP_ST_INFINITE_TICK; break; }                           // RCE:462
+            if (tick_b == (u64_t)RAMP_INF_BITS) { R.status = RAMP_ST_INFINITE_TICK; break; }        // RCE:462
             continue;
         }
         // ---- A, B: winners per worker group: largest key; t_op = min of their remaining times ----
-        double t_op = INF;
+        u64_t t_op = RAMP_INF_BITS;
         int n_active = 0;
         uint32_t best_w = 0u;                 // SIMPLE: the winner's key
         if (nO > 0) {
@@ -387,7 +408,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 _Pragma("unroll 1")
                 for (int k = 0; k < nO; ++k) {
                     const int4 r = ops.rec(k);
-                    if ((uint32_t)r.z > best_w) { best_w = (uint32_t)r.z; t_op = __hiloint2double(r.y, r.x); n_active = (int)((uint32_t)r.w >> 16); }
+                    if ((uint32_t)r.z > best_w) { best_w = (uint32_t)r.z; t_op = rem_bits(r); n_active = (int)((uint32_t)r.w >> 16); }
                 }
             } else if (tab_w) {
                 _Pragma("unroll 1")
@@ -402,7 +423,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 for (int k = 0; k < nO; ++k) {
                     const int4 r = ops.rec(k);
                     if (wk[(r.w & 0xffff) * 32] == (uint32_t)r.z) {
-                        const double rem = __hiloint2double(r.y, r.x);
+                        const u64_t rem = rem_bits(r);
                         t_op = (rem < t_op) ? rem : t_op;
                         n_active += (int)((uint32_t)r.w >> 16);
                     }
@@ -420,7 +441,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                         if ((r2.w & 0xffff) == (r.w & 0xffff) && ((uint32_t)r2.z & 0x7fffffffu) > (uint32_t)r.z) win = false;
                     }
                     if (win) {
-                        const double rem = __hiloint2double(r.y, r.x);
+                        const u64_t rem = rem_bits(r);
                         t_op = (rem < t_op) ? rem : t_op;
                         n_active += (int)((uint32_t)r.w >> 16);
                         r.z = (int)((uint32_t)r.z | 0x80000000u);
@@ -431,9 +452,9 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
         }
         // ---- C, D ----
         const bool any_nf = nNF > 0;
-        double t_comm = 0.0;
+        u64_t t_comm = 0ull;
         if (!any_nf) {
-            t_comm = INF;
+            t_comm = RAMP_INF_BITS;
             if (nF > 0) {
                 if (SIMPLE) {
                     uint32_t best = 0u;
@@ -442,7 +463,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                         const int4 f = flows.get(k);
                         if (((uint32_t)f.z >> csh) == 0u) continue;                                  // no channel: ticks, never a winner
                         const uint32_t key = (uint32_t)f.z & kmask;
-                        const double rem = __hiloint2double(f.y, f.x);
+                        const u64_t rem = rem_bits(f);
                         if (key > best) { best = key; t_comm = rem; }
                         else if (key == best) t_comm = (rem < t_comm) ? rem : t_comm;
                     }
@@ -464,7 +485,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                         uint32_t m = (uint32_t)f.z >> csh;
                         bool win = false;
                         while (m && !win) { const int q = __ffs((int)m) - 1; m &= m - 1u; win = ck[q * 32] == key; }
-                        if (win) { const double rem = __hiloint2double(f.y, f.x); t_comm = (rem < t_comm) ? rem : t_comm; }
+                        if (win) { const u64_t rem = rem_bits(f); t_comm = (rem < t_comm) ? rem : t_comm; }
                     }
                 } else {
                     _Pragma("unroll 1")
@@ -478,13 +499,14 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                             const uint32_t lo2 = (uint32_t)flows.get(j).z;
                             if ((lo2 & kmask) > key) open_groups &= ~(lo2 >> csh);
                         }
-                        if (open_groups) { const double rem = __hiloint2double(f.y, f.x); t_comm = (rem < t_comm) ? rem : t_comm; }
+                        if (open_groups) { const u64_t rem = rem_bits(f); t_comm = (rem < t_comm) ? rem : t_comm; }
                     }
                 }
             }
         }
         // ---- E, I, J ----
-        const double tick = (t_comm < t_op) ? t_comm : t_op;
+        const u64_t tick_b = (t_comm < t_op) ? t_comm : t_op;
+        const double tick = __longlong_as_double((long long)tick_b);
         {
             if ((!any_nf) && (nF > 0)) R.comm = __dadd_rn(R.comm, tick);                             // RCE:434-439, 777-791
             if (n_active > 0) R.comp = __dadd_rn(R.comp, tick);
@@ -514,9 +536,12 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             _Pragma("unroll 1")
             for (int k = 0; k < nF; ++k) {
                 int4 f = flows.get(k);
-                const double r2 = tick_down(__hiloint2double(f.y, f.x), tick);                      // JOB:561
-                if (r2 == 0.0) { complete_dep((uint32_t)f.w); ++deps_completed; }                   // JOB:562
-                else { f.x = __double2loint(r2); f.y = __double2hiint(r2); flows.put(p, f); ++p; }
+                const u64_t rb = rem_bits(f);
+                if (rb <= tick_b) { complete_dep((uint32_t)f.w); ++deps_completed; }                // JOB:561-562
+                else {
+                    const double r2 = __dsub_rn(__longlong_as_double((long long)rb), tick);
+                    f.x = __double2loint(r2); f.y = __double2hiint(r2); flows.put(p, f); ++p;
+                }
             }
             nF = p;
         }
@@ -531,8 +556,8 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             else if (tab_w) win = wk[(r.w & 0xffff) * 32] == (uint32_t)r.z;
             else { win = r.z < 0; r.z &= 0x7fffffff; }
             if (win) {                                                                              // this tick's winner
-                const double rem = tick_down(__hiloint2double(r.y, r.x), tick);                     // JOB:555
-                if (rem == 0.0) {                                                                   // JOB:556
+                const u64_t rb = rem_bits(r);
+                if (rb <= tick_b) {                                                                 // JOB:555-556
                     ++ops_completed;
                     const int2 row = op_row[op];
                     _Pragma("unroll 1")
@@ -546,6 +571,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                     }
                     continue;
                 }
+                const double rem = __dsub_rn(__longlong_as_double((long long)rb), tick);
                 r.x = __double2loint(rem); r.y = __double2hiint(rem);
             }
             ops.put(p, r, op); ++p;
@@ -560,7 +586,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
         }
         // ---- K, L ----
         if ((ops_completed == N) && (deps_completed == E)) break;                                   // JOB:549-551
-        if (isinf(tick)) { R.status = RAMP_ST_INFINITE_TICK; break; }                               // RCE:462
+        if (tick_b == (u64_t)RAMP_INF_BITS) { R.status = RAMP_ST_INFINITE_TICK; break; }            // RCE:462
     }
     return R;
 }
