@@ -157,6 +157,7 @@ struct ramp_engine {
     int32_t* d_tbase = nullptr;
     int32_t* d_rank = nullptr;           // [B]
     TemplateHints* d_hints = nullptr;    // [max_templates]
+    double* d_hint_jct = nullptr;        // [max_templates]
     // device-resident rollouts (ramp_env_*)
     bool has_env = false;
     EnvDev env{};
@@ -466,7 +467,7 @@ ThreadArgs make_thread_args(ramp_engine* e, const ChunkDesc* chunks, const int32
     a.scratch = e->d_res_scratch; a.scratch_stride = e->res_scratch_stride;
     a.res = res; a.pool = pool; a.trace_cap = e->cfg.trace_cap;
     a.tmpl_cap = e->res_tmpl_cap; a.n_cap = e->res_n_cap; a.spill_ops = e->res_spill_ops; a.spill_deps = e->res_spill_deps;
-    a.stats = stats; a.hints = e->d_hints;
+    a.stats = stats; a.hints = e->d_hints; a.hint_jct = e->d_hint_jct;
     return a;
 }
 
@@ -569,6 +570,8 @@ int ramp_engine_create(const ramp_config_t* cfg_in, ramp_engine_t** out) {
     CUDA_TRY(cudaMalloc(&e->d_rank, sizeof(int32_t) * B));
     CUDA_TRY(cudaMalloc(&e->d_hints, sizeof(TemplateHints) * (size_t)cfg.max_templates));
     CUDA_TRY(cudaMemset(e->d_hints, 0, sizeof(TemplateHints) * (size_t)cfg.max_templates));
+    CUDA_TRY(cudaMalloc(&e->d_hint_jct, sizeof(double) * (size_t)cfg.max_templates));
+    CUDA_TRY(cudaMemset(e->d_hint_jct, 0, sizeof(double) * (size_t)cfg.max_templates));
     CUDA_TRY(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
@@ -616,7 +619,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     for (void* pa : e->env_allocs) cudaFree(pa);
     cudaFree(e->ep.tick_util); cudaFree(e->ep.tick_util_n);
     if (e->env_h_need) cudaFreeHost(e->env_h_need);
-    cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank); cudaFree(e->d_hints);
+    cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank); cudaFree(e->d_hints); cudaFree(e->d_hint_jct);
     cudaFree(e->d_res_scratch); cudaFree(e->sa_chunk_items); cudaFree(e->sa_chunks);
     cudaFree(e->d_templates); cudaFree(e->d_memo_keys); cudaFree(e->d_memo_vals); cudaFree(e->d_memo_keys2);
     free_result_slots(e->res); free_result_slots(e->sa_res);

@@ -78,6 +78,8 @@ struct ThreadArgs {
     int32_t spill_ops, spill_deps;  // per-lane spill capacities (entries) in the HBM slab
     MemoStats* stats;
     TemplateHints* hints;           // [max_templates], zero = nothing recorded yet
+    double* hint_jct;               // [max_templates] job completion time the first lookahead of the template found (0 = none):
+                                    //   lets later ones accumulate the utilisation inside the tick loop (RCE:830-832 divides by it)
 };
 
 __host__ __device__ inline size_t thread_smem_bytes(int tmpl_cap, int n_cap) {
@@ -213,9 +215,10 @@ struct LaneCtx {                      // what one lane's lookahead works on
     int32_t* tr_n; double* tr_tick;  // trace destination: element k at [k * tr_stride]
     int tr_stride, tr_cap;
     int lane, n_cap;
+    double util_jct, util_dn;        // != 0: accumulate sum (n_active / util_dn) * (tick / util_jct) in tick order (RCE:830-832)
 };
 
-struct LaneResult { double t, comm, comp; int tick_no, status, max_o, max_f, max_nf; };
+struct LaneResult { double t, comm, comp, util; int tick_no, status, max_o, max_f, max_nf; };
 
 // _run_lookahead for one lane.  SPILL = false: every frontier fits its shared-memory capacity (TemplateHints);
 // SIMPLE = true: one worker group and at most one channel group (the usual quotient of a partitioned job): the winner is the
@@ -246,9 +249,17 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
     int nO = H.n_src, nF = 0, nNF = 0;
     for (int k = 0; k < nO; ++k) { const int op = src_ops[k]; ops.put(k, op_rec[op], op); }       // RCE:1334
     LaneResult R;
-    R.t = 0.0; R.comm = 0.0; R.comp = 0.0; R.tick_no = 0; R.max_o = nO; R.max_f = 0; R.max_nf = 0;
+    R.t = 0.0; R.comm = 0.0; R.comp = 0.0; R.util = 0.0; R.tick_no = 0; R.max_o = nO; R.max_f = 0; R.max_nf = 0;
     R.status = (N <= x.n_cap) ? RAMP_ST_OK : RAMP_ST_TABLE_FULL;                                    // cannot happen (eligibility)
     int ops_completed = 0, deps_completed = 0;
+    const bool do_util = x.util_jct != 0.0;
+    int util_last_n = -1;
+    double util_last_q = 0.0;
+    // the term of one tick (RCE:830-832); a tick with no active worker or no length adds +0.0 and is skipped (see the epilogue)
+    auto add_util = [&](const int n_active, const double tick) {
+        if (n_active != util_last_n) { util_last_n = n_active; util_last_q = __ddiv_rn((double)n_active, x.util_dn); }
+        R.util = __dadd_rn(R.util, __dmul_rn(util_last_q, __ddiv_rn(tick, x.util_jct)));
+    };
     int32_t* tn_ptr = x.tr_n;
     double* tt_ptr = x.tr_tick;
 
@@ -257,6 +268,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             // ======== small frontiers (the usual case on a quotient): every ready item is loaded ONCE into registers and each
             // phase runs code specialised for the exact number of ready ops (0-2) and flows (0-4): winners by pairwise
             // comparison (no tables, any number of worker / channel groups), no loop or predication overhead ========
+            static_assert(RAMP_T_FASTF == 6, "the dispatch below has cases for up to 6 ready flow entries");
             int4 fr[RAMP_T_FASTF], orr[2];
             int oi[2];
             bool ow0 = false, ow1 = false;
@@ -274,50 +286,10 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 }
                 if (ow0) { const u64_t r0 = rem_bits(orr[0]); t_op = (r0 < t_op) ? r0 : t_op; n_active += (int)((uint32_t)orr[0].w >> 16); }
             }
-            // ---- C, D ----
+            // ---- C, D, E, I, J, H: ONE dispatch on the number of ready flow entries; each case is straight-line code ----
             const bool any_nf = nNF > 0;
-            u64_t t_comm = any_nf ? 0ull : (u64_t)RAMP_INF_BITS;
-            auto load_flows = [&](auto nf_tag) {
-                constexpr int NF = decltype(nf_tag)::value;
-#pragma unroll
-                for (int k = 0; k < NF; ++k) fr[k] = x.f_sm[k * 32 + lane];
-            };
-            auto winners = [&](auto nf_tag) {
-                constexpr int NF = decltype(nf_tag)::value;
-                uint32_t gm[NF > 0 ? NF : 1], key[NF > 0 ? NF : 1];
-#pragma unroll
-                for (int k = 0; k < NF; ++k) { gm[k] = (uint32_t)fr[k].z >> csh; key[k] = (uint32_t)fr[k].z & kmask; }
-#pragma unroll
-                for (int k = 0; k < NF; ++k) {
-                    // the entry wins on a channel group of its set unless a ready entry with a larger key lies on that group too
-                    // (an empty set -- no channel -- never wins, it only ticks)
-                    uint32_t open_groups = gm[k];
-#pragma unroll
-                    for (int j = 0; j < NF; ++j) if (j != k && key[j] > key[k]) open_groups &= ~gm[j];
-                    if (open_groups) { const u64_t rem = rem_bits(fr[k]); t_comm = (rem < t_comm) ? rem : t_comm; }
-                }
-            };
-            if (!any_nf) {
-                switch (nF) {
-                    case 1: load_flows(std::integral_constant<int, 1>{}); winners(std::integral_constant<int, 1>{}); break;
-                    case 2: load_flows(std::integral_constant<int, 2>{}); winners(std::integral_constant<int, 2>{}); break;
-                    case 3: load_flows(std::integral_constant<int, 3>{}); winners(std::integral_constant<int, 3>{}); break;
-                    case 4: load_flows(std::integral_constant<int, 4>{}); winners(std::integral_constant<int, 4>{}); break;
-                    case 5: load_flows(std::integral_constant<int, 5>{}); winners(std::integral_constant<int, 5>{}); break;
-                    case 6: load_flows(std::integral_constant<int, 6>{}); winners(std::integral_constant<int, 6>{}); break;
-                    default: break;
-                }
-            }
-            // ---- E, I, J ----
-            const u64_t tick_b = (t_comm < t_op) ? t_comm : t_op;
-            const double tick = __longlong_as_double((long long)tick_b);
-            if ((!any_nf) && (nF > 0)) R.comm = __dadd_rn(R.comm, tick);                             // RCE:434-439, 777-791
-            if (n_active > 0) R.comp = __dadd_rn(R.comp, tick);
-            R.t = __dadd_rn(R.t, tick);
-            if (R.tick_no < x.tr_cap) { *tn_ptr = n_active; *tt_ptr = tick; tn_ptr += x.tr_stride; tt_ptr += x.tr_stride; }
-            else R.status = RAMP_ST_TRACE_OVERFLOW;
-            ++R.tick_no;
-            // ---- H ----
+            u64_t tick_b = 0ull;
+            double tick = 0.0;
             int tailO = nO;
             auto complete_dep = [&](const uint32_t hi) {                                            // JOB:525-536
                 const int child = (int)(hi >> dsh);
@@ -328,34 +300,62 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 cnt[child * 32] = (uint16_t)neu;
                 if (old < thr && thr <= neu) { ops.put(tailO, op_rec[child], child); ++tailO; }     // JOB:531 for every member
             };
-            if (any_nf) {
-                _Pragma("unroll 1")
-                for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
-                deps_completed += nNF;
-                nNF = 0;
-            } else if (nF > 0) {
-                int p = 0;
-                auto tick_flows = [&](auto nf_tag) {
-                    constexpr int NF = decltype(nf_tag)::value;
+            // E, I, J: the tick, the three accumulators, the utilisation term and the trace entry
+            auto take_tick = [&](const u64_t t_comm, const bool ticked_flows) {
+                tick_b = (t_comm < t_op) ? t_comm : t_op;
+                tick = __longlong_as_double((long long)tick_b);
+                if (ticked_flows) R.comm = __dadd_rn(R.comm, tick);                                  // RCE:434-439, 777-791
+                if (n_active > 0) { R.comp = __dadd_rn(R.comp, tick); if (do_util && tick_b != 0ull) add_util(n_active, tick); }
+                R.t = __dadd_rn(R.t, tick);
+                if (R.tick_no < x.tr_cap) { *tn_ptr = n_active; *tt_ptr = tick; tn_ptr += x.tr_stride; tt_ptr += x.tr_stride; }
+                else R.status = RAMP_ST_TRACE_OVERFLOW;
+                ++R.tick_no;
+            };
+            auto flow_tick = [&](auto nf_tag) {
+                constexpr int NF = decltype(nf_tag)::value;
+                uint32_t gm[NF], key[NF];
 #pragma unroll
-                    for (int k = 0; k < NF; ++k) {
-                        const u64_t rb = rem_bits(fr[k]);
-                        if (rb <= tick_b) { complete_dep((uint32_t)fr[k].w); ++deps_completed; }    // JOB:561-562
-                        else {
-                            const double r2 = __dsub_rn(__longlong_as_double((long long)rb), tick);
-                            fr[k].x = __double2loint(r2); fr[k].y = __double2hiint(r2); x.f_sm[p * 32 + lane] = fr[k]; ++p;
-                        }
+                for (int k = 0; k < NF; ++k) fr[k] = x.f_sm[k * 32 + lane];
+#pragma unroll
+                for (int k = 0; k < NF; ++k) { gm[k] = (uint32_t)fr[k].z >> csh; key[k] = (uint32_t)fr[k].z & kmask; }
+                u64_t t_comm = RAMP_INF_BITS;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    // the entry wins on a channel group of its set unless a ready entry with a larger key lies on that group too
+                    // (an empty set -- no channel -- never wins, it only ticks)
+                    uint32_t open_groups = gm[k];
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) if (j != k && key[j] > key[k]) open_groups &= ~gm[j];
+                    if (open_groups) { const u64_t rem = rem_bits(fr[k]); t_comm = (rem < t_comm) ? rem : t_comm; }
+                }
+                take_tick(t_comm, true);
+                int p = 0;
+#pragma unroll
+                for (int k = 0; k < NF; ++k) {
+                    const u64_t rb = rem_bits(fr[k]);
+                    if (rb <= tick_b) { complete_dep((uint32_t)fr[k].w); ++deps_completed; }        // JOB:561-562
+                    else {
+                        const double r2 = __dsub_rn(__longlong_as_double((long long)rb), tick);
+                        fr[k].x = __double2loint(r2); fr[k].y = __double2hiint(r2); x.f_sm[p * 32 + lane] = fr[k]; ++p;
                     }
-                };
-                switch (nF) {
-                    case 1: tick_flows(std::integral_constant<int, 1>{}); break;
-                    case 2: tick_flows(std::integral_constant<int, 2>{}); break;
-                    case 3: tick_flows(std::integral_constant<int, 3>{}); break;
-                    case 4: tick_flows(std::integral_constant<int, 4>{}); break;
-                    case 5: tick_flows(std::integral_constant<int, 5>{}); break;
-                    default: tick_flows(std::integral_constant<int, 6>{}); break;
                 }
                 nF = p;
+            };
+            switch (any_nf ? -1 : nF) {
+                case -1:                                            // zero-length tick that completes the ready non-flow deps
+                    take_tick(0ull, false);
+                    _Pragma("unroll 1")
+                    for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
+                    deps_completed += nNF;
+                    nNF = 0;
+                    break;
+                case 0: take_tick(RAMP_INF_BITS, false); break;
+                case 1: flow_tick(std::integral_constant<int, 1>{}); break;
+                case 2: flow_tick(std::integral_constant<int, 2>{}); break;
+                case 3: flow_tick(std::integral_constant<int, 3>{}); break;
+                case 4: flow_tick(std::integral_constant<int, 4>{}); break;
+                case 5: flow_tick(std::integral_constant<int, 5>{}); break;
+                default: flow_tick(std::integral_constant<int, 6>{}); break;
             }
             // ---- G ----
             int p = 0;
@@ -509,7 +509,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
         const double tick = __longlong_as_double((long long)tick_b);
         {
             if ((!any_nf) && (nF > 0)) R.comm = __dadd_rn(R.comm, tick);                             // RCE:434-439, 777-791
-            if (n_active > 0) R.comp = __dadd_rn(R.comp, tick);
+            if (n_active > 0) { R.comp = __dadd_rn(R.comp, tick); if (do_util && tick_b != 0ull) add_util(n_active, tick); }
             R.t = __dadd_rn(R.t, tick);
             if (R.tick_no < x.tr_cap) { *tn_ptr = n_active; *tt_ptr = tick; tn_ptr += x.tr_stride; tt_ptr += x.tr_stride; }
             else R.status = RAMP_ST_TRACE_OVERFLOW;
@@ -671,6 +671,12 @@ __global__ void __launch_bounds__(32) ramp_lookahead_thread_kernel(const ThreadA
             }
             if (off >= 0) { x.tr_n = a.pool.n_active + off; x.tr_tick = a.pool.tick + off; x.tr_stride = 1; x.tr_cap = hint.n_ticks; }
             else { x.tr_n = tmp_n + lane; x.tr_tick = tmp_tick + lane; x.tr_stride = 32; x.tr_cap = a.trace_cap; }
+            // utilisation inside the tick loop when an earlier lookahead of the template left its completion time
+            const int nmw = item.n_mounted_workers > 0 ? item.n_mounted_workers : H.orig_workers;
+            double hj = 0.0;
+            if (fast) hj = __ldcg(&a.hint_jct[ch.template_id]);
+            x.util_jct = (hj > 0.0 && !isinf(hj)) ? hj : 0.0;
+            x.util_dn = (double)nmw;
             LaneResult R;
             if (fast) R = simple ? thread_lookahead<false, true>(x) : thread_lookahead<false, false>(x);
             else R = simple ? thread_lookahead<true, true>(x) : thread_lookahead<true, false>(x);
@@ -678,21 +684,24 @@ __global__ void __launch_bounds__(32) ramp_lookahead_thread_kernel(const ThreadA
             if (direct && status == RAMP_ST_OK && R.tick_no != hint.n_ticks) status = RAMP_ST_TRACE_OVERFLOW;   // cannot happen
             if (!fast && status == RAMP_ST_OK) {                      // every lane of the chunk writes the same values
                 *reinterpret_cast<int4*>(&a.hints[ch.template_id]) = make_int4(R.tick_no, R.max_o, R.max_f, R.max_nf);
+                a.hint_jct[ch.template_id] = __dmul_rn(R.t, (double)H.num_training_steps);
             }
 
             // ---- results (RCE:450-452) ----
             const int n_rec = R.tick_no < x.tr_cap ? R.tick_no : x.tr_cap;
             const double steps = (double)H.num_training_steps;
             const double jct = __dmul_rn(R.t, steps);
-            const int nmw = item.n_mounted_workers > 0 ? item.n_mounted_workers : H.orig_workers;
             const bool can_util = (status == RAMP_ST_OK);
+            // the in-loop sum divided by the recorded completion time: valid when this lookahead found the very same one
+            const bool util_done = can_util && x.util_jct != 0.0 && jct == x.util_jct;
             if (!direct && a.pool.top != nullptr) {
                 const unsigned long long o = atomicAdd(a.pool.top, (unsigned long long)n_rec);
                 if (o + (unsigned long long)n_rec <= a.pool.len) off = (long long)o;
                 else if (status == RAMP_ST_OK) status = RAMP_ST_TRACE_OVERFLOW;
             }
-            double util = 0.0;
-            {
+            double util = util_done ? R.util : 0.0;
+            if (!(util_done && (direct || off < 0))) {
+                if (util_done) util = 0.0;                 // the loop below recomputes it while it copies the trace
                 // RCE:830-832: util = sum over ticks, in tick order, of (n_active / n_mounted_workers) * (tick / jct).  A term
                 // with n_active == 0 or tick == 0 is +0.0 (jct > 0 finite) and adding +0.0 leaves the non-negative sum as it
                 // is, so those ticks are skipped (about two thirds of them); n_active / n_mounted_workers is re-used while
