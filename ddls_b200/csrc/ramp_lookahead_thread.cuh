@@ -251,7 +251,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
     LaneResult R;
     R.t = 0.0; R.comm = 0.0; R.comp = 0.0; R.util = 0.0; R.tick_no = 0; R.max_o = nO; R.max_f = 0; R.max_nf = 0;
     R.status = (N <= x.n_cap) ? RAMP_ST_OK : RAMP_ST_TABLE_FULL;                                    // cannot happen (eligibility)
-    int ops_completed = 0, deps_completed = 0;
+    int to_complete = N + E;              // ops and deps still to complete (JOB:549-551)
     const bool do_util = x.util_jct != 0.0;
     int util_last_n = -1;
     double util_last_q = 0.0;
@@ -260,8 +260,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
         if (n_active != util_last_n) { util_last_n = n_active; util_last_q = __ddiv_rn((double)n_active, x.util_dn); }
         R.util = __dadd_rn(R.util, __dmul_rn(util_last_q, __ddiv_rn(tick, x.util_jct)));
     };
-    int32_t* tn_ptr = x.tr_n;
-    double* tt_ptr = x.tr_tick;
+    int tr_idx = 0;                       // trace element k lives at [k * tr_stride]
 
     while (R.status == RAMP_ST_OK) {
         if (nF <= RAMP_T_FASTF && nO <= 2) {
@@ -286,7 +285,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 }
                 if (ow0) { const u64_t r0 = rem_bits(orr[0]); t_op = (r0 < t_op) ? r0 : t_op; n_active += (int)((uint32_t)orr[0].w >> 16); }
             }
-            // ---- C, D, E, I, J, H: ONE dispatch on the number of ready flow entries; each case is straight-line code ----
+            // ---- C, D, E, I, J, H: dispatched ONCE on the number of ready flow entries; each case is straight-line code ----
             const bool any_nf = nNF > 0;
             u64_t tick_b = 0ull;
             double tick = 0.0;
@@ -307,7 +306,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 if (ticked_flows) R.comm = __dadd_rn(R.comm, tick);                                  // RCE:434-439, 777-791
                 if (n_active > 0) { R.comp = __dadd_rn(R.comp, tick); if (do_util && tick_b != 0ull) add_util(n_active, tick); }
                 R.t = __dadd_rn(R.t, tick);
-                if (R.tick_no < x.tr_cap) { *tn_ptr = n_active; *tt_ptr = tick; tn_ptr += x.tr_stride; tt_ptr += x.tr_stride; }
+                if (R.tick_no < x.tr_cap) { x.tr_n[tr_idx] = n_active; x.tr_tick[tr_idx] = tick; tr_idx += x.tr_stride; }
                 else R.status = RAMP_ST_TRACE_OVERFLOW;
                 ++R.tick_no;
             };
@@ -333,7 +332,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
 #pragma unroll
                 for (int k = 0; k < NF; ++k) {
                     const u64_t rb = rem_bits(fr[k]);
-                    if (rb <= tick_b) { complete_dep((uint32_t)fr[k].w); ++deps_completed; }        // JOB:561-562
+                    if (rb <= tick_b) { complete_dep((uint32_t)fr[k].w); --to_complete; }        // JOB:561-562
                     else {
                         const double r2 = __dsub_rn(__longlong_as_double((long long)rb), tick);
                         fr[k].x = __double2loint(r2); fr[k].y = __double2hiint(r2); x.f_sm[p * 32 + lane] = fr[k]; ++p;
@@ -341,29 +340,27 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 }
                 nF = p;
             };
-            switch (any_nf ? -1 : nF) {
-                case -1:                                            // zero-length tick that completes the ready non-flow deps
-                    take_tick(0ull, false);
-                    _Pragma("unroll 1")
-                    for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
-                    deps_completed += nNF;
-                    nNF = 0;
-                    break;
-                case 0: take_tick(RAMP_INF_BITS, false); break;
-                case 1: flow_tick(std::integral_constant<int, 1>{}); break;
-                case 2: flow_tick(std::integral_constant<int, 2>{}); break;
-                case 3: flow_tick(std::integral_constant<int, 3>{}); break;
-                case 4: flow_tick(std::integral_constant<int, 4>{}); break;
-                case 5: flow_tick(std::integral_constant<int, 5>{}); break;
-                default: flow_tick(std::integral_constant<int, 6>{}); break;
-            }
+            // by frequency on the quotient of a partitioned job: one ready flow entry, a non-flow tick, none, two, ...
+            if (any_nf) {                                           // zero-length tick that completes the ready non-flow deps
+                take_tick(0ull, false);
+                _Pragma("unroll 1")
+                for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
+                to_complete -= nNF;
+                nNF = 0;
+            } else if (nF == 1) flow_tick(std::integral_constant<int, 1>{});
+            else if (nF == 0) take_tick(RAMP_INF_BITS, false);
+            else if (nF == 2) flow_tick(std::integral_constant<int, 2>{});
+            else if (nF == 3) flow_tick(std::integral_constant<int, 3>{});
+            else if (nF == 4) flow_tick(std::integral_constant<int, 4>{});
+            else if (nF == 5) flow_tick(std::integral_constant<int, 5>{});
+            else flow_tick(std::integral_constant<int, 6>{});
             // ---- G ----
             int p = 0;
             auto tick_op = [&](int4 r, const int op, const bool win) {
                 if (win) {                                                                          // this tick's winner
                     const u64_t rb = rem_bits(r);
                     if (rb <= tick_b) {                                                             // JOB:555-556
-                        ++ops_completed;
+                        --to_complete;
                         const int2 row = op_row[op];
                         _Pragma("unroll 1")
                         for (int e = row.x; e < row.x + row.y; ++e) {                               // JOB:496-506
@@ -395,8 +392,8 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 R.max_f = (nF > R.max_f) ? nF : R.max_f;
                 R.max_nf = (nNF > R.max_nf) ? nNF : R.max_nf;
             }
-            if ((ops_completed == N) && (deps_completed == E)) break;                               // JOB:549-551
-            if (tick_b == (u64_t)RAMP_INF_BITS) { R.status = RAMP_ST_INFINITE_TICK; break; }        // RCE:462
+            if (to_complete == 0) break;                                                            // JOB:549-551
+            if ((uint32_t)(tick_b >> 32) == 0x7FF00000u) { R.status = RAMP_ST_INFINITE_TICK; break; } // RCE:462
             continue;
         }
         // ---- A, B: winners per worker group: largest key; t_op = min of their remaining times ----
@@ -511,7 +508,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             if ((!any_nf) && (nF > 0)) R.comm = __dadd_rn(R.comm, tick);                             // RCE:434-439, 777-791
             if (n_active > 0) { R.comp = __dadd_rn(R.comp, tick); if (do_util && tick_b != 0ull) add_util(n_active, tick); }
             R.t = __dadd_rn(R.t, tick);
-            if (R.tick_no < x.tr_cap) { *tn_ptr = n_active; *tt_ptr = tick; tn_ptr += x.tr_stride; tt_ptr += x.tr_stride; }
+            if (R.tick_no < x.tr_cap) { x.tr_n[tr_idx] = n_active; x.tr_tick[tr_idx] = tick; tr_idx += x.tr_stride; }
             else R.status = RAMP_ST_TRACE_OVERFLOW;
             ++R.tick_no;
         }
@@ -529,7 +526,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
         if (any_nf) {
             _Pragma("unroll 1")
             for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
-            deps_completed += nNF;
+            to_complete -= nNF;
             nNF = 0;
         } else {
             int p = 0;
@@ -537,7 +534,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             for (int k = 0; k < nF; ++k) {
                 int4 f = flows.get(k);
                 const u64_t rb = rem_bits(f);
-                if (rb <= tick_b) { complete_dep((uint32_t)f.w); ++deps_completed; }                // JOB:561-562
+                if (rb <= tick_b) { complete_dep((uint32_t)f.w); --to_complete; }                // JOB:561-562
                 else {
                     const double r2 = __dsub_rn(__longlong_as_double((long long)rb), tick);
                     f.x = __double2loint(r2); f.y = __double2hiint(r2); flows.put(p, f); ++p;
@@ -558,7 +555,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             if (win) {                                                                              // this tick's winner
                 const u64_t rb = rem_bits(r);
                 if (rb <= tick_b) {                                                                 // JOB:555-556
-                    ++ops_completed;
+                    --to_complete;
                     const int2 row = op_row[op];
                     _Pragma("unroll 1")
                     for (int e = row.x; e < row.x + row.y; ++e) {                                   // JOB:496-506
@@ -585,8 +582,8 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             R.max_nf = (nNF > R.max_nf) ? nNF : R.max_nf;
         }
         // ---- K, L ----
-        if ((ops_completed == N) && (deps_completed == E)) break;                                   // JOB:549-551
-        if (tick_b == (u64_t)RAMP_INF_BITS) { R.status = RAMP_ST_INFINITE_TICK; break; }            // RCE:462
+        if (to_complete == 0) break;                                                                // JOB:549-551
+        if ((uint32_t)(tick_b >> 32) == 0x7FF00000u) { R.status = RAMP_ST_INFINITE_TICK; break; }     // RCE:462
     }
     return R;
 }
