@@ -99,7 +99,8 @@ def workload_config(args, cfg, templates, world, B):
     return {'workload': args.config, 'episodes_per_gpu': B, 'segment': args.segment,
             'cluster': 'x'.join(map(str, cfg['shape'])) + ' RAMP', 'degrees': list(cfg['degrees']),
             'templates': [[t.n_ops, t.n_deps] for t in templates], 'run_times': args.run_times, 'memo_mode': args.memo_mode,
-            'agent': 'random partition degree + first-fit blocks (stand-in for the PAC-ML GNN policy)'}
+            'agent': 'scripted: partition degree drawn from `degrees` + first-fit blocks -- the same decision rule in both arms; the same '
+                     'rollouts driven by the GNN policy on the device are reported in batched_env.device_gnn_policy'}
 
 
 # ---------------------------------------------------------------------------------------------------------
