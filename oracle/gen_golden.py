@@ -40,6 +40,7 @@ from ddls.environments.ramp_job_partitioning.ramp_job_partitioning_environment i
 from ddls.environments.ramp_cluster.ramp_cluster_environment import RampClusterEnvironment  # noqa: E402
 from ddls.devices.processors.gpus.A100 import A100  # noqa: E402
 from ddls.distributions.fixed import Fixed  # noqa: E402
+from ddls.distributions.distribution import Distribution  # noqa: E402
 from ddls.distributions.uniform import Uniform  # noqa: E402
 from ddls.environments.ramp_job_partitioning.agents.sip_ml import SiPML  # noqa: E402
 from ddls.environments.ramp_job_partitioning.agents.random import Random  # noqa: E402
@@ -133,16 +134,29 @@ class Recorder:
             setattr(RampClusterEnvironment, k, f)
 
 
+class Exponential(Distribution):
+    """Exponential inter-arrival times (BASELINE config 5); the reference ships no such distribution, its JobsGenerator only
+    calls .sample() (jobs_generator.py).  Drawn from numpy's global generator like the reference's own distributions, so the
+    episode stays a function of the seed."""
+
+    def __init__(self, mean):
+        self.mean = float(mean)
+
+    def sample(self, size=None):
+        return float(np.random.exponential(self.mean)) if size is None else np.random.exponential(self.mean, size=size)
+
+
 def make_env(graph_dir, shape, n_jobs, max_partitions, interarrival, frac_dist, max_sim_time=1e6, quantum=0.01,
              num_training_steps=50, sampling_mode='remove', num_channels=1):
     c, r, s = shape
+    interarrival_dist = Exponential(interarrival[1]) if isinstance(interarrival, tuple) else Fixed(val=interarrival)
     return RampJobPartitioningEnvironment(
         topology_config={'type': 'ramp', 'kwargs': {'num_communication_groups': c, 'num_racks_per_communication_group': r,
                                                     'num_servers_per_rack': s, 'num_channels': num_channels,
                                                     'total_node_bandwidth': 1.6e12,
                                                     'intra_gpu_propagation_latency': 50e-9, 'worker_io_latency': 100e-9}},
         node_config={'type_1': {'num_nodes': c * r * s, 'workers_config': [{'num_workers': 1, 'worker': A100}]}},
-        jobs_config={'path_to_files': graph_dir, 'job_interarrival_time_dist': Fixed(val=interarrival),
+        jobs_config={'path_to_files': graph_dir, 'job_interarrival_time_dist': interarrival_dist,
                      'max_acceptable_job_completion_time_frac_dist': frac_dist, 'replication_factor': n_jobs,
                      'job_sampling_mode': sampling_mode, 'num_training_steps': num_training_steps, 'shuffle_files': True},
         max_partitions_per_op=max_partitions, min_op_run_time_quantum=quantum, reward_function='job_acceptance',
@@ -182,6 +196,14 @@ CASES = {
                                interarrival=1000.0, frac=(1.0, 1.0), actor='sipml', seed=1),
     'resnet64_deg2_full': dict(graphs=[synth.resnet_like_graph()], shape=(4, 4, 4), n_jobs=1, max_partitions=2,
                                interarrival=1000.0, frac=(1.0, 1.0), actor='sipml', seed=1),
+    # BASELINE configs 4 and 5 at sizes the Python reference finishes in about a minute: clusters of 256 and 128 workers (bit sets
+    # of 4 and 2 words in the batched environments), the configs' BERT-like / ResNet-50-like / GPT-2-like job graphs at full
+    # size with small partition degrees, exponential arrivals
+    'bert256_shard': dict(graphs=[synth.transformer_like_graph(n_layers=12, name='bert_base_like', seed=2)], shape=(8, 8, 4), n_jobs=4,
+                          max_partitions=8, interarrival=700.0, frac=(0.3, 1.0), actor='sipml', seed=31),
+    'mix128_exp': dict(graphs=[synth.resnet_like_graph(), synth.transformer_like_graph(n_layers=12, name='gpt2_small_like', seed=5, gpt=True)],
+                       shape=(8, 4, 4), n_jobs=3, max_partitions=4, interarrival=('exponential', 500.0), frac=(0.2, 1.0), actor='random',
+                       seed=32),
     'residual32_deg16': dict(graphs=[synth.residual_small_graph()], shape=(4, 4, 2), n_jobs=3, max_partitions=16,
                              interarrival=1000.0, frac=(0.1, 1.0), actor='sipml', seed=1),
 }

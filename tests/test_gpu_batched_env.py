@@ -25,10 +25,13 @@ def _graphs():
         'residual32_deg16': [synth.residual_small_graph()],
         'resnet64_deg16_full': [synth.resnet_like_graph()], 'resnet64_deg8_full': [synth.resnet_like_graph()],
         'resnet64_deg4_full': [synth.resnet_like_graph()], 'resnet64_deg2_full': [synth.resnet_like_graph()],
+        # BASELINE configs 4 / 5: 256- and 128-worker clusters (occupancy bit sets of 4 and 2 words)
+        'bert256_shard': [synth.transformer_like_graph(n_layers=12, name='bert_base_like', seed=2)],
+        'mix128_exp': [synth.resnet_like_graph(), synth.transformer_like_graph(n_layers=12, name='gpt2_small_like', seed=5, gpt=True)],
     }
 
 
-SHAPES = {8: (2, 2, 2), 16: (2, 2, 4), 32: (4, 4, 2), 64: (4, 4, 4)}
+SHAPES = {8: (2, 2, 2), 16: (2, 2, 4), 32: (4, 4, 2), 64: (4, 4, 4), 128: (8, 4, 4), 256: (8, 8, 4)}
 # episodes that share a topology and a max_simulation_run_time run in ONE batch
 BATCHES = [
     ['chain8', 'chain8_busy', 'residual8_deg4', 'chain8', 'chain8_busy'],
@@ -36,6 +39,8 @@ BATCHES = [
     ['mixed16', 'res16_flood', 'mixed16'],
     ['tfm32_acceptable', 'residual32_deg16'],
     ['mixed64_busy', 'resnet64_deg2_full', 'resnet64_deg4_full', 'resnet64_deg8_full', 'resnet64_deg16_full'],
+    ['mix128_exp', 'mix128_exp'],
+    ['bert256_shard'],
 ]
 
 

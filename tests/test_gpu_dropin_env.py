@@ -10,7 +10,7 @@ from golden_io import Golden
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = {8: (2, 2, 2), 16: (2, 2, 4), 32: (4, 4, 2), 64: (4, 4, 4)}
+SHAPES = {8: (2, 2, 2), 16: (2, 2, 4), 32: (4, 4, 2), 64: (4, 4, 4), 128: (8, 4, 4), 256: (8, 8, 4)}
 
 
 def _make_env(g):

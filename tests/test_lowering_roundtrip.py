@@ -28,7 +28,7 @@ class _Cluster:
 @pytest.mark.parametrize('fname', golden_files())
 def test_roundtrip_golden_templates(fname):
     g = Golden(fname)
-    shape = {8: (2, 2, 2), 16: (2, 2, 4), 32: (4, 4, 2), 64: (4, 4, 4)}[g.n_cluster_workers]
+    shape = {8: (2, 2, 2), 16: (2, 2, 4), 32: (4, 4, 2), 64: (4, 4, 4), 128: (8, 4, 4), 256: (8, 8, 4)}[g.n_cluster_workers]
     cluster = _Cluster(shape)
     for t, lj in enumerate(g.templates):
         orig = synthetic.build_original_job(job_id=t, model=f'm{lj.model_id}', orig_op_mem=1.0, orig_dep_size=2.0,

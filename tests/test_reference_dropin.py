@@ -18,7 +18,8 @@ import pytest
 from golden_io import Golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CASES = ['chain8', 'chain8_busy', 'chain8_maxtime', 'mixed16', 'res16_flood', 'residual8_deg4', 'tfm32_acceptable', 'mixed64_busy']
+CASES = ['chain8', 'chain8_busy', 'chain8_maxtime', 'mixed16', 'res16_flood', 'residual8_deg4', 'tfm32_acceptable', 'mixed64_busy',
+         'mix128_exp']            # 128 workers, exponential arrivals (BASELINE config 5 in small)
 
 
 def _reference_available():
