@@ -45,8 +45,8 @@ UNIT = 'env-steps/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=32)
-    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=256)
+    ap.add_argument('--warmup', type=int, default=16)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='cfg3-resnet50-64w')
     ap.add_argument('--episodes', type=int, default=0, help='episodes per GPU (0 = the config\'s batch size)')

@@ -262,7 +262,7 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
     };
     int tr_idx = 0;                       // trace element k lives at [k * tr_stride]
 
-    while (R.status == RAMP_ST_OK) {
+    if (R.status == RAMP_ST_OK) for (;;) {       // left through ONE combined exit test per tick
         if (nF <= RAMP_T_FASTF && nO <= 2) {
             // ======== small frontiers (the usual case on a quotient): every ready item is loaded ONCE into registers and each
             // phase runs code specialised for the exact number of ready ops (0-2) and flows (0-4): winners by pairwise
@@ -392,8 +392,10 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 R.max_f = (nF > R.max_f) ? nF : R.max_f;
                 R.max_nf = (nNF > R.max_nf) ? nNF : R.max_nf;
             }
-            if (to_complete == 0) break;                                                            // JOB:549-551
-            if ((uint32_t)(tick_b >> 32) == 0x7FF00000u) { R.status = RAMP_ST_INFINITE_TICK; break; } // RCE:462
+            if ((to_complete == 0) | ((uint32_t)(tick_b >> 32) == 0x7FF00000u) | (R.status != RAMP_ST_OK)) {
+                if (to_complete != 0 && (uint32_t)(tick_b >> 32) == 0x7FF00000u) R.status = RAMP_ST_INFINITE_TICK;   // JOB:549-551 first, then RCE:462
+                break;
+            }
             continue;
         }
         // ---- A, B: winners per worker group: largest key; t_op = min of their remaining times ----
@@ -582,8 +584,10 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
             R.max_nf = (nNF > R.max_nf) ? nNF : R.max_nf;
         }
         // ---- K, L ----
-        if (to_complete == 0) break;                                                                // JOB:549-551
-        if ((uint32_t)(tick_b >> 32) == 0x7FF00000u) { R.status = RAMP_ST_INFINITE_TICK; break; }     // RCE:462
+        if ((to_complete == 0) | ((uint32_t)(tick_b >> 32) == 0x7FF00000u) | (R.status != RAMP_ST_OK)) {
+            if (to_complete != 0 && (uint32_t)(tick_b >> 32) == 0x7FF00000u) R.status = RAMP_ST_INFINITE_TICK;       // JOB:549-551 first, then RCE:462
+            break;
+        }
     }
     return R;
 }
@@ -673,7 +677,11 @@ __global__ void __launch_bounds__(32) ramp_lookahead_thread_kernel(const ThreadA
             double hj = 0.0;
             if (fast) hj = __ldcg(&a.hint_jct[ch.template_id]);
             x.util_jct = (hj > 0.0 && !isinf(hj)) ? hj : 0.0;
-            x.util_dn = (double)nmw;
+            {   // keep the conversion out of the tick loop (the compiler re-materialised it there: one I2F.F64 per tick)
+                double dn = (double)nmw;
+                asm volatile("" : "+d"(dn));
+                x.util_dn = dn;
+            }
             LaneResult R;
             if (fast) R = simple ? thread_lookahead<false, true>(x) : thread_lookahead<false, false>(x);
             else R = simple ? thread_lookahead<true, true>(x) : thread_lookahead<true, false>(x);
