@@ -640,6 +640,21 @@ def run_b200_arm(args, rank, world, local_rank):
                             'note': '32 lookaheads share one warp: warp instructions = per-lookahead instructions x lookaheads / 32'}}
         if roofline['issue_slots']['achieved_warp_inst_per_s']:
             roofline['issue_slots']['frac'] = roofline['issue_slots']['achieved_warp_inst_per_s'] / roofline['issue_slots']['peak_warp_inst_per_s']
+        # end to end = the call a user makes.  Preferred: the batched gym-like surface on the device
+        # (DeviceRampJobPartitioningEnvironment.step(actions[B]) -> obs, reward, done: actions host -> device, observation / reward /
+        # done device -> host through page-locked arrays every step, placement + lowering lookup + rewards + observation inside).
+        # Also reported: one level down, the C-ABI call ramp_step_host with pre-lowered action rows (round 1's e2e).
+        e2e_engine = {'value': e2e_value, 'unit': UNIT, 'api': 'ramp_step_host (C ABI, pre-lowered action rows)',
+                      'h2d_bytes_per_step': int(B * engine.ACTION_DTYPE.itemsize + (arrivals.nbytes / L)),
+                      'd2h_bytes_per_step': int(B * engine.STEP_STATS_LEN * 8)}
+        if batched and isinstance(batched.get('device'), dict) and 'value' in batched['device']:
+            n_act = 17
+            e2e_line = {'value': batched['device']['value'], 'unit': UNIT,
+                        'api': 'ddls_b200.batched.DeviceRampJobPartitioningEnvironment.step(actions) (RJPE.step per episode; host policy: random valid degree)',
+                        'h2d_bytes_per_step': int(B * 4), 'd2h_bytes_per_step': int(B * (8 + 1 + 4 + 44 + n_act) + 20),
+                        'ms_per_step': batched['device']['ms_per_step']}
+        else:
+            e2e_line = dict(e2e_engine)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
@@ -649,9 +664,8 @@ def run_b200_arm(args, rank, world, local_rank):
                               'lists) in shared memory; per step it writes %.1f MB of tick traces to HBM; no explicit flush' % _trace_mb(kt),
                            parallelism=f'episodes sharded x{world}, one NCCL all-gather of episode metrics every {gather_every} steps (per batch of rollouts), on a side stream' if world > 1
                                        else 'single GPU'),
-            'e2e': {'value': e2e_value, 'unit': UNIT,
-                    'h2d_bytes_per_step': int(B * engine.ACTION_DTYPE.itemsize + (arrivals.nbytes / L)),
-                    'd2h_bytes_per_step': int(B * engine.STEP_STATS_LEN * 8)},
+            'e2e': e2e_line,
+            'e2e_engine': e2e_engine,
             'gpu_launches': int(launches),
             'roofline': roofline,
             'memo': {'lookups': memo['lookups'], 'hits': memo['hits'],

@@ -433,11 +433,18 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         _engine._check(L.ramp_env_create(self.eng._h, C.byref(cfg)))
         self._table_set = set()
         B, A = self.B, D + 1
-        self._reward = np.zeros(B, dtype=np.float64)
-        self._done = np.zeros(B, dtype=np.uint8)
-        self._qmodel = np.zeros(B, dtype=np.int32)
-        self._obs_dyn = np.zeros((B, 11), dtype=np.float32)
-        self._mask = np.zeros((B, A), dtype=np.uint8)
+        # page-locked host arrays for the per-step transfers (actions in; reward / done / observation out): numpy views
+        mirror = self._buffers('ramp_env_host_mirror')
+
+        def view(ptr, ctype, shape):
+            n = int(np.prod(shape))
+            return np.ctypeslib.as_array((ctype * n).from_address(ptr)).reshape(shape)
+        self._actions_pinned = view(mirror['actions'], C.c_int32, (B,))
+        self._reward = view(mirror['reward'], C.c_double, (B,))
+        self._done = view(mirror['done'], C.c_uint8, (B,))
+        self._qmodel = view(mirror['queued_model'], C.c_int32, (B,))
+        self._obs_dyn = view(mirror['obs_dynamic'], C.c_float, (B, 11))
+        self._mask = view(mirror['action_mask'], C.c_uint8, (B, A))
         self._need = np.zeros(B, dtype=np.int32)
         self._prewarmed = False
         if prewarm:
@@ -481,13 +488,18 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         return self._geom_index.setdefault(key, len(self._geom_index))
 
     def device_buffers(self):
+        return self._buffers('ramp_env_buffers')
+
+    def _buffers(self, fn):
         import ctypes as C
 
         class _Buf(C.Structure):
             _fields_ = ([(n, C.c_void_p) for n in ('actions', 'reward', 'done', 'queued_model', 'obs_dynamic', 'action_mask', 'busy', 'template_id')]
                         + [(n, C.c_int32) for n in ('n_episodes', 'n_actions', 'n_models')])
         b = _Buf()
-        _engine._check(self.eng._L.ramp_env_buffers(self.eng._h, C.byref(b)))
+        getattr(self.eng._L, fn).restype = C.c_int
+        getattr(self.eng._L, fn).argtypes = [C.c_void_p, C.c_void_p]
+        _engine._check(getattr(self.eng._L, fn)(self.eng._h, C.byref(b)))
         return {n: getattr(b, n) for n, _ in _Buf._fields_}
 
     @property
@@ -530,14 +542,19 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         n_need = C.c_int32(0)
         a_ptr = None
         if actions is not None:
-            actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.B)
+            self._actions_pinned[:] = np.asarray(actions).reshape(self.B)
+            actions = self._actions_pinned
             a_ptr = actions.ctypes.data
-        _engine._check(L.ramp_env_decide(h, a_ptr, C.byref(n_need), self._need.ctypes.data))
-        if n_need.value > 0:
-            self._decide_on_host(self._need[:n_need.value].copy(), actions)
+        if self._device_decides_everything:
+            # no episode can need the host's placer: nothing to wait for between the decision and the cluster step (an invalid
+            # action still raises, at the read below)
+            _engine._check(L.ramp_env_decide(h, a_ptr, None, None))
+        else:
+            _engine._check(L.ramp_env_decide(h, a_ptr, C.byref(n_need), self._need.ctypes.data))
+            if n_need.value > 0:
+                self._decide_on_host(self._need[:n_need.value].copy(), actions)
         _engine._check(L.ramp_env_advance(h))
-        obs = self._read()
-        self.eng.check_status()
+        obs = self._read()                                     # ONE synchronisation per step; raises simulation errors too
         self.step_counter += 1
         return obs, self._reward.copy(), self.done.copy(), {}
 

@@ -162,7 +162,8 @@ struct ramp_engine {
     bool has_env = false;
     EnvDev env{};
     std::vector<void*> env_allocs;
-    int32_t* env_h_need = nullptr;       // pinned: [0] = count, [1] = error flag; [2], [3]: the same, read by ramp_env_read
+    int32_t* env_h_need = nullptr;       // pinned: [0] = count, [1] = error flag; [2], [3]: the same, read by ramp_env_read; [4] engine error episode
+    void* env_h_mirror = nullptr;        // pinned host arrays (ramp_env_host_mirror)
     bool env_unchecked_decide = false;   // a ramp_env_decide without need_host_out has not been looked at yet
     // standalone lookahead buffers
     WorkItem* sa_chunk_items = nullptr;
@@ -619,6 +620,7 @@ int ramp_engine_destroy(ramp_engine_t* e) {
     for (void* pa : e->env_allocs) cudaFree(pa);
     cudaFree(e->ep.tick_util); cudaFree(e->ep.tick_util_n);
     if (e->env_h_need) cudaFreeHost(e->env_h_need);
+    if (e->env_h_mirror) cudaFreeHost(e->env_h_mirror);
     cudaFree(e->d_items_res); cudaFree(e->d_chunk_items); cudaFree(e->d_chunks); cudaFree(e->d_tcount); cudaFree(e->d_tbase); cudaFree(e->d_rank); cudaFree(e->d_hints); cudaFree(e->d_hint_jct);
     cudaFree(e->d_res_scratch); cudaFree(e->sa_chunk_items); cudaFree(e->sa_chunks);
     cudaFree(e->d_templates); cudaFree(e->d_memo_keys); cudaFree(e->d_memo_vals); cudaFree(e->d_memo_keys2);
@@ -1287,7 +1289,7 @@ int ramp_env_create(ramp_engine_t* e, const ramp_env_config_t* c) {
     if ((rc = env_upload<int32_t>(e, &v.need_host, nullptr, (size_t)B))) return rc;
     if ((rc = env_upload<int32_t>(e, &v.n_need_host, nullptr, 1))) return rc;
     if ((rc = env_upload<int32_t>(e, &v.err, nullptr, 1))) return rc;
-    CUDA_TRY(cudaMallocHost(&e->env_h_need, sizeof(int32_t) * 4));
+    CUDA_TRY(cudaMallocHost(&e->env_h_need, sizeof(int32_t) * 8));
     e->has_env = true;
     return RAMP_OK;
 }
@@ -1330,6 +1332,24 @@ int ramp_env_buffers(ramp_engine_t* e, ramp_env_buffers_t* out) {
     const EnvDev& v = e->env;
     out->actions = v.actions; out->reward = v.reward; out->done = v.done; out->queued_model = v.queued_model;
     out->obs_dynamic = v.obs_dyn; out->action_mask = v.action_mask; out->busy = (uint64_t*)v.busy; out->template_id = v.tid;
+    out->n_episodes = v.B; out->n_actions = v.max_degree + 1; out->n_models = v.n_models;
+    return RAMP_OK;
+}
+
+int ramp_env_host_mirror(ramp_engine_t* e, ramp_env_buffers_t* out) {
+    if (!e || !e->has_env || !out) return set_error(RAMP_ERR_BAD_ARG, "no environment");
+    const EnvDev& v = e->env;
+    const size_t B = (size_t)v.B, A = (size_t)v.max_degree + 1;
+    const size_t o_reward = 0, o_obs = o_reward + 8 * B, o_act = o_obs + 44 * B, o_qm = o_act + 4 * B, o_done = o_qm + 4 * B, o_mask = o_done + B;
+    if (!e->env_h_mirror) {
+        CUDA_TRY(cudaSetDevice(e->cfg.device));
+        CUDA_TRY(cudaMallocHost(&e->env_h_mirror, o_mask + B * A + 64));
+        memset(e->env_h_mirror, 0, o_mask + B * A + 64);
+    }
+    unsigned char* m = (unsigned char*)e->env_h_mirror;
+    memset(out, 0, sizeof(*out));
+    out->reward = (double*)(m + o_reward); out->obs_dynamic = (float*)(m + o_obs); out->actions = (int32_t*)(m + o_act);
+    out->queued_model = (int32_t*)(m + o_qm); out->done = m + o_done; out->action_mask = m + o_mask;
     out->n_episodes = v.B; out->n_actions = v.max_degree + 1; out->n_models = v.n_models;
     return RAMP_OK;
 }
@@ -1407,6 +1427,7 @@ int ramp_env_read(ramp_engine_t* e, double* reward, uint8_t* done, int32_t* queu
     if (queued_model) CUDA_TRY(cudaMemcpyAsync(queued_model, v.queued_model, sizeof(int32_t) * v.B, cudaMemcpyDeviceToHost, st));
     if (obs_dynamic) CUDA_TRY(cudaMemcpyAsync(obs_dynamic, v.obs_dyn, sizeof(float) * 11 * v.B, cudaMemcpyDeviceToHost, st));
     if (action_mask) CUDA_TRY(cudaMemcpyAsync(action_mask, v.action_mask, (size_t)v.B * (v.max_degree + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(e->env_h_need + 4, &e->d_counters->err_episode, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (e->env_unchecked_decide) {
         // decisions taken without the host looking (a device-resident policy): an invalid action under apply_action_mask is sticky
         // in `err`; episodes the tables could not decide were left unplaced, which only the LAST decide's count can show
@@ -1421,9 +1442,13 @@ int ramp_env_read(ramp_engine_t* e, double* reward, uint8_t* done, int32_t* queu
         }
         if (e->env_h_need[2] != 0)
             return set_error(RAMP_ERR_BAD_ARG, "%d episodes needed the host's placer but ramp_env_decide was called without need_host_out", e->env_h_need[2]);
-        return RAMP_OK;
+        return e->env_h_need[4] != 0 ? ramp_check_status(e, nullptr, nullptr) : RAMP_OK;
     }
-    return ramp_sync(e);
+    {
+        int rc = ramp_sync(e);
+        if (rc != RAMP_OK) return rc;
+    }
+    return e->env_h_need[4] != 0 ? ramp_check_status(e, nullptr, nullptr) : RAMP_OK;
 }
 
 

@@ -361,6 +361,10 @@ typedef struct {
     int32_t   n_episodes, n_actions, n_models;   /* B, max_degree + 1, job types                                    */
 } ramp_env_buffers_t;
 
+/* page-locked HOST arrays of the same shapes (valid until the engine is destroyed): give them to ramp_env_decide / ramp_env_read
+ * so that the per-step copies are true asynchronous DMA transfers (busy / template_id are not mirrored: NULL) */
+int ramp_env_host_mirror(ramp_engine_t* eng, ramp_env_buffers_t* out);
+
 int ramp_env_create(ramp_engine_t* eng, const ramp_env_config_t* cfg);
 int ramp_env_set_template(ramp_engine_t* eng, int32_t model, int32_t degree, int32_t geom, int32_t template_id, const double mount[6]);
 /* model_of / frac / max_acceptable_jct (NaN = frac x sequential time): HOST [n_episodes][jobs_per_episode]; arrivals as ramp_reset */
@@ -385,6 +389,7 @@ int ramp_get_last_step_stats(ramp_engine_t* eng, double* stats_out, int32_t* n_c
 /* HOST copies of the occupancy [n_episodes][n_words], of the actions the device holds, and of the number of decisions every episode
  * has taken since ramp_env_reset (= its env-steps; a finished episode takes none) -- any may be NULL */
 int ramp_env_read_state(ramp_engine_t* eng, uint64_t* busy_out, int32_t* actions_out, int32_t* n_decided_out);
+/* also raises what ramp_check_status would (RAMP_ERR_SIM) -- one synchronisation per step for a host-side policy */
 int ramp_env_read(ramp_engine_t* eng, double* reward, uint8_t* done, int32_t* queued_model, float* obs_dynamic, uint8_t* action_mask);
 
 
