@@ -447,6 +447,7 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
         self._mask = view(mirror['action_mask'], C.c_uint8, (B, A))
         self._need = np.zeros(B, dtype=np.int32)
         self._prewarmed = False
+        self._decides_all = None
         if prewarm:
             self.prewarm()
 
@@ -479,8 +480,12 @@ class DeviceRampJobPartitioningEnvironment(BatchedRampJobPartitioningEnvironment
 
     @property
     def _device_decides_everything(self):
-        valid = [d for d in range(1, self.max_partitions_per_op + 1) if self._shape_ok[d] and d <= self.W]
-        return self._prewarmed and all(self._uniform[m, d] for m in range(len(self.models)) for d in valid)
+        if not self._prewarmed:
+            return False
+        if self._decides_all is None:
+            valid = [d for d in range(1, self.max_partitions_per_op + 1) if self._shape_ok[d] and d <= self.W]
+            self._decides_all = all(bool(self._uniform[m, d]) for m in range(len(self.models)) for d in valid)
+        return self._decides_all
 
     def _geometry(self, coords):
         ranks = [{v: i for i, v in enumerate(sorted({c[ax] for c in coords}))} for ax in range(3)]

@@ -7,11 +7,13 @@ import numpy as np
 
 sys.path.insert(0, '.')
 from ddls_b200 import workload
-from ddls_b200.batched import BatchedRampJobPartitioningEnvironment
+from ddls_b200.batched import BatchedRampJobPartitioningEnvironment, DeviceRampJobPartitioningEnvironment
 
 cfg = workload.CONFIGS['cfg3-resnet50-64w']
 graphs = [workload.make_graph(k, **kw) for k, kw in cfg['graphs']]
-env = BatchedRampJobPartitioningEnvironment(tuple(cfg['shape']), graphs, n_episodes=4096, jobs_per_episode=8, seed=1)
+device = len(sys.argv) > 1 and sys.argv[1] == "device"
+env = (DeviceRampJobPartitioningEnvironment(tuple(cfg["shape"]), graphs, n_episodes=4096, jobs_per_episode=8, seed=1, prewarm=True) if device
+       else BatchedRampJobPartitioningEnvironment(tuple(cfg["shape"]), graphs, n_episodes=4096, jobs_per_episode=8, seed=1))
 degs = np.array([2, 4, 8, 16])
 rng = np.random.default_rng(0)
 
@@ -33,7 +35,7 @@ def run(n):
 run(8)
 pr = cProfile.Profile()
 pr.enable()
-run(16)
+run(64)
 pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(22)
 print(env.stats)

@@ -23,7 +23,8 @@ sys.path.insert(0, HERE)
 # The reference lists its job files with an UNSORTED glob (jobs_generator.py:96), so which file is "job type 0" depends on the
 # file system's directory order.  These are the orders of the container the golden fixtures were generated in; the driver pins
 # them so that the seeded episodes are the same episodes on every machine.
-FILE_ORDER = {'mixed16': ['res2.txt', 'chain5.txt', 'tfm1.txt'], 'mixed64_busy': ['tfm1b.txt', 'chain4.txt', 'res1.txt']}
+FILE_ORDER = {'mixed16': ['res2.txt', 'chain5.txt', 'tfm1.txt'], 'mixed64_busy': ['tfm1b.txt', 'chain4.txt', 'res1.txt'],
+              'mix128_exp': ['resnet50_like.txt', 'gpt2_small_like.txt']}
 
 EXTRA_CASES = {
     # a generator that never runs dry (the reference's default 'remove_and_repeat' sampling, heuristic_config.yaml:126): the
