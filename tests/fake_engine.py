@@ -19,6 +19,7 @@ class FakeEngine:
         self._env = oracle.OracleEnv(n_cluster_workers, max_jobs=max_jobs, memo_models=64, machine_epsilon=machine_epsilon)
         self._limits = (max_simulation_run_time, job_queue_capacity)
         self._templates = []
+        self._done = 0.0
 
     def close(self):
         self._env = None
@@ -34,6 +35,7 @@ class FakeEngine:
     def reset(self, arrivals):
         arr = np.ascontiguousarray(arrivals, dtype=_engine.ARRIVAL_DTYPE)
         self._env.reset(arr[0], max_simulation_run_time=self._limits[0], job_queue_capacity=self._limits[1])
+        self._done = 0.0
 
     def set_arrivals(self, episode, first_job, rows):
         rows = np.ascontiguousarray(rows, dtype=_engine.ARRIVAL_DTYPE).reshape(-1)
@@ -48,6 +50,13 @@ class FakeEngine:
         a['template_id'] = -1
         return a
 
+    def episode_state(self):
+        out = np.zeros((1, len(_engine.EP_FIELDS)))
+        out[0, _engine.EP['time']] = self._env.time
+        out[0, _engine.EP['queued_job']] = self._env.queued_job
+        out[0, _engine.EP['done']] = self._done
+        return out
+
     def step(self, actions, **_):
         tid = int(actions['template_id'][0])
         job = None
@@ -56,7 +65,9 @@ class FakeEngine:
             a = actions[0]
             job.mount = MountScalars(float(a['max_acceptable_jct']), float(a['part_op_mem']), float(a['part_dep_size']),
                                      float(a['flow_size']), int(a['n_mounted_workers']), int(a['n_mounted_channels']))
-        return self._env.step(job).reshape(1, -1)
+        stats = self._env.step(job).reshape(1, -1)
+        self._done = float(stats[0, _engine.SS['done']])
+        return stats
 
     def enable_tick_lists(self, cap=256):
         pass                      # the oracle always keeps them
