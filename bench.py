@@ -586,34 +586,29 @@ def run_b200_arm(args, rank, world, local_rank):
                 run_times=args.run_times, interarrival=('exponential', 1000.0) if cfg.get('exponential') else ('fixed', 1000.0), prewarm=True)
             pol = policy_mod.DeviceGNNPolicy(graphs_b, benv.max_partitions_per_op + 1, device=local_rank, seed=args.seed)
             pol.embed()
-            for s_ in range(max(W, L)):
-                if s_ % L == 0:
-                    benv.reset()
-                pol.act(benv, sample=True, seed=args.seed + s_)
-                benv.step_device()
-            benv.read()
+            n_seg_w, n_seg = (max(W, L) + L - 1) // L, (K + L - 1) // L
+            for g_ in range(n_seg_w):
+                pol.collect(benv, L, sample=True, seed=args.seed + 100 * g_)
             barrier()
             tb = time.perf_counter()
             n_env_steps_b = 0
-            for s_ in range(K):
-                if s_ % L == 0:
-                    if s_ > 0:
-                        n_env_steps_b += int(benv.decisions().sum())
-                    benv.reset()
-                pol.act(benv, sample=True, seed=args.seed + 1000 + s_)
-                benv.step_device()
-            n_env_steps_b += int(benv.decisions().sum())
-            _, rew_b, _ = benv.read()
+            for g_ in range(n_seg):
+                # one segment = reset + L decisions of the policy per episode on the device, every decision recorded on the device
+                # (observation, action, log-probability, value, reward, done) and read back ONCE: what a trainer consumes
+                traj = pol.collect(benv, L, sample=True, seed=args.seed + 1000 + 100 * g_)
+                n_env_steps_b += int(traj['live'].sum())
             barrier()
             tb = time.perf_counter() - tb
+            K_pol = n_seg * L
             tb_t = torch.tensor([tb], dtype=torch.float64, device='cuda')
             nb_t = torch.tensor([float(n_env_steps_b)], dtype=torch.float64, device='cuda')
             if world > 1:
                 dist.all_reduce(tb_t, op=dist.ReduceOp.MAX)
                 dist.all_reduce(nb_t, op=dist.ReduceOp.SUM)
             batched['device_gnn_policy'] = {
-                'value': float(nb_t[0]) / float(tb_t[0]), 'unit': UNIT, 'ms_per_step': float(tb_t[0]) / K * 1e3,
+                'value': float(nb_t[0]) / float(tb_t[0]), 'unit': UNIT, 'ms_per_step': float(tb_t[0]) / K_pol * 1e3,
                 'policy': 'GNNPolicy (gnn.yaml: 2 MeanPool rounds, msg 32, hidden 64, read-out [256]), random weights, categorical sampling',
+                'trajectory_bytes_per_segment': int(sum(v.nbytes for k_, v in traj.items() if k_ != 'live')),
                 'host_decisions': not benv._device_decides_everything}
             pol.close(); benv.close()
         except Exception as ex:
@@ -622,7 +617,8 @@ def run_b200_arm(args, rank, world, local_rank):
                            'host policy (random valid degree from the action mask), actions in and reward / done / observation out as host '
                            'arrays every step; env-steps of episodes that are not done are counted.  device: decision and bookkeeping as '
                            'ramp_env_* kernels; host: the same in numpy + native C++ with caches; device_gnn_policy: the device environment driven by the '
-                           'GNN policy kernels (ramp_policy_act), wall clock over whole segments including resets')
+                           'GNN policy kernels (DeviceGNNPolicy.collect: every decision recorded on the device, one read-back of the whole '
+                           'trajectory per segment), wall clock over whole segments including resets')
 
     if rank == 0:
         peak, peak_src = measured_peaks()

@@ -359,6 +359,10 @@ struct ramp_policy {
     int32_t fcap = 0;
     int32_t* f_model = nullptr; float* f_gf = nullptr; uint8_t* f_mask = nullptr; int32_t* f_actions = nullptr;
     unsigned long long act_calls = 0;
+    // trajectory of a rollout segment (ramp_policy_trajectory_*): [horizon][B] per field, on the device until read
+    int32_t traj_h = 0, traj_b = 0, traj_a = 0;
+    float* t_obs = nullptr; int32_t* t_model = nullptr; uint8_t* t_mask = nullptr; int32_t* t_action = nullptr;
+    float* t_logp = nullptr; float* t_value = nullptr; double* t_reward = nullptr; uint8_t* t_done = nullptr;
 };
 
 namespace {
@@ -483,6 +487,8 @@ void ramp_policy_destroy(ramp_policy_t* p) {
     cudaFree(p->d_w); cudaFree(p->d_models); cudaFree(p->d_emb); cudaFree(p->d_gstatic);
     cudaFree(p->d_logits); cudaFree(p->d_value); cudaFree(p->d_logp);
     cudaFree(p->f_model); cudaFree(p->f_gf); cudaFree(p->f_mask); cudaFree(p->f_actions);
+    cudaFree(p->t_obs); cudaFree(p->t_model); cudaFree(p->t_mask); cudaFree(p->t_action); cudaFree(p->t_logp); cudaFree(p->t_value);
+    cudaFree(p->t_reward); cudaFree(p->t_done);
     delete p;
 }
 
@@ -623,6 +629,74 @@ int ramp_policy_read(ramp_policy_t* p, ramp_engine_t* eng, float* logits_out, fl
     if (value_out) PCUDA(cudaMemcpyAsync(value_out, p->d_value, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
     if (logp_out) PCUDA(cudaMemcpyAsync(logp_out, p->d_logp, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
     if (actions_out) PCUDA(cudaMemcpyAsync(actions_out, eb.actions, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+    PCUDA(cudaStreamSynchronize(st));
+    return RAMP_OK;
+}
+
+int ramp_policy_trajectory_begin(ramp_policy_t* p, ramp_engine_t* eng, int32_t horizon) {
+    if (!p || !eng || horizon < 1) return perr(RAMP_ERR_BAD_ARG, "policy: bad trajectory horizon");
+    ramp_env_buffers_t eb{};
+    int rc = ramp_env_buffers(eng, &eb);
+    if (rc != RAMP_OK) return rc;
+    PCUDA(cudaSetDevice(p->device));
+    if (horizon == p->traj_h && eb.n_episodes == p->traj_b && eb.n_actions == p->traj_a) return RAMP_OK;
+    PCUDA(cudaStreamSynchronize(ramp_internal_stream(eng)));
+    cudaFree(p->t_obs); cudaFree(p->t_model); cudaFree(p->t_mask); cudaFree(p->t_action); cudaFree(p->t_logp); cudaFree(p->t_value);
+    cudaFree(p->t_reward); cudaFree(p->t_done);
+    p->t_obs = nullptr; p->t_model = nullptr; p->t_mask = nullptr; p->t_action = nullptr; p->t_logp = nullptr; p->t_value = nullptr;
+    p->t_reward = nullptr; p->t_done = nullptr; p->traj_h = 0;
+    const size_t n = (size_t)horizon * (size_t)eb.n_episodes;
+    PCUDA(cudaMalloc(&p->t_obs, sizeof(float) * 11 * n));
+    PCUDA(cudaMalloc(&p->t_model, sizeof(int32_t) * n));
+    PCUDA(cudaMalloc(&p->t_mask, (size_t)eb.n_actions * n));
+    PCUDA(cudaMalloc(&p->t_action, sizeof(int32_t) * n));
+    PCUDA(cudaMalloc(&p->t_logp, sizeof(float) * n));
+    PCUDA(cudaMalloc(&p->t_value, sizeof(float) * n));
+    PCUDA(cudaMalloc(&p->t_reward, sizeof(double) * n));
+    PCUDA(cudaMalloc(&p->t_done, n));
+    p->traj_h = horizon; p->traj_b = eb.n_episodes; p->traj_a = eb.n_actions;
+    return RAMP_OK;
+}
+
+int ramp_policy_trajectory_record(ramp_policy_t* p, ramp_engine_t* eng, int32_t t, int32_t phase) {
+    if (!p || !eng) return perr(RAMP_ERR_BAD_ARG, "null argument");
+    if (p->traj_h < 1 || t < 0 || t >= p->traj_h) return perr(RAMP_ERR_BAD_ARG, "policy: trajectory slot %d outside [0, %d)", t, p->traj_h);
+    ramp_env_buffers_t eb{};
+    int rc = ramp_env_buffers(eng, &eb);
+    if (rc != RAMP_OK) return rc;
+    if (eb.n_episodes != p->traj_b || eb.n_actions != p->traj_a || eb.n_episodes > p->cap)
+        return perr(RAMP_ERR_BAD_ARG, "policy: the trajectory was set up for another environment, or ramp_policy_act was not called");
+    cudaStream_t st = ramp_internal_stream(eng);
+    const size_t B = (size_t)eb.n_episodes, o = (size_t)t * B;
+    if (phase == 0) {           // after ramp_policy_act, before the environment steps: what the policy saw and decided
+        PCUDA(cudaMemcpyAsync(p->t_obs + o * 11, eb.obs_dynamic, sizeof(float) * 11 * B, cudaMemcpyDeviceToDevice, st));
+        PCUDA(cudaMemcpyAsync(p->t_model + o, eb.queued_model, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+        PCUDA(cudaMemcpyAsync(p->t_mask + o * p->traj_a, eb.action_mask, (size_t)p->traj_a * B, cudaMemcpyDeviceToDevice, st));
+        PCUDA(cudaMemcpyAsync(p->t_action + o, eb.actions, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+        PCUDA(cudaMemcpyAsync(p->t_logp + o, p->d_logp, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+        PCUDA(cudaMemcpyAsync(p->t_value + o, p->d_value, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    } else {                    // after the environment stepped: what came back
+        PCUDA(cudaMemcpyAsync(p->t_reward + o, eb.reward, sizeof(double) * B, cudaMemcpyDeviceToDevice, st));
+        PCUDA(cudaMemcpyAsync(p->t_done + o, eb.done, B, cudaMemcpyDeviceToDevice, st));
+    }
+    return RAMP_OK;
+}
+
+int ramp_policy_trajectory_read(ramp_policy_t* p, ramp_engine_t* eng, int32_t n_steps, float* obs_dynamic_out, int32_t* model_out,
+                                uint8_t* action_mask_out, int32_t* action_out, float* logp_out, float* value_out, double* reward_out,
+                                uint8_t* done_out) {
+    if (!p || !eng) return perr(RAMP_ERR_BAD_ARG, "null argument");
+    if (n_steps < 1 || n_steps > p->traj_h) return perr(RAMP_ERR_BAD_ARG, "policy: %d steps asked of a trajectory of %d", n_steps, p->traj_h);
+    cudaStream_t st = ramp_internal_stream(eng);
+    const size_t n = (size_t)n_steps * (size_t)p->traj_b;
+    if (obs_dynamic_out) PCUDA(cudaMemcpyAsync(obs_dynamic_out, p->t_obs, sizeof(float) * 11 * n, cudaMemcpyDeviceToHost, st));
+    if (model_out) PCUDA(cudaMemcpyAsync(model_out, p->t_model, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (action_mask_out) PCUDA(cudaMemcpyAsync(action_mask_out, p->t_mask, (size_t)p->traj_a * n, cudaMemcpyDeviceToHost, st));
+    if (action_out) PCUDA(cudaMemcpyAsync(action_out, p->t_action, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    if (logp_out) PCUDA(cudaMemcpyAsync(logp_out, p->t_logp, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (value_out) PCUDA(cudaMemcpyAsync(value_out, p->t_value, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (reward_out) PCUDA(cudaMemcpyAsync(reward_out, p->t_reward, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (done_out) PCUDA(cudaMemcpyAsync(done_out, p->t_done, n, cudaMemcpyDeviceToHost, st));
     PCUDA(cudaStreamSynchronize(st));
     return RAMP_OK;
 }

@@ -53,6 +53,12 @@ def _bind(L):
     L.ramp_policy_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64]
     L.ramp_policy_read.restype = C.c_int
     L.ramp_policy_read.argtypes = [C.c_void_p, C.c_void_p] + [C.c_void_p] * 4
+    L.ramp_policy_trajectory_begin.restype = C.c_int
+    L.ramp_policy_trajectory_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.ramp_policy_trajectory_record.restype = C.c_int
+    L.ramp_policy_trajectory_record.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    L.ramp_policy_trajectory_read.restype = C.c_int
+    L.ramp_policy_trajectory_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 8
     L._policy_bound = True
 
 
@@ -204,3 +210,30 @@ class DeviceGNNPolicy:
         value, logp, actions = np.zeros(B, dtype=np.float32), np.zeros(B, dtype=np.float32), np.zeros(B, dtype=np.int32)
         _engine._check(self._L.ramp_policy_read(self._h, env.eng._h, logits.ctypes.data, value.ctypes.data, logp.ctypes.data, actions.ctypes.data))
         return {'logits': logits, 'value': value, 'logp': logp, 'actions': actions}
+
+    def collect(self, env, horizon: int, sample: bool = True, seed: int = 0, reset: bool = True):
+        """One rollout segment entirely on the device: ``horizon`` decisions of this policy for every episode of a
+        DeviceRampJobPartitioningEnvironment, recorded on the device, read back ONCE.  Returns arrays [horizon, B, ...]:
+        what the policy saw (``model`` of the queued job, ``graph_features_dynamic``, ``action_mask``), what it did (``action``,
+        ``logp``, ``value``) and what came back (``reward``, ``done`` after the step); ``live`` marks the decisions of episodes that
+        were not finished yet."""
+        L, h = self._L, self._h
+        if reset:
+            env.reset()
+        _engine._check(L.ramp_policy_trajectory_begin(h, env.eng._h, int(horizon)))
+        for t in range(horizon):
+            self.act(env, sample=sample, seed=seed + t)
+            _engine._check(L.ramp_policy_trajectory_record(h, env.eng._h, t, 0))
+            env.step_device()
+            _engine._check(L.ramp_policy_trajectory_record(h, env.eng._h, t, 1))
+        B, A = env.B, self.n_actions
+        out = {'graph_features_dynamic': np.zeros((horizon, B, 11), dtype=np.float32), 'model': np.zeros((horizon, B), dtype=np.int32),
+               'action_mask': np.zeros((horizon, B, A), dtype=np.uint8), 'action': np.zeros((horizon, B), dtype=np.int32),
+               'logp': np.zeros((horizon, B), dtype=np.float32), 'value': np.zeros((horizon, B), dtype=np.float32),
+               'reward': np.zeros((horizon, B), dtype=np.float64), 'done': np.zeros((horizon, B), dtype=np.uint8)}
+        _engine._check(L.ramp_policy_trajectory_read(h, env.eng._h, int(horizon), *[out[k].ctypes.data for k in (
+            'graph_features_dynamic', 'model', 'action_mask', 'action', 'logp', 'value', 'reward', 'done')]))
+        env.read()                                         # raises what a step would have raised (invalid action, simulation errors)
+        out['done'] = out['done'].astype(bool)
+        out['live'] = np.concatenate([np.ones((1, B), dtype=bool), ~out['done'][:-1]], axis=0) & (out['model'] >= 0)
+        return out

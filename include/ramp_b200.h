@@ -440,6 +440,18 @@ int ramp_policy_act(ramp_policy_t* p, ramp_engine_t* eng, int32_t sample, uint64
 /* HOST copies of the last ramp_policy_act: logits [B][n_actions], value [B], log-probability of the chosen action [B], actions [B] (any may be NULL) */
 int ramp_policy_read(ramp_policy_t* p, ramp_engine_t* eng, float* logits_out, float* value_out, float* logp_out, int32_t* actions_out);
 
+/* A rollout segment recorded on the device, for a trainer: ramp_policy_trajectory_begin sizes [horizon][n_episodes] slots;
+ * ramp_policy_trajectory_record(t, 0) after ramp_policy_act stores what the policy saw and decided in slot t (dynamic graph features,
+ * model of the queued job, action mask, action, its log-probability, the value estimate), (t, 1) after ramp_env_advance stores the
+ * reward and done flag that came back -- device-to-device copies on the engine's stream, no synchronisation;
+ * ramp_policy_trajectory_read copies the first n_steps slots to HOST arrays (any may be NULL): ONE transfer per segment instead of
+ * one per step.  (The static part of the observation is a function of `model`: ramp_policy_set_model.) */
+int ramp_policy_trajectory_begin(ramp_policy_t* p, ramp_engine_t* eng, int32_t horizon);
+int ramp_policy_trajectory_record(ramp_policy_t* p, ramp_engine_t* eng, int32_t t, int32_t phase);
+int ramp_policy_trajectory_read(ramp_policy_t* p, ramp_engine_t* eng, int32_t n_steps, float* obs_dynamic_out, int32_t* model_out,
+                                uint8_t* action_mask_out, int32_t* action_out, float* logp_out, float* value_out, double* reward_out,
+                                uint8_t* done_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,3 +185,32 @@ def test_policy_rejects_bad_configurations():
     with pytest.raises(Exception, match='names node'):
         pol.set_model(0, np.zeros((3, 5)), np.zeros((1, 2)), [0], [7], np.zeros(6))
     pol.close()
+
+
+def test_collected_trajectories_equal_step_by_step_reads():
+    """DeviceGNNPolicy.collect keeps a whole segment on the device (decisions, log-probabilities, values, rewards, done flags recorded
+    by device-to-device copies) and reads it back once: the same as acting and reading step by step on an identical environment."""
+    from ddls_b200 import policy as P
+    H = 6
+    env, graphs = _env(B=192, J=H, seed=21)
+    env2, _ = _env(B=192, J=H, seed=21)
+    sd = P.random_state_dict(P.DEFAULT_CONFIG, 17, seed=4)
+    pol, pol2 = P.DeviceGNNPolicy(graphs, 17, None, sd), P.DeviceGNNPolicy(graphs, 17, None, sd)
+    traj = pol.collect(env, H, sample=True, seed=50)
+    obs = env2.reset()
+    for t in range(H):
+        pol2.act(env2, sample=True, seed=50 + t)
+        got = pol2.read(env2)
+        np.testing.assert_array_equal(traj['model'][t], obs['model'])
+        np.testing.assert_array_equal(traj['graph_features_dynamic'][t], obs['graph_features_dynamic'])
+        np.testing.assert_array_equal(traj['action_mask'][t], obs['action_mask'].astype(np.uint8))
+        np.testing.assert_array_equal(traj['action'][t], got['actions'])
+        np.testing.assert_array_equal(traj['logp'][t], got['logp'])
+        np.testing.assert_array_equal(traj['value'][t], got['value'])
+        np.testing.assert_array_equal(traj['live'][t], ~obs['done'])
+        obs, reward, done, _ = env2.step(None)
+        np.testing.assert_array_equal(traj['reward'][t], reward)
+        np.testing.assert_array_equal(traj['done'][t], done)
+    assert traj['done'][-1].all() and (traj['reward'] > 0).any() and (traj['reward'] < 0).any()
+    np.testing.assert_array_equal(env.decisions(), env2.decisions())
+    env.close(); env2.close(); pol.close(); pol2.close()
