@@ -330,6 +330,26 @@ __global__ void __launch_bounds__(256) ramp_policy_head_kernel(const PolicyDev P
     }
 }
 
+// one launch per phase instead of a handful of small device-to-device copies
+struct TrajArgs {
+    int32_t B, A, phase;
+    const float* obs; const int32_t* model; const uint8_t* mask; const int32_t* action; const float* logp; const float* value;
+    const double* reward; const uint8_t* done;
+    float* t_obs; int32_t* t_model; uint8_t* t_mask; int32_t* t_action; float* t_logp; float* t_value; double* t_reward; uint8_t* t_done;
+};
+
+__global__ void ramp_trajectory_record_kernel(const TrajArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    if (a.phase == 0) {
+        for (int k = 0; k < 11; ++k) a.t_obs[(size_t)b * 11 + k] = a.obs[(size_t)b * 11 + k];
+        for (int k = 0; k < a.A; ++k) a.t_mask[(size_t)b * a.A + k] = a.mask[(size_t)b * a.A + k];
+        a.t_model[b] = a.model[b]; a.t_action[b] = a.action[b]; a.t_logp[b] = a.logp[b]; a.t_value[b] = a.value[b];
+    } else {
+        a.t_reward[b] = a.reward[b]; a.t_done[b] = a.done[b];
+    }
+}
+
 }  // namespace ramp
 
 using namespace ramp;
@@ -633,6 +653,14 @@ int ramp_policy_read(ramp_policy_t* p, ramp_engine_t* eng, float* logits_out, fl
     return RAMP_OK;
 }
 
+void* ramp_pinned_alloc(size_t bytes) {
+    void* ptr = nullptr;
+    if (cudaMallocHost(&ptr, bytes ? bytes : 1) != cudaSuccess) { perr(RAMP_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return ptr;
+}
+
+void ramp_pinned_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
 int ramp_policy_trajectory_begin(ramp_policy_t* p, ramp_engine_t* eng, int32_t horizon) {
     if (!p || !eng || horizon < 1) return perr(RAMP_ERR_BAD_ARG, "policy: bad trajectory horizon");
     ramp_env_buffers_t eb{};
@@ -668,17 +696,17 @@ int ramp_policy_trajectory_record(ramp_policy_t* p, ramp_engine_t* eng, int32_t 
         return perr(RAMP_ERR_BAD_ARG, "policy: the trajectory was set up for another environment, or ramp_policy_act was not called");
     cudaStream_t st = ramp_internal_stream(eng);
     const size_t B = (size_t)eb.n_episodes, o = (size_t)t * B;
-    if (phase == 0) {           // after ramp_policy_act, before the environment steps: what the policy saw and decided
-        PCUDA(cudaMemcpyAsync(p->t_obs + o * 11, eb.obs_dynamic, sizeof(float) * 11 * B, cudaMemcpyDeviceToDevice, st));
-        PCUDA(cudaMemcpyAsync(p->t_model + o, eb.queued_model, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
-        PCUDA(cudaMemcpyAsync(p->t_mask + o * p->traj_a, eb.action_mask, (size_t)p->traj_a * B, cudaMemcpyDeviceToDevice, st));
-        PCUDA(cudaMemcpyAsync(p->t_action + o, eb.actions, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
-        PCUDA(cudaMemcpyAsync(p->t_logp + o, p->d_logp, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
-        PCUDA(cudaMemcpyAsync(p->t_value + o, p->d_value, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
-    } else {                    // after the environment stepped: what came back
-        PCUDA(cudaMemcpyAsync(p->t_reward + o, eb.reward, sizeof(double) * B, cudaMemcpyDeviceToDevice, st));
-        PCUDA(cudaMemcpyAsync(p->t_done + o, eb.done, B, cudaMemcpyDeviceToDevice, st));
-    }
+    // phase 0: after ramp_policy_act, before the environment steps -- what the policy saw and decided;
+    // phase 1: after the environment stepped -- what came back
+    TrajArgs a{};
+    a.B = eb.n_episodes; a.A = p->traj_a; a.phase = phase;
+    a.obs = eb.obs_dynamic; a.model = eb.queued_model; a.mask = eb.action_mask; a.action = eb.actions; a.logp = p->d_logp; a.value = p->d_value;
+    a.reward = eb.reward; a.done = eb.done;
+    a.t_obs = p->t_obs + o * 11; a.t_model = p->t_model + o; a.t_mask = p->t_mask + o * p->traj_a; a.t_action = p->t_action + o;
+    a.t_logp = p->t_logp + o; a.t_value = p->t_value + o; a.t_reward = p->t_reward + o; a.t_done = p->t_done + o;
+    ramp_trajectory_record_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(a);
+    PCUDA(cudaGetLastError());
+    ramp_internal_count_launches(eng, 1);
     return RAMP_OK;
 }
 

@@ -53,6 +53,10 @@ def _bind(L):
     L.ramp_policy_act.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64]
     L.ramp_policy_read.restype = C.c_int
     L.ramp_policy_read.argtypes = [C.c_void_p, C.c_void_p] + [C.c_void_p] * 4
+    L.ramp_pinned_alloc.restype = C.c_void_p
+    L.ramp_pinned_alloc.argtypes = [C.c_size_t]
+    L.ramp_pinned_free.restype = None
+    L.ramp_pinned_free.argtypes = [C.c_void_p]
     L.ramp_policy_trajectory_begin.restype = C.c_int
     L.ramp_policy_trajectory_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.ramp_policy_trajectory_record.restype = C.c_int
@@ -158,6 +162,7 @@ class DeviceGNNPolicy:
 
     def close(self):
         if getattr(self, '_h', None):
+            self._free_trajectory_buffers()
             self._L.ramp_policy_destroy(self._h)
             self._h = None
 
@@ -211,12 +216,37 @@ class DeviceGNNPolicy:
         _engine._check(self._L.ramp_policy_read(self._h, env.eng._h, logits.ctypes.data, value.ctypes.data, logp.ctypes.data, actions.ctypes.data))
         return {'logits': logits, 'value': value, 'logp': logp, 'actions': actions}
 
+    def _trajectory_buffers(self, horizon, B, A):
+        """Page-locked host arrays the trajectory is read into (allocated once per shape, re-used by every collect())."""
+        key = (horizon, B, A)
+        if getattr(self, '_traj_key', None) != key:
+            self._free_trajectory_buffers()
+            spec = {'graph_features_dynamic': ((horizon, B, 11), C.c_float), 'model': ((horizon, B), C.c_int32),
+                    'action_mask': ((horizon, B, A), C.c_uint8), 'action': ((horizon, B), C.c_int32), 'logp': ((horizon, B), C.c_float),
+                    'value': ((horizon, B), C.c_float), 'reward': ((horizon, B), C.c_double), 'done': ((horizon, B), C.c_uint8)}
+            self._traj_ptrs, self._traj_buf = [], {}
+            for k, (shape, ct) in spec.items():
+                n = int(np.prod(shape))
+                ptr = self._L.ramp_pinned_alloc(n * C.sizeof(ct))
+                if not ptr:
+                    raise Exception(self._L.ramp_last_error().decode('utf-8', 'replace'))
+                self._traj_ptrs.append(ptr)
+                self._traj_buf[k] = np.ctypeslib.as_array((ct * n).from_address(ptr)).reshape(shape)
+            self._traj_key = key
+        return self._traj_buf
+
+    def _free_trajectory_buffers(self):
+        for ptr in getattr(self, '_traj_ptrs', []):
+            self._L.ramp_pinned_free(ptr)
+        self._traj_ptrs, self._traj_buf, self._traj_key = [], {}, None
+
     def collect(self, env, horizon: int, sample: bool = True, seed: int = 0, reset: bool = True):
         """One rollout segment entirely on the device: ``horizon`` decisions of this policy for every episode of a
         DeviceRampJobPartitioningEnvironment, recorded on the device, read back ONCE.  Returns arrays [horizon, B, ...]:
         what the policy saw (``model`` of the queued job, ``graph_features_dynamic``, ``action_mask``), what it did (``action``,
         ``logp``, ``value``) and what came back (``reward``, ``done`` after the step); ``live`` marks the decisions of episodes that
-        were not finished yet."""
+        were not finished yet.  The arrays are views of page-locked buffers owned by the policy: valid until the next ``collect()`` /
+        ``close()`` -- copy what must outlive that."""
         L, h = self._L, self._h
         if reset:
             env.reset()
@@ -227,13 +257,11 @@ class DeviceGNNPolicy:
             env.step_device()
             _engine._check(L.ramp_policy_trajectory_record(h, env.eng._h, t, 1))
         B, A = env.B, self.n_actions
-        out = {'graph_features_dynamic': np.zeros((horizon, B, 11), dtype=np.float32), 'model': np.zeros((horizon, B), dtype=np.int32),
-               'action_mask': np.zeros((horizon, B, A), dtype=np.uint8), 'action': np.zeros((horizon, B), dtype=np.int32),
-               'logp': np.zeros((horizon, B), dtype=np.float32), 'value': np.zeros((horizon, B), dtype=np.float32),
-               'reward': np.zeros((horizon, B), dtype=np.float64), 'done': np.zeros((horizon, B), dtype=np.uint8)}
-        _engine._check(L.ramp_policy_trajectory_read(h, env.eng._h, int(horizon), *[out[k].ctypes.data for k in (
+        buf = self._trajectory_buffers(horizon, B, A)
+        _engine._check(L.ramp_policy_trajectory_read(h, env.eng._h, int(horizon), *[buf[k].ctypes.data for k in (
             'graph_features_dynamic', 'model', 'action_mask', 'action', 'logp', 'value', 'reward', 'done')]))
         env.read()                                         # raises what a step would have raised (invalid action, simulation errors)
-        out['done'] = out['done'].astype(bool)
+        out = dict(buf)                                    # views of page-locked arrays: valid until the next collect()
+        out['done'] = buf['done'].astype(bool)
         out['live'] = np.concatenate([np.ones((1, B), dtype=bool), ~out['done'][:-1]], axis=0) & (out['model'] >= 0)
         return out

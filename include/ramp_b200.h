@@ -446,6 +446,9 @@ int ramp_policy_read(ramp_policy_t* p, ramp_engine_t* eng, float* logits_out, fl
  * reward and done flag that came back -- device-to-device copies on the engine's stream, no synchronisation;
  * ramp_policy_trajectory_read copies the first n_steps slots to HOST arrays (any may be NULL): ONE transfer per segment instead of
  * one per step.  (The static part of the observation is a function of `model`: ramp_policy_set_model.) */
+/* page-locked host memory for the read-back targets (any HOST pointer works; page-locked ones make the copies asynchronous DMA) */
+void* ramp_pinned_alloc(size_t bytes);
+void ramp_pinned_free(void* ptr);
 int ramp_policy_trajectory_begin(ramp_policy_t* p, ramp_engine_t* eng, int32_t horizon);
 int ramp_policy_trajectory_record(ramp_policy_t* p, ramp_engine_t* eng, int32_t t, int32_t phase);
 int ramp_policy_trajectory_read(ramp_policy_t* p, ramp_engine_t* eng, int32_t n_steps, float* obs_dynamic_out, int32_t* model_out,
