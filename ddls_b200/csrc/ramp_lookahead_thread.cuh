@@ -347,13 +347,18 @@ __device__ __forceinline__ LaneResult thread_lookahead(const LaneCtx& x) {
                 for (int k = 0; k < nNF; ++k) complete_dep(nfs.get(k));
                 to_complete -= nNF;
                 nNF = 0;
-            } else if (nF == 1) flow_tick(std::integral_constant<int, 1>{});
-            else if (nF == 0) take_tick(RAMP_INF_BITS, false);
-            else if (nF == 2) flow_tick(std::integral_constant<int, 2>{});
-            else if (nF == 3) flow_tick(std::integral_constant<int, 3>{});
-            else if (nF == 4) flow_tick(std::integral_constant<int, 4>{});
-            else if (nF == 5) flow_tick(std::integral_constant<int, 5>{});
-            else flow_tick(std::integral_constant<int, 6>{});
+            } else {
+                // a chain of compare-and-branch, most frequent count first; the empty asm keeps the compiler from folding the chain
+                // back into a jump table (constant-bank load + indirect branch on the critical path of every tick)
+                auto opaque = [](int v) { asm volatile("" : "+r"(v)); return v; };
+                if (opaque(nF) == 1) flow_tick(std::integral_constant<int, 1>{});
+                else if (opaque(nF) == 0) take_tick(RAMP_INF_BITS, false);
+                else if (opaque(nF) == 2) flow_tick(std::integral_constant<int, 2>{});
+                else if (opaque(nF) == 3) flow_tick(std::integral_constant<int, 3>{});
+                else if (opaque(nF) == 4) flow_tick(std::integral_constant<int, 4>{});
+                else if (opaque(nF) == 5) flow_tick(std::integral_constant<int, 5>{});
+                else flow_tick(std::integral_constant<int, 6>{});
+            }
             // ---- G ----
             int p = 0;
             auto tick_op = [&](int4 r, const int op, const bool win) {
