@@ -100,7 +100,13 @@ def workload_config(args, cfg, templates, world, B):
             'cluster': 'x'.join(map(str, cfg['shape'])) + ' RAMP', 'degrees': list(cfg['degrees']),
             'templates': [[t.n_ops, t.n_deps] for t in templates], 'run_times': args.run_times, 'memo_mode': args.memo_mode,
             'agent': 'scripted: partition degree drawn from `degrees` + first-fit blocks -- the same decision rule in both arms; the same '
-                     'rollouts driven by the GNN policy on the device are reported in batched_env.device_gnn_policy'}
+                     'rollouts driven by the GNN policy on the device are reported in batched_env.device_gnn_policy',
+            # identical text in both arms so that the two `config` objects compare equal
+            'l2': 'product arm: inputs larger than L2 are not needed -- the lookahead kernel keeps its working set (template blob + per-lane '
+                  'lists) in shared memory and streams its tick traces to HBM (trace_mb_per_step in the line); no explicit flush.  '
+                  'reference arm: CPU, not applicable',
+            'parallelism': (f'product arm: episodes sharded x{world}, one process per GPU, one NCCL all-gather of episode metrics per batch of '
+                            f'rollouts on a side stream (none at 1 GPU); reference arm: one single-threaded process per usable host core on rank 0')}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -666,11 +672,8 @@ def run_b200_arm(args, rank, world, local_rank):
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': elapsed_ms / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_config(args, cfg, wl.templates, world, B),
-                           l2='inputs larger than L2 are not needed: the lookahead kernel keeps its working set (template blob + per-lane '
-                              'lists) in shared memory; per step it writes %.1f MB of tick traces to HBM; no explicit flush' % _trace_mb(kt),
-                           parallelism=f'episodes sharded x{world}, one NCCL all-gather of episode metrics every {gather_every} steps (per batch of rollouts), on a side stream' if world > 1
-                                       else 'single GPU'),
+            'config': workload_config(args, cfg, wl.templates, world, B),
+            'trace_mb_per_step': _trace_mb(kt), 'gather_every_steps': gather_every if world > 1 else None,
             'e2e': e2e_line,
             'e2e_engine': e2e_engine,
             'gpu_launches': int(launches),
