@@ -204,6 +204,9 @@ CASES = {
     'mix128_exp': dict(graphs=[synth.resnet_like_graph(), synth.transformer_like_graph(n_layers=12, name='gpt2_small_like', seed=5, gpt=True)],
                        shape=(8, 4, 4), n_jobs=3, max_partitions=4, interarrival=('exponential', 500.0), frac=(0.2, 1.0), actor='random',
                        seed=32),
+    # BASELINE config 2's cluster and job: the ResNet-50-like graph at full size on the 32-worker 4x4x2 RAMP, random degrees up to 8
+    'resnet32_cfg2': dict(graphs=[synth.resnet_like_graph()], shape=(4, 4, 2), n_jobs=4, max_partitions=8, interarrival=900.0,
+                          frac=(0.2, 1.0), actor='random', seed=41),
     'residual32_deg16': dict(graphs=[synth.residual_small_graph()], shape=(4, 4, 2), n_jobs=3, max_partitions=16,
                              interarrival=1000.0, frac=(0.1, 1.0), actor='sipml', seed=1),
 }

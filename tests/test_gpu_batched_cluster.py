@@ -13,7 +13,7 @@ SHAPES = {8: (2, 2, 2), 16: (2, 2, 4), 32: (4, 4, 2), 64: (4, 4, 4), 128: (8, 4,
 BATCHES = [
     ['chain8', 'chain8_busy', 'residual8_deg4', 'chain8', 'chain8_busy'],
     ['mixed16', 'res16_flood', 'mixed16', 'res16_flood'],
-    ['tfm32_acceptable', 'residual32_deg16'],
+    ['tfm32_acceptable', 'residual32_deg16', 'resnet32_cfg2'],
     ['mixed64_busy', 'resnet64_deg2_full', 'resnet64_deg4_full', 'mixed64_busy'],
     ['mix128_exp', 'mix128_exp'],
 ]

@@ -26,6 +26,7 @@ def _graphs():
         'resnet64_deg16_full': [synth.resnet_like_graph()], 'resnet64_deg8_full': [synth.resnet_like_graph()],
         'resnet64_deg4_full': [synth.resnet_like_graph()], 'resnet64_deg2_full': [synth.resnet_like_graph()],
         # BASELINE configs 4 / 5: 256- and 128-worker clusters (occupancy bit sets of 4 and 2 words)
+        'resnet32_cfg2': [synth.resnet_like_graph()],
         'bert256_shard': [synth.transformer_like_graph(n_layers=12, name='bert_base_like', seed=2)],
         'mix128_exp': [synth.resnet_like_graph(), synth.transformer_like_graph(n_layers=12, name='gpt2_small_like', seed=5, gpt=True)],
     }
@@ -37,7 +38,7 @@ BATCHES = [
     ['chain8', 'chain8_busy', 'residual8_deg4', 'chain8', 'chain8_busy'],
     ['chain8_maxtime'],
     ['mixed16', 'res16_flood', 'mixed16'],
-    ['tfm32_acceptable', 'residual32_deg16'],
+    ['tfm32_acceptable', 'residual32_deg16', 'resnet32_cfg2'],
     ['mixed64_busy', 'resnet64_deg2_full', 'resnet64_deg4_full', 'resnet64_deg8_full', 'resnet64_deg16_full'],
     ['mix128_exp', 'mix128_exp'],
     ['bert256_shard'],

@@ -19,7 +19,8 @@ from golden_io import Golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = ['chain8', 'chain8_busy', 'chain8_maxtime', 'mixed16', 'res16_flood', 'residual8_deg4', 'tfm32_acceptable', 'mixed64_busy',
-         'mix128_exp']            # 128 workers, exponential arrivals (BASELINE config 5 in small)
+         'mix128_exp',            # 128 workers, exponential arrivals (BASELINE config 5 in small)
+         'resnet32_cfg2']         # BASELINE config 2's cluster and job (32 workers, ResNet-50-like), degrees 4 / 6 / 8
 
 
 def _reference_available():
